@@ -1,0 +1,97 @@
+/* mfmarl_batched.h -- batched, device-resident C ABI of the B200 battle engine (new; the reference has
+ * no batched interface -- SURVEY.md section 8b "Batched extension").
+ *
+ * One engine steps E independent environments in lockstep.  State lives in HBM for the life of the
+ * engine.  Observation / action / result buffers are caller-owned DEVICE memory (e.g.
+ * torch.Tensor.data_ptr()), passed as plain pointers with the shapes stated below; `stream` is a
+ * cudaStream_t passed as void* (NULL = default stream).  For E = 1 and rng_mode = MFB_RNG_MINSTD the
+ * results are bit-identical to the single-env ABI of mfmarl_magent.h and hence to the reference engine
+ * (GridWorld.cc:303-426,430-496,498-694,696-728,760-770).
+ *
+ * Every function returns 0 on success, -1 on error (message from mfb_last_error()); nothing aborts.
+ */
+#ifndef MFMARL_BATCHED_H
+#define MFMARL_BATCHED_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mfb_engine mfb_engine;
+
+enum { MFB_RNG_MINSTD = 0, MFB_RNG_PHILOX = 1, MFB_RNG_INJECT = 2 };
+
+typedef struct mfb_config {
+    int n_envs;            /* E: environments owned by this engine (this GPU's shard)               */
+    int map_width, map_height;
+    int capacity;          /* agent slots per group (rounded up to a multiple of 4)                 */
+    int embedding_size;    /* 10 for battle                                                          */
+    int rng_mode;          /* attack-order shuffle: MINSTD = reference parity, PHILOX = production   */
+    unsigned seed;
+    int env_base;          /* global id of env 0 (keys Philox, so results do not depend on sharding) */
+    int max_steps;         /* with auto_reset: episode horizon (0 = none)                            */
+    int auto_reset;        /* re-place the armies when an episode ends (done or horizon)             */
+    int device;            /* CUDA device ordinal, -1 = current                                      */
+    int step_threads;      /* 0 = auto                                                               */
+    int obs_tile_agents;   /* agents per observation CTA, 0 = 64                                     */
+    /* agent type (python/magent/builtin/config/battle.py:16-29) and the attack reward rules (:41-42) */
+    float hp, speed, view_radius, attack_radius, damage, step_recover, kill_supply;
+    float step_reward, kill_reward, dead_penalty, attack_penalty, attack_bonus[2];
+} mfb_config;
+
+int mfb_default_config(mfb_config *cfg);                 /* battle defaults, E = 1, 40x40, cap 64    */
+int mfb_create(const mfb_config *cfg, mfb_engine **out);
+int mfb_destroy(mfb_engine *eng);
+
+/* episode set-up: the same placement goes to every env (GridWorld::reset / add_agents "custom") */
+int mfb_reset(mfb_engine *eng);
+int mfb_add_walls(mfb_engine *eng, int n, const int *xs, const int *ys);             /* host arrays */
+int mfb_add_agents(mfb_engine *eng, int group, int n, const int *xs, const int *ys,  /* host arrays */
+                   int *n_added);
+int mfb_set_seed(mfb_engine *eng, unsigned long seed);
+
+/* sizes: key in {"capacity","n_envs","n_action","view_size","n_channel","feature_size","attack_base"} */
+int mfb_query(mfb_engine *eng, const char *key, int *out);
+
+/* K1.  d_view float[E][2][cap][13][13][7], d_feature float[E][2][cap][feature_size]; rows >= num are
+ * not written.  group_mask: 1 = group 0 only, 2 = group 1 only, 3 = both.                           */
+int mfb_observe(mfb_engine *eng, float *d_view, float *d_feature, int group_mask, void *stream);
+
+/* K2, fused set_action(g0), set_action(g1), step, get_reward, get_alive, mean action, clear_dead.
+ *   d_actions      int32[E][2][cap]       in
+ *   d_attack_perm  int32[E][2*cap]        in, only for MFB_RNG_INJECT (else NULL)
+ *   d_reward       float[E][2][cap]       out, indexed like the observation rows of this step
+ *   d_alive        uint8[E][2][cap]       out
+ *   d_mean_action  float[E][2][n_action]  out (senario_battle.py:141), may be NULL
+ *   d_done         int32[E]               out
+ * clear_dead: 1 = compact survivors in the same launch (the play loop's order), 0 = leave the dead
+ * in the lists (then call mfb_clear_dead).                                                          */
+int mfb_step(mfb_engine *eng, const int32_t *d_actions, const int32_t *d_attack_perm, float *d_reward,
+             uint8_t *d_alive, float *d_mean_action, int32_t *d_done, int clear_dead, void *stream);
+int mfb_clear_dead(mfb_engine *eng, void *stream);
+
+/* K5 standalone: out[r][b] = #{i < num[r] : actions[r][i] == b} / num[r]   (senario_battle.py:141,255) */
+int mfb_mean_action(const int32_t *d_actions /* [rows][cap] */, const int32_t *d_num /* [rows] */,
+                    float *d_out /* [rows][n_action] */, int rows, int cap, int n_action, void *stream);
+
+/* state read-back into HOST buffers (synchronises `stream`): key in
+ *   "num" int32[E][2], "dead_ct" int32[E][2], "pos" int32[E][2][cap][2], "hp" float[E][2][cap],
+ *   "id" int32[E][2][cap], "alive" uint8[E][2][cap], "last_action" int32[E][2][cap],
+ *   "step_ct" int32[E], "rng" uint32[E]                                                             */
+int mfb_get(mfb_engine *eng, const char *key, void *host_buf, void *stream);
+/* device pointer to the live int32[E][2] agent counts (for masking on the device) */
+int mfb_num_device_ptr(mfb_engine *eng, const int32_t **out);
+
+/* Host-buffer convenience used for the end-to-end measurement: pinned-host actions in, results out.
+ * Copies h_actions -> device, runs mfb_step (clear_dead = 1), copies the results back, synchronises. */
+int mfb_step_host(mfb_engine *eng, const int32_t *h_actions, float *h_reward, uint8_t *h_alive,
+                  float *h_mean_action, int32_t *h_done, void *stream);
+
+const char *mfb_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFMARL_BATCHED_H */

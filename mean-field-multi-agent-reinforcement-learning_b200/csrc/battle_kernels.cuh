@@ -1,0 +1,586 @@
+// Hand-written sm_100a kernels for the MAgent battle hot path.
+//
+//   k_obs   (K1)  GridWorld::get_observation + Map::extract_view   (GridWorld.cc:303-426, Map.cc:130-218)
+//   k_step  (K2)  set_action + step + get_reward/alive + mean action + clear_dead, one CTA per env
+//                 (GridWorld.cc:430-496, 498-694, 696-728, 744-770; Map.cc:220-369;
+//                  RewardEngine.cc:216-240,373-443; senario_battle.py:141)
+//   k_mean_action (K5) standalone group mean action (senario_battle.py:141,255)
+//   k_place       episode (re)initialisation from a placement template (GridWorld.cc:76-124,256-269)
+//
+// All arithmetic that reaches an output is ordered IEEE fp32 (compiled with -fmad=false, explicit
+// _rn intrinsics where the reference divides), so results are bit-identical to the C++ engine.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "battle_types.h"
+
+namespace mfmarl {
+
+// ----------------------------------------------------------------------------------------------
+// small helpers
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ int pos_x(int p) { return p & 0xFFFF; }
+__device__ __forceinline__ int pos_y(int p) { return (p >> 16) & 0xFFFF; }
+__device__ __forceinline__ int pack_pos(int x, int y) { return (x & 0xFFFF) | (y << 16); }
+__device__ __forceinline__ uint32_t st_dead(uint32_t s) { return s & 1u; }
+__device__ __forceinline__ uint32_t st_op(uint32_t s) { return (s >> 8) & 0xFFu; }
+__device__ __forceinline__ uint32_t st_act(uint32_t s) { return (s >> 16) & 0xFFu; }
+__device__ __forceinline__ uint32_t st_with_op(uint32_t s, uint32_t op) { return (s & ~0xFF00u) | (op << 8); }
+__device__ __forceinline__ uint32_t make_state(uint32_t dead, uint32_t op, uint32_t act) {
+    return dead | (op << 8) | (act << 16);
+}
+
+// Philox4x32-10 (Salmon et al. 2011), counter-based: the draw for (seed, env, step, i) needs no state.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0; key.y += W1;
+    }
+    return ctr;
+}
+
+// minstd_rand0: x <- 16807 x mod (2^31 - 1)   (libstdc++ std::default_random_engine, GridWorld.h:106)
+__device__ __forceinline__ uint32_t minstd_next(uint32_t s) {
+    return (uint32_t)(((uint64_t)s * 16807ull) % 2147483647ull);
+}
+
+// Block-wide exclusive scan of a predicate (ballot + popc inside each warp, per-warp totals through
+// shared memory).  Must be reached by every thread of the block.  s_warp needs 32 ints.
+__device__ __forceinline__ int block_scan_flag(bool flag, int *s_warp, int &total) {
+    const unsigned ballot = __ballot_sync(0xFFFFFFFFu, flag);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) s_warp[w] = __popc(ballot);
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    int before = 0, tot = 0;
+    for (int k = 0; k < nw; k++) {
+        const int c = s_warp[k];
+        before += (k < w) ? c : 0;
+        tot += c;
+    }
+    __syncthreads();
+    total = tot;
+    return before + __popc(ballot & ((1u << lane) - 1u));
+}
+
+// ----------------------------------------------------------------------------------------------
+// K2: fused step
+// ----------------------------------------------------------------------------------------------
+struct StepSmem {  // byte offsets into dynamic shared memory
+    int pos, hp, nr, state, id, lr, att, aux, mv, mvt, grid, misc, total;
+};
+__host__ __device__ inline StepSmem step_smem_layout(int W, int H, int cap) {
+    StepSmem L;
+    const int n = 2 * cap;
+    int o = 0;
+    L.pos = o;   o += 4 * n;
+    L.hp = o;    o += 4 * n;
+    L.nr = o;    o += 4 * n;
+    L.state = o; o += 4 * n;
+    L.id = o;    o += 4 * n;
+    L.lr = o;    o += 4 * n;
+    L.att = o;   o += 4 * n;   // shuffled attack list: slot | attack index << 16
+    L.aux = o;   o += 4 * n;   // shuffle scratch, then victim slot per attack (-1 = miss)
+    L.mv = o;    o += 4 * n;   // move list: slot | move index << 16
+    L.mvt = o;   o += 4 * n;   // target cell per move (-1 = outside the board)
+    L.misc = o;  o += 4 * 64;  // warp totals [32], counters
+    L.grid = o;  o += 2 * W * H;
+    L.total = (o + 15) & ~15;
+    return L;
+}
+
+enum { MISC_WARP = 0, MISC_N = 32, MISC_DEAD = 34, MISC_NA = 36, MISC_NM = 37, MISC_DONE = 38, MISC_RESET = 39 };
+
+__global__ void k_step(const __grid_constant__ BattleParams P, const BattleState S, const StepIO io) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const StepSmem L = step_smem_layout(P.W, P.H, P.cap);
+    int *s_pos = (int *)(smem_raw + L.pos);
+    float *s_hp = (float *)(smem_raw + L.hp);
+    float *s_nr = (float *)(smem_raw + L.nr);
+    uint32_t *s_state = (uint32_t *)(smem_raw + L.state);
+    int *s_id = (int *)(smem_raw + L.id);
+    float *s_lr = (float *)(smem_raw + L.lr);
+    uint32_t *s_att = (uint32_t *)(smem_raw + L.att);
+    int *s_aux = (int *)(smem_raw + L.aux);
+    uint32_t *s_mv = (uint32_t *)(smem_raw + L.mv);
+    int *s_mvt = (int *)(smem_raw + L.mvt);
+    int *s_misc = (int *)(smem_raw + L.misc);
+    uint16_t *s_grid = (uint16_t *)(smem_raw + L.grid);
+
+    const int e = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const int cap = P.cap, W = P.W, H = P.H, cells = W * H;
+    const int n_action = P.n_move + P.n_attack;
+    const size_t ebase = (size_t)e * 2 * cap;
+    const int phases = io.phases;
+    const int step_before = S.step_ct[e];   // read by all threads long before thread 0 rewrites it
+
+    // ---- load: agent records -> smem, occupancy grid from walls + alive agents ----
+    if (tid < 2) { s_misc[MISC_N + tid] = S.num[e * 2 + tid]; s_misc[MISC_DEAD + tid] = S.dead_ct[e * 2 + tid]; }
+    const uint8_t *walls = S.walls + (size_t)e * P.wall_stride;
+    for (int c = tid; c < cells; c += nt) s_grid[c] = walls[c];
+    __syncthreads();
+    const int n0 = s_misc[MISC_N], n1 = s_misc[MISC_N + 1];
+    for (int s = tid; s < 2 * cap; s += nt) {
+        const int g = s >= cap, i = s - g * cap;
+        if (i < (g ? n1 : n0)) {
+            const int p = S.pos[ebase + s];
+            uint32_t st = S.state[ebase + s];
+            if ((phases & PH_SETACT) && ((io.setact_mask >> g) & 1)) {
+                int a = io.actions[ebase + s];                    // Agent::set_action, GridWorld.cc:485
+                a = (a < 0 || a >= n_action) ? n_action : a;      // out-of-range: recorded, never executed
+                st = (st & 0xFF00FFFFu) | ((uint32_t)a << 16);
+            }
+            s_pos[s] = p; s_hp[s] = S.hp[ebase + s]; s_nr[s] = S.next_rew[ebase + s];
+            s_state[s] = st; s_id[s] = S.id[ebase + s]; s_lr[s] = S.last_rew[ebase + s];
+            if (!st_dead(st)) s_grid[pos_y(p) * W + pos_x(p)] = (uint16_t)(2 + s);
+        }
+    }
+    __syncthreads();
+
+    int done = 0;
+    if (phases & PH_STEP) {
+        // ---- attack / move lists in set_action call order (GridWorld.cc:481-495) ----
+        int nA = 0, nM = 0;
+        for (int gi = 0; gi < kGroups; gi++) {
+            const int g = io.group_seq[gi];
+            if (g < 0) continue;
+            const int ng = g ? n1 : n0;
+            for (int base = 0; base < ng; base += nt) {
+                const int i = base + tid, s = g * cap + i;
+                const bool valid = i < ng;
+                const int a = valid ? (int)st_act(s_state[s]) : n_action;
+                const bool is_mv = valid && a < P.n_move, is_at = valid && a >= P.n_move && a < n_action;
+                int tot;
+                int p = block_scan_flag(is_at, s_misc + MISC_WARP, tot);
+                if (is_at) s_att[nA + p] = (uint32_t)s | ((uint32_t)(a - P.n_move) << 16);
+                nA += tot;
+                p = block_scan_flag(is_mv, s_misc + MISC_WARP, tot);
+                if (is_mv) s_mv[nM + p] = (uint32_t)s | ((uint32_t)a << 16);
+                nM += tot;
+            }
+        }
+        __syncthreads();
+
+        // ---- shuffle attacks (GridWorld.cc:510-515): inside-out Fisher-Yates, draw i picks j in [0, i] ----
+        if (P.rng_mode == RNG_INJECT) {
+            const int32_t *perm = io.attack_perm + (size_t)e * 2 * cap;
+            for (int i = tid; i < nA; i += nt) s_aux[i] = (int)s_att[perm[i]];
+            __syncthreads();
+            for (int i = tid; i < nA; i += nt) s_att[i] = (uint32_t)s_aux[i];
+        } else {
+            if (P.rng_mode == RNG_PHILOX) {   // draws are independent of each other: all in parallel
+                for (int i = tid; i < nA; i += nt) {
+                    const uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)step_before, 0u, 0u),
+                                                  make_uint2(P.seed, (uint32_t)(P.env_base + e)));
+                    s_aux[i] = (int)(r.x % (uint32_t)(i + 1));
+                }
+                __syncthreads();
+            }
+            if (tid == 0) {
+                uint32_t rs = S.rng[e];
+                for (int i = 0; i < nA; i++) {
+                    int j;
+                    if (P.rng_mode == RNG_MINSTD) { rs = minstd_next(rs); j = (int)rs % (i + 1); }
+                    else j = s_aux[i];
+                    const uint32_t t = s_att[i]; s_att[i] = s_att[j]; s_att[j] = t;
+                }
+                S.rng[e] = rs;
+            }
+        }
+        __syncthreads();
+
+        // ---- victims (Map::get_attack_obj, Map.cc:220-263): positions are frozen during the attack
+        //      phase, so the only thing that can change before an attack's turn is the victim dying ----
+        for (int i = tid; i < nA; i += nt) {
+            const uint32_t ent = s_att[i];
+            const int k = ent & 0xFFFF, a = ent >> 16, p = s_pos[k];
+            const int tx = pos_x(p) + P.att_dx[a], ty = pos_y(p) + P.att_dy[a];
+            int v = -1;
+            if (tx >= 0 && tx < W && ty >= 0 && ty < H) {
+                const int code = s_grid[ty * W + tx];
+                if (code >= 2 && ((code - 2) >= cap) != (k >= cap)) v = code - 2;
+            }
+            s_aux[i] = v;
+        }
+        __syncthreads();
+
+        // ---- ordered attack resolve (GridWorld.cc:524-557 at one thread, Map::do_attack Map.cc:266-321) ----
+        if (tid == 0) {
+            for (int i = 0; i < nA; i++) {
+                const int k = s_att[i] & 0xFFFF;
+                if (st_dead(s_state[k])) continue;                         // attacker died earlier this step
+                const int v = s_aux[i];
+                if (v < 0 || st_dead(s_state[v])) {                         // blank / wall / team-mate / already dead
+                    s_nr[k] = s_nr[k] + P.attack_penalty;
+                    continue;
+                }
+                const float hp = s_hp[v] - P.damage;                        // Agent::be_attack, GridWorld.h:208-214
+                s_hp[v] = hp;
+                float reward = 0.0f;
+                if (hp < 0.0f) {
+                    s_state[v] |= 1u;
+                    s_nr[v] = P.dead_penalty;
+                    const int pv = s_pos[v];
+                    s_grid[pos_y(pv) * W + pos_x(pv)] = 0;                  // Map::remove_agent
+                    s_misc[MISC_DEAD + (v >= cap)]++;
+                    s_state[k] = st_with_op(s_state[k], OP_KILL);
+                    s_hp[k] = fminf(P.hp, s_hp[k] + P.kill_supply);         // Agent::add_hp
+                    reward = P.kill_reward;
+                } else {
+                    s_state[k] = st_with_op(s_state[k], OP_ATTACK);
+                }
+                s_nr[k] = s_nr[k] + (reward + P.attack_penalty);            // GridWorld.cc:556
+            }
+        }
+        __syncthreads();
+
+        // ---- starve / recover (GridWorld.cc:574-595, Agent::starve GridWorld.h:199-206) ----
+        for (int s = tid; s < 2 * cap; s += nt) {
+            const int g = s >= cap, i = s - g * cap;
+            if (i >= (g ? n1 : n0) || st_dead(s_state[s])) continue;
+            if (P.step_recover > 0.0f) {
+                s_hp[s] = fminf(P.hp, s_hp[s] + P.step_recover);
+            } else {
+                const float hp = s_hp[s] - (-P.step_recover);
+                s_hp[s] = hp;
+                if (hp < 0.0f) {
+                    s_state[s] |= 1u; s_nr[s] = P.dead_penalty;
+                    s_grid[pos_y(s_pos[s]) * W + pos_x(s_pos[s])] = 0;
+                    atomicAdd(&s_misc[MISC_DEAD + g], 1);
+                }
+            }
+        }
+        // ---- move targets (Map::do_move bounds test, Map.cc:326,466-468) ----
+        for (int m = tid; m < nM; m += nt) {
+            const uint32_t ent = s_mv[m];
+            const int k = ent & 0xFFFF, a = ent >> 16, p = s_pos[k];
+            const int nx = pos_x(p) + P.move_dx[a], ny = pos_y(p) + P.move_dy[a];
+            s_mvt[m] = (nx < 0 || ny < 0 || nx + 1 >= W || ny + 1 >= H) ? -1 : ny * W + nx;
+        }
+        __syncthreads();
+
+        // ---- ordered moves, first come first served (GridWorld.cc:631-672, Map.cc:324-369) ----
+        if (tid == 0) {
+            for (int m = 0; m < nM; m++) {
+                const int k = s_mv[m] & 0xFFFF;
+                if (st_dead(s_state[k])) continue;
+                const int tc = s_mvt[m];
+                if (tc < 0) continue;
+                const int occ = s_grid[tc], self = 2 + k;
+                if (occ == 0 || occ == self) {
+                    const int p = s_pos[k];
+                    s_grid[pos_y(p) * W + pos_x(p)] = 0;
+                    s_grid[tc] = (uint16_t)self;
+                    const int ny = tc / W;
+                    s_pos[k] = pack_pos(tc - ny * W, ny);
+                } else if (occ >= 2) {
+                    s_state[k] = st_with_op(s_state[k], OP_COLLIDE);        // no reward effect in the battle rules
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- reward rules (calc_reward GridWorld.cc:744-758): for the battle rule set an agent whose
+        //      last_op is OP_ATTACK necessarily hit the other group; dead agents included ----
+        for (int s = tid; s < 2 * cap; s += nt) {
+            const int g = s >= cap, i = s - g * cap;
+            if (i < (g ? n1 : n0) && st_op(s_state[s]) == OP_ATTACK) s_nr[s] = s_nr[s] + P.attack_bonus[g];
+        }
+        // ---- done (GridWorld.cc:680-686) ----
+        done = (n0 - s_misc[MISC_DEAD] <= 0) || (n1 - s_misc[MISC_DEAD + 1] <= 0);
+        __syncthreads();
+        if (tid == 0) {
+            if (io.done) io.done[e] = done;
+            S.step_ct[e] = step_before + 1;
+        }
+    }
+
+    // ---- export: get_reward (+ group reward, always 0), alive, mean action of this step ----
+    if (phases & PH_EXPORT) {
+        for (int s = tid; s < 2 * cap; s += nt) {
+            const int g = s >= cap, i = s - g * cap;
+            if (i < (g ? n1 : n0)) {
+                if (io.reward) io.reward[ebase + s] = s_nr[s] + 0.0f;
+                if (io.alive) io.alive[ebase + s] = (uint8_t)!st_dead(s_state[s]);
+            }
+        }
+        if (io.mean_action) {
+            // 21-bin one-hot mean with ballots: warp g counts group g, lane b owns bin b
+            const int w = tid >> 5, lane = tid & 31;
+            for (int g = w; g < kGroups; g += (nt >> 5)) {
+                const int ng = g ? n1 : n0;
+                int cnt = 0;
+                for (int base = 0; base < ng; base += 32) {
+                    const int i = base + lane;
+                    const int a = i < ng ? (int)st_act(s_state[g * cap + i]) : -1;
+                    for (int b = 0; b < n_action; b++) {
+                        const int c = __popc(__ballot_sync(0xFFFFFFFFu, a == b));
+                        if (lane == b) cnt += c;
+                    }
+                }
+                if (lane < n_action)
+                    io.mean_action[((size_t)e * 2 + g) * n_action + lane] =
+                        ng > 0 ? __fdiv_rn((float)cnt, (float)ng) : 0.0f;
+            }
+        }
+    }
+
+    // ---- write back; clear_dead = stable compaction of the survivors (GridWorld.cc:696-728) ----
+    const bool horizon = (phases & PH_STEP) && P.max_steps > 0 && step_before + 1 >= P.max_steps;
+    if ((phases & PH_AUTORESET) && (done || horizon)) {
+        __syncthreads();
+        for (int s = tid; s < 2 * cap; s += nt) {
+            const int g = s >= cap, i = s - g * cap;
+            if (i < S.init_num[g]) {
+                S.pos[ebase + s] = S.init_pos[s];
+                S.hp[ebase + s] = P.hp;
+                S.id[ebase + s] = S.init_pos[2 * cap + s];
+                S.state[ebase + s] = make_state(0, OP_NULL, (uint32_t)n_action);
+                S.next_rew[ebase + s] = P.step_reward;
+                S.last_rew[ebase + s] = 0.0f;
+            }
+        }
+        if (tid < 2) { S.num[e * 2 + tid] = S.init_num[tid]; S.dead_ct[e * 2 + tid] = 0; }
+        if (tid == 0) { S.step_ct[e] = 0; S.id_counter[e] = S.init_num[0] + S.init_num[1]; }
+    } else if (phases & PH_CLEAR) {
+        for (int g = 0; g < kGroups; g++) {
+            const int ng = g ? n1 : n0;
+            int kept = 0;
+            for (int base = 0; base < ng; base += nt) {
+                const int i = base + tid, s = g * cap + i;
+                const bool keep = i < ng && !st_dead(s_state[s]);
+                int tot;
+                const int p = block_scan_flag(keep, s_misc + MISC_WARP, tot);
+                if (keep) {
+                    const size_t d = ebase + (size_t)g * cap + kept + p;
+                    S.pos[d] = s_pos[s]; S.hp[d] = s_hp[s]; S.id[d] = s_id[s];
+                    S.state[d] = make_state(0, OP_NULL, st_act(s_state[s]));   // Agent::init_reward
+                    S.last_rew[d] = s_nr[s];
+                    S.next_rew[d] = P.step_reward;
+                }
+                kept += tot;
+            }
+            if (tid == 0) { S.num[e * 2 + g] = kept; S.dead_ct[e * 2 + g] = 0; }
+        }
+    } else if (phases & (PH_STEP | PH_SETACT)) {
+        for (int s = tid; s < 2 * cap; s += nt) {
+            const int g = s >= cap, i = s - g * cap;
+            if (i < (g ? n1 : n0)) {
+                S.pos[ebase + s] = s_pos[s]; S.hp[ebase + s] = s_hp[s];
+                S.state[ebase + s] = s_state[s]; S.next_rew[ebase + s] = s_nr[s];
+            }
+        }
+        if (tid < 2) S.dead_ct[e * 2 + tid] = s_misc[MISC_DEAD + tid];
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// K1: observations.  One CTA per (env, group, tile of agents).
+//
+// The per-agent view is 13*13*7 fp32 = 4732 B, >90 % zeros, and it is the whole of the HBM traffic
+// of the path.  Each warp composes one agent's 4732 B row in shared memory (7 conflict-free STS per
+// view cell: stride 7 words is coprime with the 32 banks), rows are packed back to back in a staging
+// buffer, and one elected thread hands each 8-agent chunk (37 856 B) to the TMA engine with a single
+// cp.async.bulk shared->global store; two staging buffers keep a store in flight while the next
+// chunk is composed.  The map is never re-read from HBM: the occupancy/hp grid and both minimaps are
+// rebuilt per CTA in shared memory from the SoA agent arrays.
+// ----------------------------------------------------------------------------------------------
+constexpr int kObsThreads = 256, kObsWarps = kObsThreads / 32;
+constexpr int kObsChunk = 8;                                   // agents per bulk store (multiple of 4)
+constexpr int kObsStageBytes = kObsChunk * kViewRow * 4;       // 37 856, a multiple of 16
+
+struct ObsSmem { int stage0, stage1, hp10, mini, cnt, kind, total; };
+__host__ __device__ inline ObsSmem obs_smem_layout(int W, int H) {
+    ObsSmem L; int o = 0;
+    L.stage0 = o; o += kObsStageBytes;
+    L.stage1 = o; o += kObsStageBytes;
+    L.hp10 = o;   o += 4 * W * H;
+    L.mini = o;   o += 4 * 2 * kViewCells;
+    L.cnt = o;    o += 4 * 2 * kViewCells;
+    L.kind = o;   o += W * H;
+    L.total = (o + 127) & ~127;
+    return L;
+}
+
+__device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *ssrc, uint32_t bytes) {
+    const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"(saddr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory");
+}
+template <int N> __device__ __forceinline__ void bulk_wait() {
+    asm volatile("cp.async.bulk.wait_group %0;" :: "n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kObsThreads, 2)
+k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO io) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const ObsSmem L = obs_smem_layout(P.W, P.H);
+    float *s_stage[2] = {(float *)(smem_raw + L.stage0), (float *)(smem_raw + L.stage1)};
+    float *s_hp10 = (float *)(smem_raw + L.hp10);
+    float *s_mini = (float *)(smem_raw + L.mini);
+    int *s_cnt = (int *)(smem_raw + L.cnt);
+    uint8_t *s_kind = smem_raw + L.kind;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int W = P.W, H = P.H, cap = P.cap, cells = W * H;
+
+    // tile -> (env, group, first agent)
+    int t = blockIdx.x;
+    const int tile = t % io.tiles_per_group; t /= io.tiles_per_group;
+    int g, e;
+    if (io.group_mask == 3) { g = t & 1; e = t >> 1; } else { g = io.group_mask >> 1; e = t; }
+    const int n0 = S.num[e * 2], n1 = S.num[e * 2 + 1];
+    const int ng = g ? n1 : n0;
+    const int a_begin = tile * io.tile_agents;
+    if (a_begin >= ng) return;
+    const int a_end = min(ng, a_begin + io.tile_agents);
+    const size_t ebase = (size_t)e * 2 * cap;
+
+    // ---- occupancy (kind: 0 empty, 1 wall, 2 group0, 3 group1), hp/10 per cell, minimap counts ----
+    const uint8_t *walls = S.walls + (size_t)e * P.wall_stride;
+    for (int c = tid; c < cells; c += kObsThreads) s_kind[c] = walls[c];
+    for (int c = tid; c < 2 * kViewCells; c += kObsThreads) s_cnt[c] = 0;
+    __syncthreads();
+    for (int s = tid; s < 2 * cap; s += kObsThreads) {
+        const int gg = s >= cap, i = s - gg * cap;
+        if (i < (gg ? n1 : n0)) {
+            const int p = S.pos[ebase + s], x = pos_x(p), y = pos_y(p);
+            // minimap counts every agent still in the list, dead or not (GridWorld.cc:359-370)
+            atomicAdd(&s_cnt[gg * kViewCells + (y / P.scale_h) * kView + x / P.scale_w], 1);
+            if (!st_dead(S.state[ebase + s])) {
+                s_kind[y * W + x] = (uint8_t)(2 + gg);
+                s_hp10[y * W + x] = __fdiv_rn(S.hp[ebase + s], P.hp);   // Map.cc:208
+            }
+        }
+    }
+    __syncthreads();
+    for (int c = tid; c < 2 * kViewCells; c += kObsThreads) {
+        const int gg = c >= kViewCells;
+        s_mini[c] = __fdiv_rn((float)s_cnt[c], (float)(gg ? n1 : n0));  // GridWorld.cc:372-377
+    }
+
+    // ---- features (GridWorld.cc:411-421): coalesced over the tile's flat [agents * feature_size] block ----
+    {
+        const int FS = P.feature_size, emb = P.embedding_size, n_action = P.n_move + P.n_attack;
+        float *fout = io.feature + (ebase + (size_t)g * cap + a_begin) * FS;
+        const int nf = (a_end - a_begin) * FS;
+        for (int f = tid; f < nf; f += kObsThreads) {
+            const int al = f / FS, k = f - al * FS;
+            const size_t s = ebase + (size_t)g * cap + a_begin + al;
+            float v;
+            if (k < emb) v = (float)((S.id[s] >> k) & 1);                       // GridWorld.h:162-171
+            else if (k < emb + n_action) v = ((int)st_act(S.state[s]) == k - emb) ? 1.0f : 0.0f;
+            else if (k == emb + n_action) v = S.last_rew[s];
+            else if (k == emb + n_action + 1) v = __fdiv_rn((float)pos_x(S.pos[s]), (float)W);
+            else v = __fdiv_rn((float)pos_y(S.pos[s]), (float)H);
+            fout[f] = v;
+        }
+    }
+    __syncthreads();
+
+    // ---- views: compose in smem, stream out with TMA bulk stores ----
+    const float *mini_own = s_mini + g * kViewCells, *mini_oth = s_mini + (1 - g) * kViewCells;
+    const uint8_t own_kind = (uint8_t)(2 + g), oth_kind = (uint8_t)(3 - g);
+    float *vout = io.view + (ebase + (size_t)g * cap) * kViewRow;
+    int buf = 0;
+    for (int c0 = a_begin; c0 < a_end; c0 += kObsChunk, buf ^= 1) {
+        const int cn = min(kObsChunk, a_end - c0);
+        // the store issued two chunks ago read this buffer: wait until its smem reads are done
+        if (tid == 0) bulk_wait_read<1>();
+        __syncthreads();
+        if (warp < cn) {
+            const size_t s = ebase + (size_t)g * cap + c0 + warp;
+            const int p = S.pos[s], ax = pos_x(p), ay = pos_y(p);
+            const int self_cell = (ay / P.scale_h) * kView + ax / P.scale_w;
+            float *row = s_stage[buf] + warp * kViewRow;
+#pragma unroll
+            for (int it = 0; it < (kViewCells + 31) / 32; it++) {
+                const int c = it * 32 + lane;
+                if (c < kViewCells) {
+                    const int vy = c / kView, vx = c - vy * kView;
+                    const int x = ax - kView / 2 + vx, y = ay - kView / 2 + vy;
+                    const bool in = ((P.disc[c >> 5] >> (c & 31)) & 1u) && x >= 0 && x < W && y >= 0 && y < H;
+                    const int cell = in ? y * W + x : 0;
+                    const uint8_t kind = in ? s_kind[cell] : (uint8_t)0;
+                    const float hp = s_hp10[cell];
+                    const bool own = kind == own_kind, oth = kind == oth_kind;
+                    float *o = row + c * kChan;
+                    o[0] = kind == 1 ? 1.0f : 0.0f;
+                    o[1] = own ? 1.0f : 0.0f;
+                    o[2] = own ? hp : 0.0f;
+                    o[3] = c == self_cell ? mini_own[c] + 1.0f : mini_own[c];   // GridWorld.cc:404-407
+                    o[4] = oth ? 1.0f : 0.0f;
+                    o[5] = oth ? hp : 0.0f;
+                    o[6] = c == self_cell ? mini_oth[c] + 1.0f : mini_oth[c];
+                }
+            }
+        }
+        fence_proxy_async_smem();   // make the generic-proxy smem writes visible to the async proxy
+        __syncthreads();
+        if (tid == 0) {
+            // rows are 4732 B (= 12 mod 16): a ragged tail is rounded up to 16 B; the <= 12 spill bytes land
+            // in the next, unused row of the same [cap] block (cap is a multiple of 4, see engine.cu)
+            const uint32_t bytes = ((uint32_t)cn * kViewRow * 4 + 15u) & ~15u;
+            bulk_store_s2g(vout + (size_t)c0 * kViewRow, s_stage[buf], bytes);
+            bulk_commit();
+        }
+    }
+    if (tid == 0) bulk_wait<0>();
+}
+
+// ----------------------------------------------------------------------------------------------
+// K5: group mean action, standalone (senario_battle.py:141,255): out[e][g][b] = #{i : act_i = b} / n
+// One warp per (env, group); 21 ballots per 32 agents, lane b owns bin b.
+// ----------------------------------------------------------------------------------------------
+__global__ void k_mean_action(const int32_t *__restrict__ actions, const int32_t *__restrict__ num,
+                              float *__restrict__ out, int n_rows, int cap, int n_action) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= n_rows) return;
+    const int n = num[row];
+    const int32_t *a = actions + (size_t)row * cap;
+    int cnt = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        const int v = i < n ? a[i] : -1;
+        for (int b = 0; b < n_action; b++) {
+            const int c = __popc(__ballot_sync(0xFFFFFFFFu, v == b));
+            if (lane == b) cnt += c;
+        }
+    }
+    if (lane < n_action) out[(size_t)row * n_action + lane] = n > 0 ? __fdiv_rn((float)cnt, (float)n) : 0.0f;
+}
+
+// ----------------------------------------------------------------------------------------------
+// episode (re)initialisation: every env gets the placement template
+// ----------------------------------------------------------------------------------------------
+__global__ void k_place(const __grid_constant__ BattleParams P, const BattleState S) {
+    const int e = blockIdx.x, cap = P.cap;
+    const size_t ebase = (size_t)e * 2 * cap;
+    const int n_action = P.n_move + P.n_attack;
+    for (int s = threadIdx.x; s < 2 * cap; s += blockDim.x) {
+        const int g = s >= cap, i = s - g * cap;
+        const bool live = i < S.init_num[g];
+        S.pos[ebase + s] = live ? S.init_pos[s] : 0;
+        S.hp[ebase + s] = P.hp;
+        S.id[ebase + s] = live ? S.init_pos[2 * cap + s] : 0;
+        S.state[ebase + s] = make_state(0, OP_NULL, (uint32_t)n_action);   // GridWorld.h:145
+        S.next_rew[ebase + s] = P.step_reward;                             // Agent::init_reward
+        S.last_rew[ebase + s] = 0.0f;
+    }
+    if (threadIdx.x < 2) { S.num[e * 2 + threadIdx.x] = S.init_num[threadIdx.x]; S.dead_ct[e * 2 + threadIdx.x] = 0; }
+    if (threadIdx.x == 0) { S.step_ct[e] = 0; S.id_counter[e] = S.init_num[0] + S.init_num[1]; }
+}
+
+}  // namespace mfmarl

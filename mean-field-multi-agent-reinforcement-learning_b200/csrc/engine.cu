@@ -1,0 +1,369 @@
+// Host engine: HBM state, placement, kernel launches.  See engine.h.
+#include "engine.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "battle_kernels.cuh"
+
+namespace mfmarl {
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+void set_last_error(const std::string &msg) { g_last_error = msg; }
+const char *last_error() { return g_last_error.c_str(); }
+
+int report_fatal(const char *where, const std::exception &ex) {
+    set_last_error(std::string(where) + ": " + ex.what());
+    fprintf(stderr, "[magent/b200] fatal in %s: %s\n", where, ex.what());
+    const char *mode = getenv("MAGENT_ERRORS");
+    if (mode && strcmp(mode, "return") == 0) return -1;
+    // the reference throws std::runtime_error through the C boundary (utility.h:77-81), which
+    // terminates a ctypes caller; do the same, loudly
+    abort();
+}
+
+// ---------------------------------------------------------------------------------------------
+// range tables: a disc of the given radius on a square of odd/even width (reference Range.h:171-215)
+// ---------------------------------------------------------------------------------------------
+CircleRange::CircleRange(float radius, float inner_radius, int parity) {
+    const double eps = 1e-8;
+    width = 2 * (int)(radius + eps) + parity;
+    center = (int)radius;
+    if (width % 2 != parity) width++;
+    in.assign((size_t)width * width, 0);
+    const double delta = parity == 0 ? 0.5 : 0.0;
+    for (int i = 0; i < width; i++)
+        for (int j = 0; j < width; j++) {
+            const double ax = std::fabs(j - center + delta), ay = std::fabs(i - center + delta);
+            const double dis = std::sqrt(ax * ax + ay * ay);
+            if (dis < radius + eps && dis > inner_radius - eps) {
+                in[(size_t)i * width + j] = 1;
+                dx.push_back(j - center);
+                dy.push_back(i - center);
+                count++;
+            }
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
+// construction
+// ---------------------------------------------------------------------------------------------
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+Engine::Engine(const EngineConfig &cfg) : cfg_(cfg) {
+    int ndev = 0;
+    cudaError_t err = cudaGetDeviceCount(&ndev);
+    if (err != cudaSuccess || ndev == 0)
+        throw Fatal(std::string("no CUDA device: the battle engine has no CPU fallback (") +
+                    cudaGetErrorString(err) + ")");
+    if (cfg.device >= 0) MF_CUDA(cudaSetDevice(cfg.device));
+    MF_CUDA(cudaGetDevice(&device_));
+    MF_CUDA(cudaDeviceGetAttribute(&n_sm_, cudaDevAttrMultiProcessorCount, device_));
+
+    if (cfg.n_envs < 1 || cfg.width < 3 || cfg.height < 3 || cfg.width > 4096 || cfg.height > 4096)
+        throw Fatal("invalid engine config (n_envs / map size)");
+
+    view_ = CircleRange(cfg.type.view_radius, 0.0f, 1);
+    attack_ = CircleRange(cfg.type.attack_radius, 0.5f, 1);   // inner radius = width / 2.0f (AgentType.cc:107)
+    move_ = CircleRange(cfg.type.speed, 0.0f, 1);
+    if (view_.width != kView)
+        throw Fatal("view range " + std::to_string(view_.width) + "x" + std::to_string(view_.width) +
+                    " unsupported: the observation kernel is specialised for the 13x13 battle view");
+    if (move_.count > kMaxMoves || attack_.count > kMaxAttacks)
+        throw Fatal("move/attack range too large");
+
+    P_.E = cfg.n_envs; P_.W = cfg.width; P_.H = cfg.height;
+    P_.env_base = cfg.env_base;
+    P_.embedding_size = cfg.embedding_size;
+    P_.n_move = move_.count; P_.n_attack = attack_.count;
+    P_.view = kView;
+    P_.feature_size = cfg.embedding_size + P_.n_move + P_.n_attack + 1 + 2;   // GridWorld.cc:1010-1018
+    P_.scale_w = (cfg.width + kView - 1) / kView;                             // GridWorld.cc:341-342
+    P_.scale_h = (cfg.height + kView - 1) / kView;
+    P_.wall_stride = 0;
+    P_.rng_mode = cfg.rng_mode; P_.max_steps = cfg.max_steps; P_.seed = cfg.seed;
+    P_.hp = cfg.type.hp; P_.damage = cfg.type.damage; P_.step_recover = cfg.type.step_recover;
+    P_.kill_supply = cfg.type.kill_supply; P_.step_reward = cfg.type.step_reward;
+    P_.kill_reward = cfg.type.kill_reward; P_.dead_penalty = cfg.type.dead_penalty;
+    P_.attack_penalty = cfg.type.attack_penalty;
+    for (int g = 0; g < kGroups; g++) P_.attack_bonus[g] = cfg.attack_bonus[g];
+    for (int i = 0; i < move_.count; i++) { P_.move_dx[i] = (int8_t)move_.dx[i]; P_.move_dy[i] = (int8_t)move_.dy[i]; }
+    for (int i = 0; i < attack_.count; i++) { P_.att_dx[i] = (int8_t)attack_.dx[i]; P_.att_dy[i] = (int8_t)attack_.dy[i]; }
+    memset(P_.disc, 0, sizeof(P_.disc));
+    for (int c = 0; c < kViewCells; c++)
+        if (view_.in[c]) P_.disc[c >> 5] |= 1u << (c & 31);
+
+    // cap-independent per-env arrays
+    const size_t E = (size_t)P_.E;
+    MF_CUDA(cudaMalloc(&S_.num, E * 2 * sizeof(int32_t)));
+    MF_CUDA(cudaMalloc(&S_.dead_ct, E * 2 * sizeof(int32_t)));
+    MF_CUDA(cudaMalloc(&S_.rng, E * sizeof(uint32_t)));
+    MF_CUDA(cudaMalloc(&S_.step_ct, E * sizeof(int32_t)));
+    MF_CUDA(cudaMalloc(&S_.id_counter, E * sizeof(int32_t)));
+    MF_CUDA(cudaMalloc(&S_.walls, (size_t)P_.W * P_.H));
+    MF_CUDA(cudaMalloc(&S_.init_num, 2 * sizeof(int32_t)));
+    MF_CUDA(cudaMemset(S_.num, 0, E * 2 * sizeof(int32_t)));
+    MF_CUDA(cudaMemset(S_.dead_ct, 0, E * 2 * sizeof(int32_t)));
+    MF_CUDA(cudaMemset(S_.step_ct, 0, E * sizeof(int32_t)));
+    MF_CUDA(cudaMemset(S_.id_counter, 0, E * sizeof(int32_t)));
+    h_num_.assign(E * 2, 0);
+    set_seed(cfg.seed);   // seed 0 -> minstd state 1, as GridWorld.cc:31 random_engine.seed(0)
+    alloc_state(std::max(4, round_up(cfg.capacity, 4)));
+    reset();
+}
+
+Engine::~Engine() {
+    free_state();
+    cudaFree(S_.num); cudaFree(S_.dead_ct); cudaFree(S_.rng); cudaFree(S_.step_ct);
+    cudaFree(S_.id_counter); cudaFree(S_.walls); cudaFree(S_.init_num);
+}
+
+void Engine::alloc_state(int cap) {
+    if (2 * cap + 2 > 65535) throw Fatal("capacity too large for the 16-bit occupancy grid");
+    P_.cap = cap;
+    const size_t n = slots();
+    MF_CUDA(cudaMalloc(&S_.pos, n * 4)); MF_CUDA(cudaMalloc(&S_.hp, n * 4));
+    MF_CUDA(cudaMalloc(&S_.id, n * 4)); MF_CUDA(cudaMalloc(&S_.state, n * 4));
+    MF_CUDA(cudaMalloc(&S_.next_rew, n * 4)); MF_CUDA(cudaMalloc(&S_.last_rew, n * 4));
+    MF_CUDA(cudaMalloc(&S_.init_pos, (size_t)4 * cap * 4));
+    MF_CUDA(cudaMemset(S_.pos, 0, n * 4)); MF_CUDA(cudaMemset(S_.hp, 0, n * 4));
+    MF_CUDA(cudaMemset(S_.id, 0, n * 4)); MF_CUDA(cudaMemset(S_.state, 0, n * 4));
+    MF_CUDA(cudaMemset(S_.next_rew, 0, n * 4)); MF_CUDA(cudaMemset(S_.last_rew, 0, n * 4));
+}
+
+void Engine::free_state() {
+    cudaFree(S_.pos); cudaFree(S_.hp); cudaFree(S_.id); cudaFree(S_.state);
+    cudaFree(S_.next_rew); cudaFree(S_.last_rew); cudaFree(S_.init_pos);
+    S_.pos = nullptr; S_.hp = nullptr; S_.id = nullptr; S_.state = nullptr;
+    S_.next_rew = S_.last_rew = nullptr; S_.init_pos = nullptr;
+}
+
+void Engine::set_seed(unsigned long seed) {
+    // libstdc++ linear_congruential_engine<.., 16807, 0, 2147483647>::seed: s mod m, 0 -> 1
+    unsigned long s = seed % 2147483647ul;
+    std::vector<uint32_t> h((size_t)P_.E, (uint32_t)(s == 0 ? 1 : s));
+    MF_CUDA(cudaMemcpy(S_.rng, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+    P_.seed = (uint32_t)seed;
+}
+
+// ---------------------------------------------------------------------------------------------
+// placement (host)
+// ---------------------------------------------------------------------------------------------
+void Engine::reset() {   // GridWorld::reset (GridWorld.cc:76-124) + Map::reset (Map.cc:23-47); RNG untouched
+    const int W = P_.W, H = P_.H;
+    h_walls_.assign((size_t)W * H, 0);
+    for (int i = 0; i < W; i++) { h_walls_[i] = 1; h_walls_[(size_t)(H - 1) * W + i] = 1; }
+    for (int i = 0; i < H; i++) { h_walls_[(size_t)i * W] = 1; h_walls_[(size_t)i * W + W - 1] = 1; }
+    h_occ_.assign(h_walls_.begin(), h_walls_.end());
+    for (int g = 0; g < kGroups; g++) { h_tpos_[g].clear(); h_tid_[g].clear(); }
+    h_id_counter_ = 0;
+    placement_dirty_ = true;
+    stepped_ = false;
+    std::fill(h_num_.begin(), h_num_.end(), 0);
+}
+
+int Engine::add_walls(int n, const int *xs, const int *ys) {   // GridWorld.cc:203-211, Map::add_wall Map.cc:108-115
+    if (stepped_) throw Fatal("add_walls after stepping is not supported (call reset first)");
+    int added = 0;
+    for (int i = 0; i < n; i++) {
+        const int x = xs[i], y = ys[i];
+        if (x < 0 || y < 0 || x >= P_.W || y >= P_.H) continue;
+        const size_t c = (size_t)y * P_.W + x;
+        if (h_occ_[c] == 2) continue;   // an agent stands there: ignored
+        h_walls_[c] = 1; h_occ_[c] = 1; added++;
+    }
+    placement_dirty_ = true;
+    return added;
+}
+
+int Engine::add_agents(int group, int n, const int *xs, const int *ys) {
+    if (group < 0 || group >= kGroups) throw Fatal("invalid group handle in add_agents");
+    if (stepped_) {
+        if (P_.E != 1) throw Fatal("add_agents after stepping is only supported for a single env");
+        late_add_sync_down();
+    }
+    int added = 0;
+    for (int i = 0; i < n; i++) {   // GridWorld.cc:256-269; Map::add_agent Map.cc:75-97; add_or_error :180-187
+        const int x = xs[i], y = ys[i];
+        if (x < 0 || y < 0 || x + 1 >= P_.W || y + 1 >= P_.H) continue;   // is_blank_area bounds
+        const size_t c = (size_t)y * P_.W + x;
+        if (h_occ_[c] != 0) continue;                                      // occupied: ignored
+        h_occ_[c] = 2;
+        h_tpos_[group].push_back(x | (y << 16));
+        h_tid_[group].push_back(h_id_counter_++);
+        added++;
+    }
+    if (stepped_) late_add_sync_up(); else placement_dirty_ = true;
+    return added;
+}
+
+// E == 1, device state is newer than the template: pull the full records, patch, push back.
+struct LateRecords {
+    std::vector<int32_t> pos, id; std::vector<float> hp, nr, lr; std::vector<uint32_t> state;
+    int num[2], dead[2];
+};
+static LateRecords g_late;   // only touched between sync_down and sync_up of one add_agents call
+
+void Engine::late_add_sync_down() {
+    MF_CUDA(cudaDeviceSynchronize());
+    const size_t n = slots();
+    LateRecords &R = g_late;
+    R.pos.resize(n); R.id.resize(n); R.hp.resize(n); R.nr.resize(n); R.lr.resize(n); R.state.resize(n);
+    MF_CUDA(cudaMemcpy(R.pos.data(), S_.pos, n * 4, cudaMemcpyDeviceToHost));
+    MF_CUDA(cudaMemcpy(R.id.data(), S_.id, n * 4, cudaMemcpyDeviceToHost));
+    MF_CUDA(cudaMemcpy(R.hp.data(), S_.hp, n * 4, cudaMemcpyDeviceToHost));
+    MF_CUDA(cudaMemcpy(R.nr.data(), S_.next_rew, n * 4, cudaMemcpyDeviceToHost));
+    MF_CUDA(cudaMemcpy(R.lr.data(), S_.last_rew, n * 4, cudaMemcpyDeviceToHost));
+    MF_CUDA(cudaMemcpy(R.state.data(), S_.state, n * 4, cudaMemcpyDeviceToHost));
+    MF_CUDA(cudaMemcpy(R.num, S_.num, 8, cudaMemcpyDeviceToHost));
+    MF_CUDA(cudaMemcpy(R.dead, S_.dead_ct, 8, cudaMemcpyDeviceToHost));
+    MF_CUDA(cudaMemcpy(&h_id_counter_, S_.id_counter, 4, cudaMemcpyDeviceToHost));
+    h_occ_.assign(h_walls_.begin(), h_walls_.end());
+    for (int g = 0; g < kGroups; g++) {
+        h_tpos_[g].clear(); h_tid_[g].clear();
+        for (int i = 0; i < R.num[g]; i++) {
+            const size_t s = (size_t)g * P_.cap + i;
+            if (!(R.state[s] & 1u)) h_occ_[(size_t)((R.pos[s] >> 16) & 0xFFFF) * P_.W + (R.pos[s] & 0xFFFF)] = 2;
+        }
+    }
+}
+
+void Engine::late_add_sync_up() {
+    LateRecords &R = g_late;
+    const int old_cap = P_.cap;
+    int need = 0;
+    for (int g = 0; g < kGroups; g++) need = std::max(need, R.num[g] + (int)h_tpos_[g].size());
+    const int new_cap = need > old_cap ? round_up(need, 64) : old_cap;
+    const size_t n = (size_t)2 * new_cap;
+    std::vector<int32_t> pos(n, 0), id(n, 0); std::vector<float> hp(n, 0), nr(n, 0), lr(n, 0);
+    std::vector<uint32_t> st(n, 0);
+    int num[2];
+    for (int g = 0; g < kGroups; g++) {
+        for (int i = 0; i < R.num[g]; i++) {
+            const size_t s = (size_t)g * old_cap + i, d = (size_t)g * new_cap + i;
+            pos[d] = R.pos[s]; id[d] = R.id[s]; hp[d] = R.hp[s]; nr[d] = R.nr[s]; lr[d] = R.lr[s]; st[d] = R.state[s];
+        }
+        num[g] = R.num[g];
+        for (size_t k = 0; k < h_tpos_[g].size(); k++) {
+            const size_t d = (size_t)g * new_cap + num[g]++;
+            pos[d] = h_tpos_[g][k]; id[d] = h_tid_[g][k]; hp[d] = P_.hp; nr[d] = P_.step_reward; lr[d] = 0.0f;
+            st[d] = 0u | (OP_NULL << 8) | ((uint32_t)n_action() << 16);
+        }
+    }
+    if (new_cap != old_cap) { free_state(); alloc_state(new_cap); }
+    MF_CUDA(cudaMemcpy(S_.pos, pos.data(), n * 4, cudaMemcpyHostToDevice));
+    MF_CUDA(cudaMemcpy(S_.id, id.data(), n * 4, cudaMemcpyHostToDevice));
+    MF_CUDA(cudaMemcpy(S_.hp, hp.data(), n * 4, cudaMemcpyHostToDevice));
+    MF_CUDA(cudaMemcpy(S_.next_rew, nr.data(), n * 4, cudaMemcpyHostToDevice));
+    MF_CUDA(cudaMemcpy(S_.last_rew, lr.data(), n * 4, cudaMemcpyHostToDevice));
+    MF_CUDA(cudaMemcpy(S_.state, st.data(), n * 4, cudaMemcpyHostToDevice));
+    MF_CUDA(cudaMemcpy(S_.num, num, 8, cudaMemcpyHostToDevice));
+    MF_CUDA(cudaMemcpy(S_.id_counter, &h_id_counter_, 4, cudaMemcpyHostToDevice));
+    h_num_[0] = num[0]; h_num_[1] = num[1];
+}
+
+uint32_t Engine::pull_rng0() {
+    uint32_t s = 1;
+    MF_CUDA(cudaDeviceSynchronize());
+    MF_CUDA(cudaMemcpy(&s, S_.rng, 4, cudaMemcpyDeviceToHost));
+    return s;
+}
+void Engine::push_rng0(uint32_t s) { MF_CUDA(cudaMemcpy(S_.rng, &s, 4, cudaMemcpyHostToDevice)); }
+
+bool Engine::cell_blank_for_placement(int x, int y) {
+    if (stepped_) {
+        if (P_.E != 1) throw Fatal("placement queries after stepping need a single env");
+        late_add_sync_down();   // refreshes h_occ_ from the device; nothing is modified
+        h_tpos_[0].clear(); h_tpos_[1].clear(); h_tid_[0].clear(); h_tid_[1].clear();
+    }
+    if (x < 0 || y < 0 || x + 1 >= P_.W || y + 1 >= P_.H) return false;
+    return h_occ_[(size_t)y * P_.W + x] == 0;
+}
+
+void Engine::grow(int need_cap) {
+    if (need_cap <= P_.cap) return;
+    free_state();
+    alloc_state(round_up(need_cap, 64));
+}
+
+void Engine::commit(cudaStream_t st) {
+    if (!placement_dirty_) return;
+    const int need = (int)std::max(h_tpos_[0].size(), h_tpos_[1].size());
+    grow(need);
+    const int cap = P_.cap;
+    std::vector<int32_t> tmpl((size_t)4 * cap, 0);
+    int32_t num[2];
+    for (int g = 0; g < kGroups; g++) {
+        num[g] = (int32_t)h_tpos_[g].size();
+        for (int i = 0; i < num[g]; i++) {
+            tmpl[(size_t)g * cap + i] = h_tpos_[g][i];
+            tmpl[(size_t)2 * cap + (size_t)g * cap + i] = h_tid_[g][i];
+        }
+    }
+    // pageable sources: these copies are synchronous with respect to the host
+    MF_CUDA(cudaMemcpyAsync(S_.init_pos, tmpl.data(), tmpl.size() * 4, cudaMemcpyHostToDevice, st));
+    MF_CUDA(cudaMemcpyAsync(S_.init_num, num, 8, cudaMemcpyHostToDevice, st));
+    MF_CUDA(cudaMemcpyAsync(S_.walls, h_walls_.data(), h_walls_.size(), cudaMemcpyHostToDevice, st));
+    MF_CUDA(cudaStreamSynchronize(st));
+    k_place<<<P_.E, 128, 0, st>>>(P_, S_);
+    MF_CUDA(cudaGetLastError());
+    for (int e = 0; e < P_.E; e++) { h_num_[e * 2] = num[0]; h_num_[e * 2 + 1] = num[1]; }
+    placement_dirty_ = false;
+    stepped_ = false;
+}
+
+void Engine::download_num(cudaStream_t st) {
+    MF_CUDA(cudaMemcpyAsync(h_num_.data(), S_.num, h_num_.size() * 4, cudaMemcpyDeviceToHost, st));
+    MF_CUDA(cudaStreamSynchronize(st));
+}
+
+// ---------------------------------------------------------------------------------------------
+// launches
+// ---------------------------------------------------------------------------------------------
+void Engine::observe(float *d_view, float *d_feature, int group_mask, cudaStream_t st) {
+    commit(st);
+    if (group_mask < 1 || group_mask > 3) throw Fatal("observe: bad group mask");
+    ObsIO io;
+    io.view = d_view; io.feature = d_feature; io.group_mask = group_mask;
+    io.tile_agents = std::max(kObsChunk, round_up(cfg_.obs_tile_agents, kObsChunk));
+    io.tiles_per_group = (P_.cap + io.tile_agents - 1) / io.tile_agents;
+    const ObsSmem L = obs_smem_layout(P_.W, P_.H);
+    if (obs_attr_ != L.total) {
+        MF_CUDA(cudaFuncSetAttribute(k_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        obs_attr_ = L.total;
+    }
+    const unsigned grid = (unsigned)((size_t)P_.E * (group_mask == 3 ? 2 : 1) * io.tiles_per_group);
+    k_obs<<<grid, kObsThreads, L.total, st>>>(P_, S_, io);
+    MF_CUDA(cudaGetLastError());
+}
+
+void Engine::step(const StepIO &io, cudaStream_t st) {
+    commit(st);
+    const StepSmem L = step_smem_layout(P_.W, P_.H, P_.cap);
+    if (step_attr_ != L.total) {
+        MF_CUDA(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        step_attr_ = L.total;
+    }
+    int threads = cfg_.step_threads > 0 ? cfg_.step_threads : std::min(1024, std::max(64, P_.cap));
+    threads = round_up(threads, 32);
+    k_step<<<P_.E, threads, L.total, st>>>(P_, S_, io);
+    MF_CUDA(cudaGetLastError());
+    if (io.phases & (PH_STEP | PH_CLEAR | PH_SETACT)) stepped_ = true;
+}
+
+void Engine::mean_action(const int32_t *d_actions, const int32_t *d_num, float *d_out, int rows, int cap,
+                         int n_action, cudaStream_t st) {
+    if (n_action > 32) throw Fatal("mean_action: at most 32 actions");
+    const int warps_per_block = 8;
+    const int blocks = (rows + warps_per_block - 1) / warps_per_block;
+    k_mean_action<<<blocks, warps_per_block * 32, 0, st>>>(d_actions, d_num, d_out, rows, cap, n_action);
+    MF_CUDA(cudaGetLastError());
+}
+
+}  // namespace mfmarl

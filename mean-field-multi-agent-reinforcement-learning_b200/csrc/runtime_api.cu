@@ -1,0 +1,532 @@
+// The drop-in boundary: the reference's runtime_api.h C symbols (examples/battle_model/src/runtime_api.h:20-55,
+// implemented there in runtime_api.cc:15-169) over the CUDA engine.  One game = one environment;
+// every data buffer is a caller-owned HOST array sized from get_info("num") exactly as the reference's
+// Python binding does (python/magent/gridworld.py:282-342,377-389), so each call ends with a
+// device->host copy.  Declared in include/mfmarl_magent.h.
+//
+// Scope: the battle path.  Configurations the kernels are not built for
+// (turn_mode, food_mode, bodies larger than 1x1, sector ranges, reward rules other than
+// `any(a) attack any(b) -> a`) fail loudly at reset instead of running something different.
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/mfmarl_magent.h"
+#include "engine.h"
+
+using namespace mfmarl;
+
+namespace {
+
+struct TypeDef {   // AgentType.cc:30-84
+    int width = 1, length = 1;
+    float view_angle = 360, attack_angle = 0;
+    bool attack_in_group = false, can_absorb = false;
+    AgentTypeParams p;
+    TypeDef() { p.hp = 1.0f; p.speed = 1.0f; p.view_radius = 1; p.attack_radius = 0; p.damage = 0;
+                p.step_recover = 0; p.kill_supply = 0; p.step_reward = 0; p.kill_reward = 0;
+                p.dead_penalty = 0; p.attack_penalty = 0; }
+};
+
+struct Symbol { int group = 0, index = -1; };
+struct Node { int op = -1; std::vector<int> inputs; };
+struct Rule { int on; std::vector<int> receivers; std::vector<float> values; bool terminal, auto_value; };
+
+struct Game {
+    // config (GridWorld::set_config, GridWorld.cc:126-155)
+    int width = 0, height = 0, embedding_size = 0;
+    bool food_mode = false, turn_mode = false, minimap_mode = false, goal_mode = false;
+    bool seed_set = false; unsigned long seed = 0;
+    std::map<std::string, TypeDef> types;
+    std::vector<std::string> groups;
+    std::vector<Symbol> symbols;
+    std::vector<Node> nodes;
+    std::vector<Rule> rules;
+
+    std::unique_ptr<Engine> eng;
+    cudaStream_t st = nullptr;
+
+    // device staging for the host-buffer ABI
+    float *d_view = nullptr, *d_feat = nullptr; int obs_cap = 0;
+    int32_t *d_actions = nullptr, *d_perm = nullptr, *d_done = nullptr; int act_cap = 0;
+    std::vector<int> seq;          // groups in set_action call order since the last step
+    bool inject_next = false;
+
+    ~Game() {
+        cudaFree(d_view); cudaFree(d_feat); cudaFree(d_actions); cudaFree(d_perm); cudaFree(d_done);
+    }
+
+    const TypeDef &type_of(int group) const {
+        if (group < 0 || group >= (int)groups.size()) throw Fatal("invalid group handle " + std::to_string(group));
+        return types.at(groups[group]);
+    }
+
+    void check_supported() const {
+        if (groups.size() != 2) throw Fatal("the CUDA battle engine supports exactly two groups");
+        const TypeDef &a = type_of(0), &b = type_of(1);
+        if (groups[0] != groups[1] && memcmp(&a.p, &b.p, sizeof(a.p)) != 0)
+            throw Fatal("both groups must use the same agent type attributes");
+        if (turn_mode || food_mode || goal_mode) throw Fatal("turn_mode / food_mode / goal_mode are out of scope");
+        if (!minimap_mode) throw Fatal("minimap_mode must be on (7-channel battle observation)");
+        if (a.width != 1 || a.length != 1) throw Fatal("only 1x1 agent bodies are supported");
+        if (a.view_angle != 360.0f || a.attack_angle != 360.0f) throw Fatal("only circular view/attack ranges are supported");
+        if (a.attack_in_group || a.can_absorb) throw Fatal("attack_in_group / can_absorb are out of scope");
+        if (width <= 0 || height <= 0) throw Fatal("map_width / map_height not configured");
+    }
+
+    // reduce the reward DSL to the one shape the battle config uses (RewardEngine.cc:216-240,373-443)
+    void attack_bonus(float out[2]) const {
+        out[0] = out[1] = 0.0f;
+        bool seen[2] = {false, false};
+        for (const Rule &r : rules) {
+            if (r.on < 0 || r.on >= (int)nodes.size()) throw Fatal("reward rule refers to an undefined event node");
+            const Node &n = nodes[r.on];
+            bool ok = n.op == 7 /* OP_ATTACK */ && n.inputs.size() == 2 && r.receivers.size() == 1 &&
+                      r.receivers[0] == n.inputs[0] && !r.terminal && !r.auto_value;
+            if (ok) {
+                const Symbol &a = symbols.at(n.inputs[0]), &b = symbols.at(n.inputs[1]);
+                ok = a.index == -1 && b.index == -1 && a.group != b.group && a.group >= 0 && a.group < 2 && !seen[a.group];
+                if (ok) { out[a.group] = r.values[0]; seen[a.group] = true; }
+            }
+            if (!ok) throw Fatal("unsupported reward rule: only Event(any(a), 'attack', any(b)) -> receiver a, one per group");
+        }
+    }
+
+    Engine &engine() {
+        if (!eng) throw Fatal("env_reset must be called before this function");
+        return *eng;
+    }
+
+    void ensure_engine() {
+        if (eng) return;
+        check_supported();
+        EngineConfig c;
+        c.n_envs = 1; c.width = width; c.height = height; c.capacity = 64;
+        c.embedding_size = embedding_size; c.rng_mode = RNG_MINSTD; c.seed = (unsigned)(seed % 2147483647ul);
+        c.type = type_of(0).p;
+        attack_bonus(c.attack_bonus);
+        eng.reset(new Engine(c));
+        if (seed_set) eng->set_seed(seed);
+        MF_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    }
+
+    void ensure_staging() {
+        Engine &E = engine();
+        E.commit(st);
+        const int cap = E.cap();
+        if (obs_cap < cap) {
+            cudaFree(d_view); cudaFree(d_feat);
+            MF_CUDA(cudaMalloc(&d_view, (size_t)2 * cap * kViewRow * 4 + 64));
+            MF_CUDA(cudaMalloc(&d_feat, (size_t)2 * cap * E.params().feature_size * 4));
+            obs_cap = cap;
+        }
+        if (act_cap < cap) {
+            cudaFree(d_actions); cudaFree(d_perm);
+            MF_CUDA(cudaMalloc(&d_actions, (size_t)2 * cap * 4));
+            MF_CUDA(cudaMalloc(&d_perm, (size_t)2 * cap * 4));
+            MF_CUDA(cudaMemset(d_actions, 0, (size_t)2 * cap * 4));
+            act_cap = cap;
+        }
+        if (!d_done) MF_CUDA(cudaMalloc(&d_done, 4));
+    }
+};
+
+Game *G(EnvHandle h) {
+    if (!h) throw Fatal("null game handle");
+    return reinterpret_cast<Game *>(h);
+}
+
+bool streq(const char *a, const char *b) { return strcmp(a, b) == 0; }
+
+template <typename T>
+std::vector<T> pull(const T *dptr, size_t n, cudaStream_t st) {
+    std::vector<T> h(n);
+    if (n) {
+        MF_CUDA(cudaMemcpyAsync(h.data(), dptr, n * sizeof(T), cudaMemcpyDeviceToHost, st));
+        MF_CUDA(cudaStreamSynchronize(st));
+    }
+    return h;
+}
+
+}  // namespace
+
+#define API_BEGIN try {
+#define API_END(name) } catch (const std::exception &ex) { return report_fatal(name, ex); } return 0;
+
+extern "C" {
+
+int env_new_game(EnvHandle *game, const char *name) {
+    API_BEGIN
+    if (!streq(name, "GridWorld")) throw Fatal(std::string("invalid name of game: ") + name + " (only GridWorld is built)");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        throw Fatal("no CUDA device visible: this engine has no CPU fallback");
+    *game = reinterpret_cast<EnvHandle>(new Game());
+    API_END("env_new_game")
+}
+
+int env_delete_game(EnvHandle game) {
+    API_BEGIN
+    Game *g = reinterpret_cast<Game *>(game);
+    if (g) { if (g->st) { cudaStreamSynchronize(g->st); } g->eng.reset(); if (g->st) cudaStreamDestroy(g->st); delete g; }
+    API_END("env_delete_game")
+}
+
+int env_config_game(EnvHandle game, const char *name, void *p_value) {
+    API_BEGIN
+    Game *g = G(game);
+    const int ivalue = *(int *)p_value;
+    const bool bvalue = *(bool *)p_value;
+    if (streq(name, "map_width")) g->width = ivalue;
+    else if (streq(name, "map_height")) g->height = ivalue;
+    else if (streq(name, "food_mode")) g->food_mode = bvalue;
+    else if (streq(name, "turn_mode")) g->turn_mode = bvalue;
+    else if (streq(name, "minimap_mode")) g->minimap_mode = bvalue;
+    else if (streq(name, "goal_mode")) g->goal_mode = bvalue;
+    else if (streq(name, "embedding_size")) g->embedding_size = ivalue;
+    else if (streq(name, "render_dir")) { /* rendering is out of scope: accepted and ignored */ }
+    else if (streq(name, "seed")) {                       // GridWorld.cc:150-151
+        g->seed = (unsigned long)ivalue; g->seed_set = true;
+        if (g->eng) g->eng->set_seed(g->seed);
+    } else throw Fatal(std::string("invalid argument in GridWorld::set_config : ") + name);
+    if (g->eng && !streq(name, "seed") && !streq(name, "render_dir"))
+        throw Fatal("game configuration cannot change after the first reset");
+    API_END("env_config_game")
+}
+
+int env_reset(EnvHandle game) {
+    API_BEGIN
+    Game *g = G(game);
+    g->ensure_engine();
+    g->eng->reset();
+    g->seq.clear();
+    API_END("env_reset")
+}
+
+int env_get_observation(EnvHandle game, GroupHandle group, float **buffer) {
+    API_BEGIN
+    Game *g = G(game);
+    Engine &E = g->engine();
+    g->type_of(group);
+    g->ensure_staging();
+    const int n = E.host_num(0, group), cap = E.cap(), FS = E.params().feature_size;
+    if (n == 0) return 0;
+    E.observe(g->d_view, g->d_feat, 1 << group, g->st);
+    MF_CUDA(cudaMemcpyAsync(buffer[0], g->d_view + (size_t)group * cap * kViewRow, (size_t)n * kViewRow * 4,
+                            cudaMemcpyDeviceToHost, g->st));
+    MF_CUDA(cudaMemcpyAsync(buffer[1], g->d_feat + (size_t)group * cap * FS, (size_t)n * FS * 4,
+                            cudaMemcpyDeviceToHost, g->st));
+    MF_CUDA(cudaStreamSynchronize(g->st));
+    API_END("env_get_observation")
+}
+
+int env_set_action(EnvHandle game, GroupHandle group, const int *actions) {
+    API_BEGIN
+    Game *g = G(game);
+    Engine &E = g->engine();
+    g->type_of(group);
+    g->ensure_staging();
+    for (int s : g->seq)
+        if (s == group) throw Fatal("set_action called twice for one group before step");
+    const int n = E.host_num(0, group);
+    if (n > 0)
+        MF_CUDA(cudaMemcpyAsync(g->d_actions + (size_t)group * E.cap(), actions, (size_t)n * 4,
+                                cudaMemcpyHostToDevice, g->st));
+    StepIO io{};
+    io.actions = g->d_actions; io.phases = PH_SETACT; io.setact_mask = 1 << group;
+    io.group_seq[0] = io.group_seq[1] = -1;
+    E.step(io, g->st);
+    MF_CUDA(cudaStreamSynchronize(g->st));   // `actions` may be freed by the caller on return
+    g->seq.push_back(group);
+    API_END("env_set_action")
+}
+
+int env_step(EnvHandle game, int *done) {
+    API_BEGIN
+    Game *g = G(game);
+    Engine &E = g->engine();
+    g->ensure_staging();
+    StepIO io{};
+    io.phases = PH_STEP; io.done = g->d_done; io.attack_perm = g->d_perm;
+    io.group_seq[0] = g->seq.size() > 0 ? g->seq[0] : -1;
+    io.group_seq[1] = g->seq.size() > 1 ? g->seq[1] : -1;
+    if (g->inject_next) E.set_rng_mode(RNG_INJECT);
+    E.step(io, g->st);
+    if (g->inject_next) { E.set_rng_mode(RNG_MINSTD); g->inject_next = false; }
+    int h_done = 0;
+    MF_CUDA(cudaMemcpyAsync(&h_done, g->d_done, 4, cudaMemcpyDeviceToHost, g->st));
+    MF_CUDA(cudaStreamSynchronize(g->st));
+    *done = h_done;
+    g->seq.clear();
+    API_END("env_step")
+}
+
+int env_get_reward(EnvHandle game, GroupHandle group, float *buffer) {
+    API_BEGIN
+    Game *g = G(game);
+    Engine &E = g->engine();
+    g->type_of(group);
+    g->ensure_staging();
+    const int n = E.host_num(0, group);
+    if (n > 0) {
+        MF_CUDA(cudaMemcpyAsync(buffer, E.state().next_rew + (size_t)group * E.cap(), (size_t)n * 4,
+                                cudaMemcpyDeviceToHost, g->st));
+        MF_CUDA(cudaStreamSynchronize(g->st));
+    }
+    for (int i = 0; i < n; i++) buffer[i] = buffer[i] + 0.0f;   // + Group::get_reward(), always 0 (GridWorld.cc:764-768)
+    API_END("env_get_reward")
+}
+
+int env_get_info(EnvHandle game, GroupHandle group, const char *name, void *void_buffer) {
+    API_BEGIN
+    Game *g = G(game);
+    int *ibuf = (int *)void_buffer;
+    float *fbuf = (float *)void_buffer;
+    bool *bbuf = (bool *)void_buffer;
+
+    // ---- answers that do not need the engine (callable before reset, like the reference) ----
+    if (streq(name, "action_space") || streq(name, "view_space") || streq(name, "feature_space") ||
+        streq(name, "attack_base") || streq(name, "view2attack")) {
+        const TypeDef &t = g->type_of(group);
+        const CircleRange view(t.p.view_radius, 0.0f, t.width % 2), attack(t.p.attack_radius, t.width / 2.0f, t.width % 2),
+            move(t.p.speed, 0.0f, 1);
+        const int n_action = move.count + attack.count;
+        if (streq(name, "action_space")) ibuf[0] = n_action;
+        else if (streq(name, "view_space")) {              // GridWorld.cc:929-934
+            ibuf[0] = view.width; ibuf[1] = view.width;
+            ibuf[2] = 1 + (g->food_mode ? 1 : 0) + (int)g->groups.size() * (g->minimap_mode ? 3 : 2);
+        } else if (streq(name, "feature_space"))           // GridWorld.cc:1010-1018
+            ibuf[0] = g->embedding_size + n_action + 1 + (g->goal_mode ? 2 : 0) + (g->minimap_mode ? 2 : 0);
+        else if (streq(name, "attack_base")) ibuf[0] = move.count;
+        else {                                             // view2attack, GridWorld.cc:937-954
+            for (int i = 0; i < view.width * view.width; i++) ibuf[i] = -1;
+            for (int i = 0; i < attack.count; i++)
+                ibuf[(attack.dy[i] + view.center) * view.width + attack.dx[i] + view.center] = i;
+        }
+        return 0;
+    }
+    if (streq(name, "groups_info")) {                      // GridWorld.cc:957-972
+        static const int colors[4][3] = {{192, 64, 64}, {64, 64, 192}, {64, 192, 64}, {64, 64, 64}};
+        for (size_t i = 0; i < g->groups.size(); i++) {
+            const TypeDef &t = g->type_of((int)i);
+            ibuf[5 * i] = t.width; ibuf[5 * i + 1] = t.length;
+            for (int k = 0; k < 3; k++) ibuf[5 * i + 2 + k] = colors[i % 4][k];
+        }
+        return 0;
+    }
+    if (streq(name, "both_attack")) { ibuf[0] = 0; return 0; }
+
+    Engine &E = g->engine();
+    g->ensure_staging();
+    const int cap = E.cap();
+    const BattleState &S = E.state();
+
+    if (streq(name, "walls_info")) {                       // GridWorld.cc:871-880
+        const std::vector<unsigned char> &w = E.host_walls();
+        int ct = 0;
+        for (size_t i = 0; i < w.size(); i++)
+            if (w[i]) { ct++; ibuf[2 * ct] = (int)(i % E.params().W); ibuf[2 * ct + 1] = (int)(i / E.params().W); }
+        ibuf[0] = ct;
+        return 0;
+    }
+    if (streq(name, "global_minimap")) {                   // GridWorld.cc:811-846
+        const int vh = (int)lroundf(fbuf[0]), vw = (int)lroundf(fbuf[1]);
+        const int ng = 2;
+        memset(fbuf, 0, sizeof(float) * vh * vw * ng);
+        const int scale_h = (E.params().H + vh - 1) / vh, scale_w = (E.params().W + vw - 1) / vw;
+        for (int i = 0; i < ng; i++) {
+            const int channel = ((i - group + ng) % ng + ng) % ng;
+            const int n = E.host_num(0, i);
+            const std::vector<int32_t> pos = pull(S.pos + (size_t)i * cap, n, g->st);
+            for (int j = 0; j < n; j++)
+                fbuf[(((pos[j] >> 16) & 0xFFFF) / scale_h * vw + (pos[j] & 0xFFFF) / scale_w) * ng + channel] += 1.0f;
+            for (int k = 0; k < vh * vw; k++) fbuf[k * ng + channel] /= (size_t)n;
+        }
+        return 0;
+    }
+
+    g->type_of(group);
+    const int n = E.host_num(0, group);
+    if (streq(name, "num")) {
+        ibuf[0] = n;
+    } else if (streq(name, "id")) {
+        if (n) { MF_CUDA(cudaMemcpyAsync(ibuf, S.id + (size_t)group * cap, (size_t)n * 4, cudaMemcpyDeviceToHost, g->st));
+                 MF_CUDA(cudaStreamSynchronize(g->st)); }
+    } else if (streq(name, "pos")) {
+        const std::vector<int32_t> pos = pull(S.pos + (size_t)group * cap, n, g->st);
+        for (int i = 0; i < n; i++) { ibuf[2 * i] = pos[i] & 0xFFFF; ibuf[2 * i + 1] = (pos[i] >> 16) & 0xFFFF; }
+    } else if (streq(name, "alive")) {
+        const std::vector<uint32_t> st = pull(S.state + (size_t)group * cap, n, g->st);
+        for (int i = 0; i < n; i++) bbuf[i] = !(st[i] & 1u);
+    } else if (streq(name, "mean_info")) {                 // GridWorld.cc:849-870
+        const std::vector<int32_t> pos = pull(S.pos + (size_t)group * cap, n, g->st);
+        const std::vector<uint32_t> st = pull(S.state + (size_t)group * cap, n, g->st);
+        const int n_action = E.n_action();
+        std::vector<int> counter(n_action + 1, 0);
+        float sum_x = 0, sum_y = 0;
+        for (int i = 0; i < n; i++) {
+            sum_x += (float)(pos[i] & 0xFFFF); sum_y += (float)((pos[i] >> 16) & 0xFFFF);
+            counter[std::min<int>((st[i] >> 16) & 0xFF, n_action)]++;
+        }
+        const size_t an = (size_t)n;
+        fbuf[0] = sum_x / an; fbuf[1] = sum_y / an;
+        for (int i = 0; i < n_action; i++) fbuf[2 + i] = (float)(1.0 * counter[i] / an);
+    } else {
+        throw Fatal(std::string("unsupported info name in GridWorld::get_info : ") + name);
+    }
+    API_END("env_get_info")
+}
+
+int env_render(EnvHandle) { return 0; }             // rendering (RenderGenerator.cc) is out of scope: no-op
+int env_render_next_file(EnvHandle) { return 0; }
+
+int gridworld_register_agent_type(EnvHandle game, const char *name, int n, const char **keys, float *values) {
+    API_BEGIN
+    Game *g = G(game);
+    if (g->types.count(name)) throw Fatal(std::string("duplicated name of agent type in GridWorld::register_agent_type : ") + name);
+    TypeDef t;
+    for (int i = 0; i < n; i++) {
+        const char *k = keys[i]; const float v = values[i];
+        auto as_int = [&](float x) { return (int)(x + 0.5f); };
+        if (streq(k, "width")) t.width = as_int(v);
+        else if (streq(k, "length")) t.length = as_int(v);
+        else if (streq(k, "speed")) t.p.speed = v;
+        else if (streq(k, "hp")) t.p.hp = v;
+        else if (streq(k, "view_radius")) t.p.view_radius = v;
+        else if (streq(k, "view_angle")) t.view_angle = v;
+        else if (streq(k, "attack_radius")) t.p.attack_radius = v;
+        else if (streq(k, "attack_angle")) t.attack_angle = v;
+        else if (streq(k, "damage")) t.p.damage = v;
+        else if (streq(k, "step_recover")) t.p.step_recover = v;
+        else if (streq(k, "kill_supply")) t.p.kill_supply = v;
+        else if (streq(k, "step_reward")) t.p.step_reward = v;
+        else if (streq(k, "kill_reward")) t.p.kill_reward = v;
+        else if (streq(k, "dead_penalty")) t.p.dead_penalty = v;
+        else if (streq(k, "attack_penalty")) t.p.attack_penalty = v;
+        else if (streq(k, "attack_in_group")) t.attack_in_group = as_int(v) != 0;
+        else if (streq(k, "can_absorb")) t.can_absorb = as_int(v) != 0;
+        else if (streq(k, "hear_radius") || streq(k, "speak_radius") || streq(k, "speak_ability") ||
+                 streq(k, "trace") || streq(k, "eat_ability") || streq(k, "food_supply") ||
+                 streq(k, "view_x_offset") || streq(k, "view_y_offset") || streq(k, "att_x_offset") ||
+                 streq(k, "att_y_offset") || streq(k, "turn_x_offset") || streq(k, "turn_y_offset")) {
+            /* accepted, no effect on the battle path (offsets are recomputed, AgentType.cc:115-118) */
+        } else throw Fatal(std::string("invalid agent config in AgentType::AgentType : ") + k);
+    }
+    g->types.emplace(name, t);
+    API_END("gridworld_register_agent_type")
+}
+
+int gridworld_new_group(EnvHandle game, const char *agent_type_name, GroupHandle *group) {
+    API_BEGIN
+    Game *g = G(game);
+    if (!g->types.count(agent_type_name)) throw Fatal(std::string("invalid name of agent type in new_group : ") + agent_type_name);
+    if (g->eng) throw Fatal("groups cannot be added after the first reset");
+    *group = (GroupHandle)g->groups.size();
+    g->groups.push_back(agent_type_name);
+    API_END("gridworld_new_group")
+}
+
+int gridworld_add_agents(EnvHandle game, GroupHandle group, int n, const char *method,
+                         const int *pos_x, const int *pos_y, const int *dir) {
+    API_BEGIN
+    (void)dir;   // no turn_mode: every agent faces NORTH (GridWorld.cc:264)
+    Game *g = G(game);
+    Engine &E = g->engine();
+    std::vector<int> xs, ys;
+    if (streq(method, "custom")) {
+        xs.assign(pos_x, pos_x + n); ys.assign(pos_y, pos_y + n);
+    } else if (streq(method, "fill")) {                    // GridWorld.cc:212-223,270-296: xs = {x, y, width, height(, dir)}
+        for (int x = pos_x[0]; x < pos_x[0] + pos_x[2]; x++)
+            for (int y = pos_x[1]; y < pos_x[1] + pos_x[3]; y++) { xs.push_back(x); ys.push_back(y); }
+    } else if (streq(method, "random")) {                  // GridWorld.cc:194-202,236-255 + Map::get_random_blank Map.cc:49-63
+        uint32_t rs = E.pull_rng0();
+        const int W = E.params().W, H = E.params().H;
+        for (int i = 0; i < n; i++) {
+            int tries = 0;
+            while (true) {
+                rs = (uint32_t)(((uint64_t)rs * 16807ull) % 2147483647ull); const int x = (int)rs % (W - 1);
+                rs = (uint32_t)(((uint64_t)rs * 16807ull) % 2147483647ull); const int y = (int)rs % (H - 1);
+                if (E.cell_blank_for_placement(x, y)) {
+                    if (group == -1) E.add_walls(1, &x, &y); else E.add_agents(group, 1, &x, &y);
+                    break;
+                }
+                if (tries++ > W * H) throw Fatal("cannot find a blank position in a filled map");
+            }
+        }
+        E.push_rng0(rs);
+        if (group != -1) { E.commit(g->st); }
+        return 0;
+    } else throw Fatal(std::string("unsupported method in GridWorld::add_agents : ") + method);
+
+    if (group == -1) E.add_walls((int)xs.size(), xs.data(), ys.data());
+    else { g->type_of(group); E.add_agents(group, (int)xs.size(), xs.data(), ys.data()); }
+    API_END("gridworld_add_agents")
+}
+
+int gridworld_clear_dead(EnvHandle game) {
+    API_BEGIN
+    Game *g = G(game);
+    Engine &E = g->engine();
+    g->ensure_staging();
+    StepIO io{};
+    io.phases = PH_CLEAR; io.group_seq[0] = io.group_seq[1] = -1;
+    E.step(io, g->st);
+    E.download_num(g->st);
+    API_END("gridworld_clear_dead")
+}
+
+int gridworld_set_goal(EnvHandle, GroupHandle, const char *, const int *) {
+    API_BEGIN
+    throw Fatal("gridworld_set_goal is deprecated in the reference and out of scope here");
+    API_END("gridworld_set_goal")
+}
+
+int gridworld_define_agent_symbol(EnvHandle game, int no, int group, int index) {
+    API_BEGIN
+    Game *g = G(game);
+    if (no < 0) throw Fatal("negative symbol number");
+    if (no >= (int)g->symbols.size()) g->symbols.resize(no + 1);
+    g->symbols[no].group = group; g->symbols[no].index = index;
+    API_END("gridworld_define_agent_symbol")
+}
+
+int gridworld_define_event_node(EnvHandle game, int no, int op, int *inputs, int n_inputs) {
+    API_BEGIN
+    Game *g = G(game);
+    if (no < 0) throw Fatal("negative event node number");
+    if (no >= (int)g->nodes.size()) g->nodes.resize(no + 1);
+    g->nodes[no].op = op;
+    g->nodes[no].inputs.assign(inputs, inputs + n_inputs);
+    API_END("gridworld_define_event_node")
+}
+
+int gridworld_add_reward_rule(EnvHandle game, int on, int *receiver, float *value, int n_receiver,
+                              bool is_terminal, bool auto_value) {
+    API_BEGIN
+    Game *g = G(game);
+    Rule r;
+    r.on = on; r.receivers.assign(receiver, receiver + n_receiver); r.values.assign(value, value + n_receiver);
+    r.terminal = is_terminal; r.auto_value = auto_value;
+    g->rules.push_back(r);
+    API_END("gridworld_add_reward_rule")
+}
+
+// ---- test hook (not in the reference ABI): the next env_step resolves attacks in the given order ----
+int mfmarl_inject_attack_order(EnvHandle game, const int *perm, int n) {
+    API_BEGIN
+    Game *g = G(game);
+    Engine &E = g->engine();
+    g->ensure_staging();
+    if (n > 2 * E.cap()) throw Fatal("attack order longer than the agent capacity");
+    if (n > 0) MF_CUDA(cudaMemcpyAsync(g->d_perm, perm, (size_t)n * 4, cudaMemcpyHostToDevice, g->st));
+    MF_CUDA(cudaStreamSynchronize(g->st));
+    g->inject_next = true;
+    API_END("mfmarl_inject_attack_order")
+}
+
+const char *mfmarl_last_error(void) { return last_error(); }
+
+}  // extern "C"
