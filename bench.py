@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- battle agent-steps/s (observations + mean action included) on N B200s, with the roofline of
+the dominant kernel and the reference CPU engine timed beside it.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path (one process per GPU)
+  python bench.py --impl reference [--gpus N] [--steps K] ...    the reference CPU engine on the host cores
+
+Workload (BASELINE.json configs[2], "C3"): 40x40 battle, 64 v 64 agents, 4096 lock-stepped environments per
+GPU, synthetic uniform-random actions, episodes auto-reset at done / 400 steps.  One "step" = one lockstep
+pass of the hot path over all environments of the GPU: k_obs (both groups' views + features) then k_step
+(set_action x2, step, reward, alive, mean action, clear_dead).  Unit of work: agent-step.
+Inputs (actions) are resident in HBM for `value`; `e2e` feeds them from pinned host memory every step and
+reads rewards / alive / done / mean actions back to the host inside the timed region.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(REPO, "mean-field-multi-agent-reinforcement-learning_b200")
+for _p in (os.path.join(PKG, "python"), os.path.join(REPO, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+BYTES_PER_AGENT_OBS = 13 * 13 * 7 * 4 + 34 * 4          # 4868: view + feature rows written by k_obs
+BYTES_PER_AGENT_STEP = BYTES_PER_AGENT_OBS + 4 + 4 + 1  # + action read, reward + alive written
+WORKLOADS = {
+    "c3": dict(name="battle_40x40_64v64_4096envs_per_gpu_uniform_actions (BASELINE configs[2])",
+               map_size=40, cap=64, envs=4096, max_steps=400),
+    "c4": dict(name="battle_80x80_512v512_128envs_per_gpu_uniform_actions (BASELINE configs[3] shard)",
+               map_size=80, cap=512, envs=128, max_steps=400),
+}
+REF_SO = os.path.join(REPO, "oracle", "_ref", "libmagent_ref.so")
+
+
+def placement(wl):
+    from scenarios import c4_positions, generate_map_positions
+    return generate_map_positions(40) if wl["map_size"] == 40 else c4_positions()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU side: the reference engine (or the C oracle port) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_worker(argv):
+    """One single-threaded environment: `warm` untimed + `steps` timed lockstep steps of the hot loop
+    (get_observation x2, set_action x2, step, get_reward/get_alive x2, mean action, clear_dead)."""
+    kind, map_size, warm, steps, seed = argv[0], int(argv[1]), int(argv[2]), int(argv[3]), int(argv[4])
+    os.environ["OMP_NUM_THREADS"] = "1"
+    import numpy as np
+    from engines import OracleEngine, RefEngine
+    from scenarios import c4_positions, generate_map_positions
+    eng = RefEngine(map_size) if kind == "reference" else OracleEngine(map_size)
+    left, right = generate_map_positions(40) if map_size == 40 else c4_positions()
+    rng = np.random.RandomState(seed)
+    eye = np.eye(21)
+
+    def episode_reset():
+        eng.reset(); eng.add_agents(0, left); eng.add_agents(1, right)
+
+    episode_reset()
+    agent_steps, t_start, ep_steps = 0, None, 0
+    for s in range(warm + steps):
+        if s == warm:
+            t_start = time.perf_counter()
+        n = [eng.get_num(0), eng.get_num(1)]
+        for g in range(2):
+            eng.get_observation(g)
+        acts = [rng.randint(0, 21, size=n[g]).astype(np.int32) for g in range(2)]
+        for g in range(2):
+            eng.set_action(g, acts[g])
+        done = eng.step()
+        for g in range(2):
+            eng.get_reward(g); eng.get_alive(g)
+            np.mean(eye[acts[g]], axis=0, keepdims=True)      # senario_battle.py:141
+        eng.clear_dead()
+        if s >= warm:
+            agent_steps += n[0] + n[1]
+        ep_steps += 1
+        if done or ep_steps >= 400:
+            episode_reset(); ep_steps = 0
+    print(json.dumps({"agent_steps": agent_steps, "seconds": time.perf_counter() - t_start}))
+
+
+def run_cpu(kind, map_size, warm, steps, procs):
+    """`procs` independent single-thread environments side by side (the fair throughput comparator:
+    intra-env OpenMP scales ~1.4x at 8 threads and is nondeterministic)."""
+    cmds = [[sys.executable, os.path.abspath(__file__), "--_cpu_worker", kind, str(map_size), str(warm),
+             str(steps), str(1000 + i)] for i in range(procs)]
+    env = dict(os.environ, OMP_NUM_THREADS="1", CUDA_VISIBLE_DEVICES="")
+    ps = [subprocess.Popen(c, stdout=subprocess.PIPE, env=env) for c in cmds]
+    outs = [json.loads(p.communicate()[0].decode().strip().splitlines()[-1]) for p in ps]
+    total = sum(o["agent_steps"] for o in outs)
+    seconds = max(o["seconds"] for o in outs)
+    return total / seconds, total, seconds
+
+
+def cpu_kind():
+    return "reference" if os.path.exists(REF_SO) else "port"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks: sampled DURING the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake"}
+
+    def __init__(self, device_index):
+        self.samples, self.reason_bits, self.max_mhz = [], 0, None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+                if not uuid.startswith("GPU-"):
+                    uuid = "GPU-" + uuid
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.reason_bits |= nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": [n for b, n in self.REASONS.items() if self.reason_bits & b],
+                "samples": len(self.samples)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(workload):
+    """dram bytes per k_obs launch from the committed ncu --set full capture, if one exists."""
+    try:
+        with open(os.path.join(REPO, "profiles", "obs_traffic.json")) as f:
+            return json.load(f).get(workload)
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from mfmarl_b200 import BatchedGridWorld
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    wl = WORKLOADS[args.workload]
+    E, cap, K, W = args.envs or wl["envs"], wl["cap"], args.steps, args.warmup
+    left, right = placement(wl)
+    env = BatchedGridWorld(E, map_size=wl["map_size"], capacity=cap, device=dev, rng="philox", seed=0,
+                           env_base=rank * E, max_steps=wl["max_steps"], auto_reset=True)
+    env.reset(); env.add_agents(0, left); env.add_agents(1, right)
+
+    # synthetic actions, uniform{0..20} from torch's Philox generator, resident in HBM: a pool the steps cycle through
+    gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
+    POOL = 8
+    pool = [torch.randint(0, 21, (E, 2, cap), generator=gen, device=dev, dtype=torch.int32) for _ in range(POOL)]
+    view, feat = env.observe()        # allocates the observation block (E*2*cap*4868 B)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for k in range(W):
+        env.observe(); env.step(pool[k % POOL])
+    barrier()
+
+    # ---- timed region: exactly K steps, CUDA events on the launching stream ----
+    as0 = int(env.get("agent_steps").sum())
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with ClockSampler(local) as clocks:
+        t0.record()
+        for k in range(K):
+            ev[k][0].record()
+            env.observe()
+            ev[k][1].record()
+            env.step(pool[k % POOL])
+            ev[k][2].record()
+        t1.record()
+        barrier()
+    ms = t0.elapsed_time(t1)
+    agent_steps = int(env.get("agent_steps").sum()) - as0
+    obs_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / K
+    step_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / K
+
+    # ---- e2e: actions from pinned host memory each step, results read back to the host each step ----
+    h_act = [p.cpu().pin_memory() for p in pool]
+    n_act = env.sizes["n_action"]
+    h_reward = torch.empty((E, 2, cap), dtype=torch.float32).pin_memory()
+    h_alive = torch.empty((E, 2, cap), dtype=torch.uint8).pin_memory()
+    h_mean = torch.empty((E, 2, n_act), dtype=torch.float32).pin_memory()
+    h_done = torch.empty((E,), dtype=torch.int32).pin_memory()
+    for k in range(min(W, 3)):
+        env.observe(); env.step_host(h_act[k % POOL], h_reward, h_alive, h_mean, h_done)
+    as1 = int(env.get("agent_steps").sum())
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(K):
+        env.observe()
+        env.step_host(h_act[k % POOL], h_reward, h_alive, h_mean, h_done)   # H2D + k_step + D2H + sync
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    e2e_agent_steps = int(env.get("agent_steps").sum()) - as1
+    h2d = h_act[0].numel() * 4
+    d2h = h_reward.numel() * 4 + h_alive.numel() + h_mean.numel() * 4 + h_done.numel() * 4
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        c = torch.tensor([agent_steps, e2e_agent_steps], device=dev, dtype=torch.int64)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        ms, e2e_ms = float(t[0]), float(t[1])
+        agent_steps_all, e2e_all = int(c[0]), int(c[1])
+    else:
+        agent_steps_all, e2e_all = agent_steps, e2e_agent_steps
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        agents_per_launch = agent_steps / K
+        achieved = agents_per_launch * BYTES_PER_AGENT_OBS / (obs_ms * 1e-3) / 1e9
+        line = {
+            "metric": "battle agent-steps/sec incl. obs+mean-action",
+            "value": agent_steps_all / (ms * 1e-3), "unit": "agent-steps/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "envs_per_gpu": E, "map": wl["map_size"], "agents_per_env": 2 * cap,
+                       "actions": "uniform{0..20}, torch Philox, pool of %d resident tensors" % POOL,
+                       "rng": "philox(seed, env, step)", "auto_reset": "done or %d steps" % wl["max_steps"],
+                       "l2": "outputs per step (%.2f GB) exceed the 126 MB L2; no explicit flush"
+                             % (E * 2 * cap * BYTES_PER_AGENT_OBS / 1e9),
+                       "sharding": "envs [r*E,(r+1)*E) on rank r, no collective on the env path"},
+            "gpu_launches": 2 * K,
+            "kernels_ms": {"k_obs": obs_ms, "k_step": step_ms},
+            "roofline": {"bound": "hbm", "kernel": "k_obs", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
+                         "bytes_per_agent": BYTES_PER_AGENT_OBS, "agents_per_launch": agents_per_launch,
+                         "whole_step_frac": (agent_steps / K) * BYTES_PER_AGENT_STEP / (ms / K * 1e-3) / 1e9 / peak},
+            "e2e": {"value": e2e_all / (e2e_ms * 1e-3), "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h,
+                    "note": "mfb_step_host: actions from pinned host memory, rewards/alive/done/mean action read "
+                            "back; observations stay in HBM for the policy network"},
+            "clocks": clocks.summary(),
+        }
+        if world == 1 and not args.no_cpu:
+            kind = cpu_kind()
+            procs = os.cpu_count() or 1
+            v, total, secs = run_cpu(kind, wl["map_size"], 20, args.cpu_steps, procs)
+            line["cpu_baseline"] = {"value": v, "unit": "agent-steps/s", "cores": procs, "kind": kind,
+                                    "sample": "%d independent single-thread envs (OMP_NUM_THREADS=1) x %d lockstep steps "
+                                              "of the same hot loop, %.1f s" % (procs, args.cpu_steps, secs)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU engine on the host cores, same metric / config
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    kind = cpu_kind()
+    procs = os.cpu_count() or 1
+    CHUNK = 32  # one reference "step" = every worker advances its own env by CHUNK lockstep steps
+    v, total, secs = run_cpu(kind, wl["map_size"], args.warmup * CHUNK, args.steps * CHUNK, procs)
+    sample = ("%d independent single-thread envs of the %s engine (OMP_NUM_THREADS=1), each step = %d lockstep "
+              "steps per env (bounded sample of the %d-env workload), %.1f s"
+              % (procs, "reference C++" if kind == "reference" else "C oracle port", CHUNK, wl["envs"], secs))
+    line = {
+        "impl": "reference",
+        "metric": "battle agent-steps/sec incl. obs+mean-action", "value": v, "unit": "agent-steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3 / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "envs_per_gpu": wl["envs"], "map": wl["map_size"],
+                   "agents_per_env": 2 * wl["cap"]},
+        "cpu_baseline": {"value": v, "unit": "agent-steps/s", "cores": procs, "kind": kind, "sample": sample},
+        "e2e": {"value": v, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--_cpu_worker":
+        return cpu_worker(sys.argv[2:])
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's)")
+    ap.add_argument("--cpu-steps", type=int, default=60000, help="timed steps per CPU-baseline worker")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: relaunch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000),
+               os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

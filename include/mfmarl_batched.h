@@ -79,7 +79,7 @@ int mfb_mean_action(const int32_t *d_actions /* [rows][cap] */, const int32_t *d
 /* state read-back into HOST buffers (synchronises `stream`): key in
  *   "num" int32[E][2], "dead_ct" int32[E][2], "pos" int32[E][2][cap][2], "hp" float[E][2][cap],
  *   "id" int32[E][2][cap], "alive" uint8[E][2][cap], "last_action" int32[E][2][cap],
- *   "step_ct" int32[E], "rng" uint32[E]                                                             */
+ *   "step_ct" int32[E], "rng" uint32[E], "agent_steps" uint64[E] (agents stepped since creation)   */
 int mfb_get(mfb_engine *eng, const char *key, void *host_buf, void *stream);
 /* device pointer to the live int32[E][2] agent counts (for masking on the device) */
 int mfb_num_device_ptr(mfb_engine *eng, const int32_t **out);

@@ -154,6 +154,7 @@ int mfb_get(mfb_engine *h, const char *key, void *host_buf, void *stream) {
     else if (k == "id") copy(S.id, n * 4);
     else if (k == "step_ct") copy(S.step_ct, ne * 4);
     else if (k == "rng") copy(S.rng, ne * 4);
+    else if (k == "agent_steps") copy(S.agent_steps, ne * 8);
     else if (k == "pos" || k == "alive" || k == "last_action") {
         std::vector<int32_t> tmp(n);
         MF_CUDA(cudaMemcpyAsync(tmp.data(), k == "pos" ? (const void *)S.pos : (const void *)S.state, n * 4,

@@ -297,6 +297,7 @@ __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState
         if (tid == 0) {
             if (io.done) io.done[e] = done;
             S.step_ct[e] = step_before + 1;
+            S.agent_steps[e] += (unsigned long long)(n0 + n1);
         }
     }
 

@@ -108,6 +108,8 @@ Engine::Engine(const EngineConfig &cfg) : cfg_(cfg) {
     MF_CUDA(cudaMalloc(&S_.id_counter, E * sizeof(int32_t)));
     MF_CUDA(cudaMalloc(&S_.walls, (size_t)P_.W * P_.H));
     MF_CUDA(cudaMalloc(&S_.init_num, 2 * sizeof(int32_t)));
+    MF_CUDA(cudaMalloc(&S_.agent_steps, E * sizeof(unsigned long long)));
+    MF_CUDA(cudaMemset(S_.agent_steps, 0, E * sizeof(unsigned long long)));
     MF_CUDA(cudaMemset(S_.num, 0, E * 2 * sizeof(int32_t)));
     MF_CUDA(cudaMemset(S_.dead_ct, 0, E * 2 * sizeof(int32_t)));
     MF_CUDA(cudaMemset(S_.step_ct, 0, E * sizeof(int32_t)));
@@ -121,7 +123,7 @@ Engine::Engine(const EngineConfig &cfg) : cfg_(cfg) {
 Engine::~Engine() {
     free_state();
     cudaFree(S_.num); cudaFree(S_.dead_ct); cudaFree(S_.rng); cudaFree(S_.step_ct);
-    cudaFree(S_.id_counter); cudaFree(S_.walls); cudaFree(S_.init_num);
+    cudaFree(S_.id_counter); cudaFree(S_.walls); cudaFree(S_.init_num); cudaFree(S_.agent_steps);
 }
 
 void Engine::alloc_state(int cap) {

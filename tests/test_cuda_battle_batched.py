@@ -1,0 +1,216 @@
+"""GPU parity tests for the batched, device-resident path (mfb_* C ABI through mfmarl_b200):
+every environment of a batch is compared bit for bit with its own C-oracle instance."""
+import numpy as np
+import pytest
+
+from engines import OracleEngine
+from lockstep import assert_same
+from scenarios import c4_positions, fight_actions, generate_map_positions, uniform_actions
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def make(E, map_size=40, cap=64, pos=None, **kw):
+    from mfmarl_b200 import BatchedGridWorld
+    env = BatchedGridWorld(E, map_size=map_size, capacity=cap, **kw)
+    env.reset()
+    left, right = pos if pos is not None else generate_map_positions(map_size)
+    env.add_agents(0, left)
+    env.add_agents(1, right)
+    oracles = []
+    for _ in range(E):
+        o = OracleEngine(map_size)
+        o.reset()
+        o.add_agents(0, left)
+        o.add_agents(1, right)
+        oracles.append(o)
+    return env, oracles
+
+
+def lockstep_batched(env, oracles, steps, seed, stream="fight", check_obs_every=1, min_deaths=0):
+    E, cap = env.n_envs, env.capacity
+    rngs = [np.random.RandomState(seed * 1000 + e) for e in range(E)]
+    deaths = 0
+    for s in range(steps):
+        num = env.get_num()
+        for e, o in enumerate(oracles):
+            assert [o.get_num(0), o.get_num(1)] == list(num[e]), "num differs env %d step %d" % (e, s)
+        if num.min() == 0:
+            break
+        if check_obs_every and s % check_obs_every == 0:
+            view, feat = env.observe()
+            view, feat = view.cpu().numpy(), feat.cpu().numpy()
+            for e, o in enumerate(oracles):
+                for g in range(2):
+                    v, f = o.get_observation(g)
+                    assert_same("view[e%d g%d]" % (e, g), v, view[e, g, :num[e, g]], s)
+                    assert_same("feat[e%d g%d]" % (e, g), f, feat[e, g, :num[e, g]], s)
+        pos = env.get("pos")
+        actions = np.zeros((E, 2, cap), np.int32)
+        for e, o in enumerate(oracles):
+            for g in range(2):
+                n = num[e, g]
+                assert_same("pos[e%d g%d]" % (e, g), o.get_pos(g), pos[e, g, :n], s)
+                a = fight_actions(rngs[e], pos[e, g, :n], env.map_size) if stream == "fight" \
+                    else uniform_actions(rngs[e], n)
+                actions[e, g, :n] = a
+                o.set_action(g, a)
+        reward, alive, done, mean = env.step(torch.from_numpy(actions).cuda())
+        reward, alive, done, mean = reward.cpu().numpy(), alive.cpu().numpy(), done.cpu().numpy(), mean.cpu().numpy()
+        for e, o in enumerate(oracles):
+            d = o.step()
+            assert bool(done[e]) == d, "done differs env %d step %d" % (e, s)
+            for g in range(2):
+                n = num[e, g]
+                assert_same("reward[e%d g%d]" % (e, g), o.get_reward(g), reward[e, g, :n], s)
+                al = o.get_alive(g)
+                assert_same("alive[e%d g%d]" % (e, g), al, alive[e, g, :n].astype(bool), s)
+                deaths += int((~al).sum())
+                ref_mean = o.mean_action(actions[e, g, :n])
+                np.testing.assert_allclose(mean[e, g], ref_mean, rtol=1e-6, atol=0)   # north_star tolerance
+            o.clear_dead()
+        hp = env.get("hp")
+        num2 = env.get_num()
+        for e, o in enumerate(oracles):
+            for g in range(2):
+                assert_same("hp[e%d g%d]" % (e, g), o.get_hp(g), hp[e, g, :num2[e, g]], s)
+        if done.any():
+            break
+    assert deaths >= min_deaths, deaths
+    return deaths
+
+
+def test_batched_envs_with_independent_action_streams():
+    env, oracles = make(6)
+    lockstep_batched(env, oracles, steps=150, seed=1, min_deaths=50)
+
+
+def test_batched_uniform_stream():
+    env, oracles = make(3)
+    lockstep_batched(env, oracles, steps=40, seed=2, stream="uniform")
+
+
+def test_batched_80x80_512v512():
+    env, oracles = make(2, map_size=80, cap=512, pos=c4_positions())
+    lockstep_batched(env, oracles, steps=40, seed=3, check_obs_every=8, min_deaths=20)
+
+
+def test_batched_ragged_capacity():
+    """capacity not a multiple of the store chunk; n < capacity from the start"""
+    left, right = generate_map_positions(40)
+    env, oracles = make(2, cap=36, pos=(left[:29], right[:33]))
+    assert env.capacity == 36
+    lockstep_batched(env, oracles, steps=100, seed=4, min_deaths=1)
+
+
+def test_mean_action_kernel_matches_numpy():
+    from mfmarl_b200 import mean_action
+    rng = np.random.RandomState(0)
+    rows, cap = 37, 100
+    acts = rng.randint(0, 21, size=(rows, cap)).astype(np.int32)
+    num = rng.randint(1, cap + 1, size=rows).astype(np.int32)
+    num[0] = cap
+    out = mean_action(torch.from_numpy(acts).cuda(), torch.from_numpy(num).cuda()).cpu().numpy()
+    for r in range(rows):
+        # senario_battle.py:141 -- np.mean(one_hot(acts)) in float64, fed to the nets as fp32
+        ref = np.mean(np.eye(21)[acts[r, :num[r]]], axis=0)
+        np.testing.assert_allclose(out[r], ref, rtol=1e-6, atol=0)
+        assert abs(out[r].sum() - 1.0) < 1e-5
+
+
+def test_philox_results_do_not_depend_on_sharding():
+    """Philox is keyed by the global env id: a shard that owns envs [2, 4) reproduces envs 2, 3 of the
+    4-env engine exactly (multi-GPU sharding)."""
+    from mfmarl_b200 import BatchedGridWorld
+    left, right = generate_map_positions(40)
+
+    def run(E, base):
+        env = BatchedGridWorld(E, rng="philox", seed=7, env_base=base)
+        env.reset(); env.add_agents(0, left); env.add_agents(1, right)
+        outs = []
+        for s in range(60):
+            pos, num = env.get("pos"), env.get_num()
+            acts = np.zeros((E, 2, 64), np.int32)
+            for e in range(E):
+                r = np.random.RandomState(100 * (base + e) + s)
+                for g in range(2):
+                    acts[e, g, :num[e, g]] = fight_actions(r, pos[e, g, :num[e, g]], 40)
+            reward, alive, done, _ = env.step(torch.from_numpy(acts).cuda())
+            outs.append((reward.cpu().numpy().copy(), alive.cpu().numpy().copy(), env.get("pos"), env.get("hp")))
+        return outs
+
+    full, shard = run(4, 0), run(2, 2)
+    deaths = 0
+    for (r4, a4, p4, h4), (r2, a2, p2, h2) in zip(full, shard):
+        assert_same("reward", r4[2:], r2, 0); assert_same("alive", a4[2:], a2, 0)
+        assert_same("pos", p4[2:], p2, 0); assert_same("hp", h4[2:], h2, 0)
+        deaths += int((a4 == 0).sum())
+    assert deaths > 0
+
+
+def test_auto_reset_replaces_the_armies():
+    from mfmarl_b200 import BatchedGridWorld
+    left, right = generate_map_positions(40)
+    env = BatchedGridWorld(2, max_steps=5, auto_reset=True)
+    env.reset(); env.add_agents(0, left); env.add_agents(1, right)
+    pos0, id0 = env.get("pos").copy(), env.get("id").copy()
+    rng = np.random.RandomState(0)
+    for s in range(5):
+        acts = torch.from_numpy(rng.randint(0, 13, size=(2, 2, 64)).astype(np.int32)).cuda()
+        env.step(acts)
+        if s < 4:
+            assert (env.get("step_ct") == s + 1).all()
+            assert not np.array_equal(env.get("pos"), pos0)
+    assert (env.get("step_ct") == 0).all()
+    assert np.array_equal(env.get("pos"), pos0) and np.array_equal(env.get("id"), id0)
+    assert (env.get("hp") == 10).all() and (env.get_num() == 64).all()
+    assert (env.get("agent_steps") == 5 * 128).all()
+
+
+def test_full_size_properties_4096_envs():
+    """BASELINE config 3 at full size (4096 envs x 64 v 64): size-independent properties.
+    (1) every env given the same actions equals env 0 (checksum of checksums), and env 0 equals the oracle;
+    (2) one agent per cell, hp <= 10, alive bookkeeping; (3) observation identities per agent row."""
+    E = 4096
+    env, oracles = make(E)
+    oracles = oracles[:1]
+    o = oracles[0]
+    rng = np.random.RandomState(5)
+    for s in range(12):
+        num = env.get_num()
+        assert (num == num[0]).all()
+        pos = env.get("pos")
+        acts1 = np.zeros((1, 2, 64), np.int32)
+        for g in range(2):
+            acts1[0, g, :num[0, g]] = fight_actions(rng, pos[0, g, :num[0, g]], 40)
+            o.set_action(g, acts1[0, g, :num[0, g]])
+        view, feat = env.observe()
+        if s % 4 == 0:
+            # (3) own-has at the view centre, minimap channels sum to 1 (+1 self marker), id bits
+            n0 = int(num[0, 0])
+            v = view[:, 0, :n0]
+            assert bool((v[:, :, 6, 6, 1] == 1).all())
+            assert torch.allclose(v[..., 3].sum(dim=(-1, -2)), torch.full_like(v[:, :, 0, 0, 0], 2.0), atol=1e-5)
+            assert torch.allclose(v[..., 6].sum(dim=(-1, -2)), torch.full_like(v[:, :, 0, 0, 0], 2.0), atol=1e-5)
+            # (1) all envs identical to env 0
+            assert bool((view[:, :, :n0] == view[0:1, :, :n0]).all())
+            assert bool((feat[:, :, :n0] == feat[0:1, :, :n0]).all())
+        actions = torch.from_numpy(acts1).cuda().expand(E, 2, 64).contiguous()
+        reward, alive, done, mean = env.step(actions)
+        d = o.step()
+        assert bool((done == int(d)).all())
+        for g in range(2):
+            n = num[0, g]
+            assert_same("reward", o.get_reward(g), reward[0, g, :n].cpu().numpy(), s)
+            assert bool((reward[:, g, :n] == reward[0:1, g, :n]).all())
+            assert bool((alive[:, g, :n] == alive[0:1, g, :n]).all())
+        o.clear_dead()
+        # (2) invariants on the whole batch
+        pos, hp, num2 = env.get("pos"), env.get("hp"), env.get_num()
+        assert hp.max() <= 10.0
+        assert (num2 == [o.get_num(0), o.get_num(1)]).all()
+        cells = pos[..., 1] * 40 + pos[..., 0]
+        for e in (0, 1, E // 2, E - 1):
+            live = np.concatenate([cells[e, g, :num2[e, g]] for g in range(2)])
+            assert len(np.unique(live)) == len(live), "two agents in one cell"
