@@ -384,16 +384,26 @@ __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState
 // K1: observations.  One CTA per (env, group, tile of agents).
 //
 // The per-agent view is 13*13*7 fp32 = 4732 B, >90 % zeros, and it is the whole of the HBM traffic
-// of the path.  Each warp composes one agent's 4732 B row in shared memory (7 conflict-free STS per
-// view cell: stride 7 words is coprime with the 32 banks), rows are packed back to back in a staging
-// buffer, and one elected thread hands each 8-agent chunk (37 856 B) to the TMA engine with a single
-// cp.async.bulk shared->global store; two staging buffers keep a store in flight while the next
-// chunk is composed.  The map is never re-read from HBM: the occupancy/hp grid and both minimaps are
-// rebuilt per CTA in shared memory from the SoA agent arrays.
+// of the path.  Rows are composed in shared memory and streamed out by the TMA engine: 8 agents'
+// rows sit back to back in a staging buffer (37 856 B, a multiple of 16) and one elected thread
+// hands the chunk to a single cp.async.bulk shared->global store; two staging buffers keep a store
+// in flight while the next chunk is composed.
+//
+// Composition is incremental.  At CTA start every staging row is filled once with the BACKGROUND that
+// all agents of the group share (zeros + the two minimap channels).  For each agent its warp then only
+//   - scans the 169 view cells against the shared-memory occupancy grid (lane = cell, 6 passes),
+//   - writes the few cells that differ from the background (wall / own / other has+hp) and restores
+//     the ones the previous agent of that row had written (2-bit kind per cell kept in a register),
+//   - moves the "+1" self marker of the two minimap channels.
+// All shared-memory stores are stride-7-word (coprime with the 32 banks): conflict-free.
+// The map is never re-read from HBM: occupancy/hp grid and both minimaps are rebuilt per CTA from the
+// SoA agent arrays.
 // ----------------------------------------------------------------------------------------------
 constexpr int kObsThreads = 256, kObsWarps = kObsThreads / 32;
 constexpr int kObsChunk = 8;                                   // agents per bulk store (multiple of 4)
 constexpr int kObsStageBytes = kObsChunk * kViewRow * 4;       // 37 856, a multiple of 16
+constexpr int kObsPasses = (kViewCells + 31) / 32;             // 6
+static_assert(kObsChunk == kObsWarps, "one warp composes one row of a chunk");
 
 struct ObsSmem { int stage0, stage1, hp10, mini, cnt, kind, total; };
 __host__ __device__ inline ObsSmem obs_smem_layout(int W, int H) {
@@ -403,7 +413,7 @@ __host__ __device__ inline ObsSmem obs_smem_layout(int W, int H) {
     L.hp10 = o;   o += 4 * W * H;
     L.mini = o;   o += 4 * 2 * kViewCells;
     L.cnt = o;    o += 4 * 2 * kViewCells;
-    L.kind = o;   o += W * H;
+    L.kind = o;   o += (W * H + 3) & ~3;
     L.total = (o + 127) & ~127;
     return L;
 }
@@ -424,11 +434,14 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// cell kinds in the CTA-local grid, relative to the observing group
+enum : uint32_t { KIND_EMPTY = 0, KIND_WALL = 1, KIND_OWN = 2, KIND_OTHER = 3 };
+
 __global__ void __launch_bounds__(kObsThreads, 2)
 k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO io) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const ObsSmem L = obs_smem_layout(P.W, P.H);
-    float *s_stage[2] = {(float *)(smem_raw + L.stage0), (float *)(smem_raw + L.stage1)};
+    float *const s_stage0 = (float *)(smem_raw + L.stage0), *const s_stage1 = (float *)(smem_raw + L.stage1);
     float *s_hp10 = (float *)(smem_raw + L.hp10);
     float *s_mini = (float *)(smem_raw + L.mini);
     int *s_cnt = (int *)(smem_raw + L.cnt);
@@ -448,20 +461,27 @@ k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO i
     if (a_begin >= ng) return;
     const int a_end = min(ng, a_begin + io.tile_agents);
     const size_t ebase = (size_t)e * 2 * cap;
+    const size_t gbase = ebase + (size_t)g * cap;
 
-    // ---- occupancy (kind: 0 empty, 1 wall, 2 group0, 3 group1), hp/10 per cell, minimap counts ----
+    // ---- occupancy grid (kind per cell), hp/10 per cell, minimap counts ----
     const uint8_t *walls = S.walls + (size_t)e * P.wall_stride;
-    for (int c = tid; c < cells; c += kObsThreads) s_kind[c] = walls[c];
+    if ((cells & 3) == 0) {
+        for (int c = tid; c < (cells >> 2); c += kObsThreads)
+            ((uint32_t *)s_kind)[c] = ((const uint32_t *)walls)[c];
+    } else {
+        for (int c = tid; c < cells; c += kObsThreads) s_kind[c] = walls[c];
+    }
     for (int c = tid; c < 2 * kViewCells; c += kObsThreads) s_cnt[c] = 0;
     __syncthreads();
+    const uint8_t *lut = S.mini_lut;   // [W] x / scale_w, then [H] (y / scale_h) * 13
     for (int s = tid; s < 2 * cap; s += kObsThreads) {
         const int gg = s >= cap, i = s - gg * cap;
         if (i < (gg ? n1 : n0)) {
             const int p = S.pos[ebase + s], x = pos_x(p), y = pos_y(p);
             // minimap counts every agent still in the list, dead or not (GridWorld.cc:359-370)
-            atomicAdd(&s_cnt[gg * kViewCells + (y / P.scale_h) * kView + x / P.scale_w], 1);
+            atomicAdd(&s_cnt[gg * kViewCells + lut[W + y] + lut[x]], 1);
             if (!st_dead(S.state[ebase + s])) {
-                s_kind[y * W + x] = (uint8_t)(2 + gg);
+                s_kind[y * W + x] = (uint8_t)(gg == g ? KIND_OWN : KIND_OTHER);
                 s_hp10[y * W + x] = __fdiv_rn(S.hp[ebase + s], P.hp);   // Map.cc:208
             }
         }
@@ -471,70 +491,101 @@ k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO i
         const int gg = c >= kViewCells;
         s_mini[c] = __fdiv_rn((float)s_cnt[c], (float)(gg ? n1 : n0));  // GridWorld.cc:372-377
     }
+    __syncthreads();
+    const float *mini_own = s_mini + g * kViewCells, *mini_oth = s_mini + (1 - g) * kViewCells;
 
-    // ---- features (GridWorld.cc:411-421): coalesced over the tile's flat [agents * feature_size] block ----
-    {
-        const int FS = P.feature_size, emb = P.embedding_size, n_action = P.n_move + P.n_attack;
-        float *fout = io.feature + (ebase + (size_t)g * cap + a_begin) * FS;
-        const int nf = (a_end - a_begin) * FS;
-        for (int f = tid; f < nf; f += kObsThreads) {
-            const int al = f / FS, k = f - al * FS;
-            const size_t s = ebase + (size_t)g * cap + a_begin + al;
-            float v;
-            if (k < emb) v = (float)((S.id[s] >> k) & 1);                       // GridWorld.h:162-171
-            else if (k < emb + n_action) v = ((int)st_act(S.state[s]) == k - emb) ? 1.0f : 0.0f;
-            else if (k == emb + n_action) v = S.last_rew[s];
-            else if (k == emb + n_action + 1) v = __fdiv_rn((float)pos_x(S.pos[s]), (float)W);
-            else v = __fdiv_rn((float)pos_y(S.pos[s]), (float)H);
-            fout[f] = v;
+    // ---- per-lane view geometry: cell c = pass * 32 + lane -> (dx, dy) relative to the agent, disc bit ----
+    int rel[kObsPasses];
+    uint32_t disc = 0;
+#pragma unroll
+    for (int it = 0; it < kObsPasses; it++) {
+        const int c = it * 32 + lane;
+        const int vy = c / kView, vx = c - vy * kView;
+        rel[it] = ((vx - kView / 2) & 0xFFFF) | ((vy - kView / 2) << 16);
+        if (c < kViewCells && ((P.disc[it] >> lane) & 1u)) disc |= 1u << it;
+    }
+
+    // ---- background: this warp's row of both staging buffers = zeros + minimap channels ----
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+        float *row = (b ? s_stage1 : s_stage0) + warp * kViewRow;
+#pragma unroll
+        for (int it = 0; it < kObsPasses; it++) {
+            const int c = it * 32 + lane;
+            if (c < kViewCells) {
+                float *o = row + c * kChan;
+                o[0] = 0.0f; o[1] = 0.0f; o[2] = 0.0f; o[4] = 0.0f; o[5] = 0.0f;
+                o[3] = mini_own[c]; o[6] = mini_oth[c];
+            }
         }
     }
-    __syncthreads();
 
-    // ---- views: compose in smem, stream out with TMA bulk stores ----
-    const float *mini_own = s_mini + g * kViewCells, *mini_oth = s_mini + (1 - g) * kViewCells;
-    const uint8_t own_kind = (uint8_t)(2 + g), oth_kind = (uint8_t)(3 - g);
-    float *vout = io.view + (ebase + (size_t)g * cap) * kViewRow;
+    // ---- stream the tile: compose (delta vs previous occupant of the row), bulk-store ----
+    const int FS = P.feature_size, emb = P.embedding_size, n_action = P.n_move + P.n_attack;
+    float *vout = io.view + gbase * kViewRow;
+    float *fout = io.feature + gbase * FS;
+    uint32_t kinds_prev1 = 0, kinds_prev2 = 0;   // 2-bit kind per pass, for the row in the other / this buffer
+    int self_prev1 = -1, self_prev2 = -1;
     int buf = 0;
     for (int c0 = a_begin; c0 < a_end; c0 += kObsChunk, buf ^= 1) {
         const int cn = min(kObsChunk, a_end - c0);
         // the store issued two chunks ago read this buffer: wait until its smem reads are done
         if (tid == 0) bulk_wait_read<1>();
         __syncthreads();
+        uint32_t kinds_new = 0;
+        int self_new = -1;
         if (warp < cn) {
-            const size_t s = ebase + (size_t)g * cap + c0 + warp;
+            const size_t s = gbase + c0 + warp;
             const int p = S.pos[s], ax = pos_x(p), ay = pos_y(p);
-            const int self_cell = (ay / P.scale_h) * kView + ax / P.scale_w;
-            float *row = s_stage[buf] + warp * kViewRow;
+            const int id = S.id[s];
+            const uint32_t st = S.state[s];
+            const float last_rew = S.last_rew[s];
+            float *row = (buf ? s_stage1 : s_stage0) + warp * kViewRow;
 #pragma unroll
-            for (int it = 0; it < (kViewCells + 31) / 32; it++) {
-                const int c = it * 32 + lane;
-                if (c < kViewCells) {
-                    const int vy = c / kView, vx = c - vy * kView;
-                    const int x = ax - kView / 2 + vx, y = ay - kView / 2 + vy;
-                    const bool in = ((P.disc[c >> 5] >> (c & 31)) & 1u) && x >= 0 && x < W && y >= 0 && y < H;
-                    const int cell = in ? y * W + x : 0;
-                    const uint8_t kind = in ? s_kind[cell] : (uint8_t)0;
-                    const float hp = s_hp10[cell];
-                    const bool own = kind == own_kind, oth = kind == oth_kind;
-                    float *o = row + c * kChan;
-                    o[0] = kind == 1 ? 1.0f : 0.0f;
-                    o[1] = own ? 1.0f : 0.0f;
-                    o[2] = own ? hp : 0.0f;
-                    o[3] = c == self_cell ? mini_own[c] + 1.0f : mini_own[c];   // GridWorld.cc:404-407
-                    o[4] = oth ? 1.0f : 0.0f;
-                    o[5] = oth ? hp : 0.0f;
-                    o[6] = c == self_cell ? mini_oth[c] + 1.0f : mini_oth[c];
+            for (int it = 0; it < kObsPasses; it++) {
+                const int x = ax + (int)(short)(rel[it] & 0xFFFF), y = ay + (rel[it] >> 16);
+                const bool in = ((disc >> it) & 1u) && (unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H;
+                const int cell = in ? y * W + x : 0;
+                const uint32_t k = in ? (uint32_t)s_kind[cell] : (uint32_t)KIND_EMPTY;
+                const float hp = s_hp10[cell];
+                const uint32_t old = (kinds_prev2 >> (2 * it)) & 3u;
+                float *o = row + (it * 32 + lane) * kChan;
+                if (old == KIND_WALL || k == KIND_WALL) o[0] = k == KIND_WALL ? 1.0f : 0.0f;
+                if (old == KIND_OWN || k == KIND_OWN) { o[1] = k == KIND_OWN ? 1.0f : 0.0f; o[2] = k == KIND_OWN ? hp : 0.0f; }
+                if (old == KIND_OTHER || k == KIND_OTHER) { o[4] = k == KIND_OTHER ? 1.0f : 0.0f; o[5] = k == KIND_OTHER ? hp : 0.0f; }
+                kinds_new |= k << (2 * it);
+            }
+            // self marker in BOTH minimap channels (GridWorld.cc:396-408): move it
+            self_new = lut[W + ay] + lut[ax];
+            if (lane == 0) {
+                if (self_prev2 >= 0) {
+                    row[self_prev2 * kChan + 3] = mini_own[self_prev2];
+                    row[self_prev2 * kChan + 6] = mini_oth[self_prev2];
                 }
+                row[self_new * kChan + 3] = mini_own[self_new] + 1.0f;
+                row[self_new * kChan + 6] = mini_oth[self_new] + 1.0f;
+            }
+            // features (GridWorld.cc:411-421): id bits LSB first, one-hot last action, last reward, x/W, y/H
+            float *f = fout + (size_t)(c0 + warp) * FS;
+            for (int k = lane; k < FS; k += 32) {
+                float v;
+                if (k < emb) v = (float)((id >> k) & 1);                      // GridWorld.h:162-171
+                else if (k < emb + n_action) v = ((int)st_act(st) == k - emb) ? 1.0f : 0.0f;
+                else if (k == emb + n_action) v = last_rew;
+                else if (k == emb + n_action + 1) v = __fdiv_rn((float)ax, (float)W);
+                else v = __fdiv_rn((float)ay, (float)H);
+                f[k] = v;
             }
         }
+        kinds_prev2 = kinds_prev1; kinds_prev1 = kinds_new;
+        self_prev2 = self_prev1; self_prev1 = self_new;
         fence_proxy_async_smem();   // make the generic-proxy smem writes visible to the async proxy
         __syncthreads();
         if (tid == 0) {
             // rows are 4732 B (= 12 mod 16): a ragged tail is rounded up to 16 B; the <= 12 spill bytes land
             // in the next, unused row of the same [cap] block (cap is a multiple of 4, see engine.cu)
             const uint32_t bytes = ((uint32_t)cn * kViewRow * 4 + 15u) & ~15u;
-            bulk_store_s2g(vout + (size_t)c0 * kViewRow, s_stage[buf], bytes);
+            bulk_store_s2g(vout + (size_t)c0 * kViewRow, buf ? s_stage1 : s_stage0, bytes);
             bulk_commit();
         }
     }

@@ -71,6 +71,7 @@ struct BattleState {   // device pointers
     int32_t *pos; float *hp; int32_t *id; uint32_t *state; float *next_rew; float *last_rew;
     int32_t *num; int32_t *dead_ct; uint32_t *rng; int32_t *step_ct; int32_t *id_counter;
     uint8_t *walls;
+    uint8_t *mini_lut;                 // [W] x / scale_w, then [H] (y / scale_h) * view: minimap cell of a position
     unsigned long long *agent_steps;   // [E] running count of agents taken through a step (statistic)
     // episode template for auto-reset
     int32_t *init_pos; int32_t *init_num;   // [2][cap], [2]

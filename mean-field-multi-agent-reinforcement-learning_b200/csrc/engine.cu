@@ -108,6 +108,14 @@ Engine::Engine(const EngineConfig &cfg) : cfg_(cfg) {
     MF_CUDA(cudaMalloc(&S_.id_counter, E * sizeof(int32_t)));
     MF_CUDA(cudaMalloc(&S_.walls, (size_t)P_.W * P_.H));
     MF_CUDA(cudaMalloc(&S_.init_num, 2 * sizeof(int32_t)));
+    {   // minimap cell of a position, as a table: the kernels never divide by the runtime scale
+        if ((P_.H - 1) / P_.scale_h * kView + (P_.W - 1) / P_.scale_w > 255) throw Fatal("minimap table overflow");
+        std::vector<uint8_t> lut((size_t)P_.W + P_.H);
+        for (int x = 0; x < P_.W; x++) lut[x] = (uint8_t)(x / P_.scale_w);
+        for (int y = 0; y < P_.H; y++) lut[(size_t)P_.W + y] = (uint8_t)((y / P_.scale_h) * kView);
+        MF_CUDA(cudaMalloc(&S_.mini_lut, lut.size()));
+        MF_CUDA(cudaMemcpy(S_.mini_lut, lut.data(), lut.size(), cudaMemcpyHostToDevice));
+    }
     MF_CUDA(cudaMalloc(&S_.agent_steps, E * sizeof(unsigned long long)));
     MF_CUDA(cudaMemset(S_.agent_steps, 0, E * sizeof(unsigned long long)));
     MF_CUDA(cudaMemset(S_.num, 0, E * 2 * sizeof(int32_t)));
@@ -123,7 +131,7 @@ Engine::Engine(const EngineConfig &cfg) : cfg_(cfg) {
 Engine::~Engine() {
     free_state();
     cudaFree(S_.num); cudaFree(S_.dead_ct); cudaFree(S_.rng); cudaFree(S_.step_ct);
-    cudaFree(S_.id_counter); cudaFree(S_.walls); cudaFree(S_.init_num); cudaFree(S_.agent_steps);
+    cudaFree(S_.id_counter); cudaFree(S_.walls); cudaFree(S_.init_num); cudaFree(S_.agent_steps); cudaFree(S_.mini_lut);
 }
 
 void Engine::alloc_state(int cap) {
