@@ -91,6 +91,25 @@ int mfb_step_host(mfb_engine *eng, const int32_t *h_actions, float *h_reward, ui
 
 const char *mfb_last_error(void);
 
+/* ---- K6: Ising tabular mean-field Q-learning, one fused sweep over a batch of lattices -----------------
+ * Replaces the loop body of main_MFQ_Ising.py:105-134 (Boltzmann action per site from Q[i, s, :] with
+ * s = up-neighbour count on the old lattice, spin <- action, reward on the new lattice
+ * (examples/ising_model/Ising.py:101-111), Q[i,s,a] += lr (r - Q[i,s,a])) for `n_lattices` independent
+ * side x side tori.  All pointers are DEVICE memory.
+ *   dtype          0 = fp32 (production), 1 = fp64 (the reference's precision; used for trajectory parity)
+ *   d_spins        int8 [n_lattices][side][side]      in/out, values {0, 1}
+ *   d_q            T    [n_lattices][5][side*side][2]  in/out, entry (s, a) of site i at ((s*N + i)*2 + a)
+ *   d_uniforms     T    [n_lattices][side*side] or NULL: injected uniforms (test hook; a = [u >= p0]);
+ *                  NULL = Philox4x32-10 keyed by (seed, lattice_base + lattice) x (column, row band, step)
+ *   d_update_mask  uint8[n_lattices][side*side] or NULL: the act group (act_rate < 1); NULL = all sites
+ *   d_n_up         int32[n_lattices]  out: up spins after the sweep (order parameter = |2 up - N| / N)
+ *   d_reward_sum,
+ *   d_mse          T    [n_lattices]  out (may be NULL): sum of rewards; mse vs reward_target / N
+ * Returns 0, or -1 with the message in mfb_last_error(). */
+int mfi_step(int dtype, int n_lattices, int side, int8_t *d_spins, void *d_q, double temperature, double lr,
+             const void *d_uniforms, const uint8_t *d_update_mask, unsigned seed, unsigned lattice_base,
+             unsigned step, int32_t *d_n_up, void *d_reward_sum, void *d_mse, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

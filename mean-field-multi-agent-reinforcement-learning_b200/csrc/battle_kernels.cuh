@@ -14,6 +14,7 @@
 #include <stdint.h>
 
 #include "battle_types.h"
+#include "rng.cuh"
 
 namespace mfmarl {
 
@@ -29,24 +30,6 @@ __device__ __forceinline__ uint32_t st_act(uint32_t s) { return (s >> 16) & 0xFF
 __device__ __forceinline__ uint32_t st_with_op(uint32_t s, uint32_t op) { return (s & ~0xFF00u) | (op << 8); }
 __device__ __forceinline__ uint32_t make_state(uint32_t dead, uint32_t op, uint32_t act) {
     return dead | (op << 8) | (act << 16);
-}
-
-// Philox4x32-10 (Salmon et al. 2011), counter-based: the draw for (seed, env, step, i) needs no state.
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-    for (int r = 0; r < 10; r++) {
-        uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-        uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-        key.x += W0; key.y += W1;
-    }
-    return ctr;
-}
-
-// minstd_rand0: x <- 16807 x mod (2^31 - 1)   (libstdc++ std::default_random_engine, GridWorld.h:106)
-__device__ __forceinline__ uint32_t minstd_next(uint32_t s) {
-    return (uint32_t)(((uint64_t)s * 16807ull) % 2147483647ull);
 }
 
 // Block-wide exclusive scan of a predicate (ballot + popc inside each warp, per-warp totals through

@@ -1,0 +1,151 @@
+"""Ising-model tabular mean-field Q-learning on the GPU (kernel K6, C ABI `mfi_step`).
+
+`IsingMFQ` holds a batch of B independent L x L tori (spins int8 [B, L, L], Q [B, 5, L*L, 2]) in HBM and
+advances all of them by one fused step per call: Boltzmann action per site, spin update, reward, Q update
+-- the loop body of the reference's main_MFQ_Ising.py:105-134.  `run` re-expresses that script's outer loop
+(temperature schedule :108-112, order-parameter stagnation stop :149-156) over the fused step, with the
+same command-line flags (:13-26).
+"""
+import argparse
+import ctypes
+import time
+
+import numpy as np
+import torch
+
+from .lib import check, load_library
+
+_DTYPES = {torch.float32: 0, torch.float64: 1}
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class IsingMFQ:
+    def __init__(self, n_lattices, side, dtype=torch.float32, device=None, seed=13, lr=0.1, lattice_base=0,
+                 spins=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("IsingMFQ needs a CUDA device: there is no CPU fallback")
+        self.lib = load_library()
+        self.lib.mfi_step.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_uint, ctypes.c_uint, ctypes.c_uint, ctypes.c_void_p,
+                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        self.lib.mfi_step.restype = ctypes.c_int
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.B, self.L, self.N = n_lattices, side, side * side
+        self.dtype, self.seed, self.lr, self.lattice_base = dtype, seed, lr, lattice_base
+        self.t = 0
+        if spins is None:   # Bernoulli(0.5) spins (Ising.py:79-99 draws np.random.choice(2) per agent)
+            gen = torch.Generator(device=self.device)
+            gen.manual_seed(seed + 7919 * lattice_base)
+            spins = torch.randint(0, 2, (n_lattices, side, side), generator=gen, device=self.device,
+                                  dtype=torch.int8)
+        self.spins = torch.as_tensor(spins, dtype=torch.int8, device=self.device).contiguous().clone()
+        assert tuple(self.spins.shape) == (n_lattices, side, side)
+        self.Q = torch.zeros((n_lattices, 5, self.N, 2), dtype=dtype, device=self.device)   # main_MFQ_Ising.py:92
+        self.n_up = torch.zeros((n_lattices,), dtype=torch.int32, device=self.device)
+        self.reward_sum = torch.zeros((n_lattices,), dtype=dtype, device=self.device)
+        self.mse = torch.zeros((n_lattices,), dtype=dtype, device=self.device)
+
+    def step(self, temperature, uniforms=None, update_mask=None, stats=True):
+        """One fused sweep.  uniforms [B, N] (same dtype) injects the Boltzmann draws (test hook);
+        update_mask uint8 [B, N] restricts the Q update to the act group (act_rate < 1)."""
+        if uniforms is not None:
+            assert uniforms.dtype == self.dtype and uniforms.is_cuda and uniforms.is_contiguous()
+        if update_mask is not None:
+            assert update_mask.dtype == torch.uint8 and update_mask.is_cuda and update_mask.is_contiguous()
+        with torch.cuda.device(self.device):
+            check(self.lib.mfi_step(_DTYPES[self.dtype], self.B, self.L, _ptr(self.spins), _ptr(self.Q),
+                                    float(temperature), float(self.lr), _ptr(uniforms), _ptr(update_mask),
+                                    self.seed, self.lattice_base, self.t, _ptr(self.n_up),
+                                    _ptr(self.reward_sum) if stats else None, _ptr(self.mse) if stats else None,
+                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        self.t += 1
+        return self.n_up, self.reward_sum, self.mse
+
+    def order_param(self):
+        """|n_up - n_down| / N per lattice (core.py:106-110), from the last step's up counts."""
+        up = self.n_up.to(torch.float64)
+        # tensor / tensor: a true IEEE division (torch turns `/ python_scalar` into a reciprocal multiply)
+        return (2 * up - self.N).abs() / torch.full_like(up, float(self.N))
+
+    def q_table(self):
+        """Q as the reference lays it out: [B, N, 5, 2]."""
+        return self.Q.permute(0, 2, 1, 3).contiguous()
+
+
+def run(argv=None):
+    """`python -m mfmarl_b200.ising -n 400 -t 0.8`: the experiment of main_MFQ_Ising.py on the GPU."""
+    ap = argparse.ArgumentParser(description="Ising tabular MFQ (B200)")
+    ap.add_argument("-n", "--num_agents", default=100, type=int)
+    ap.add_argument("-t", "--temperature", default=1, type=float)
+    ap.add_argument("-epi", "--episode", default=1, type=int)
+    ap.add_argument("-ts", "--time_steps", default=10000, type=int)
+    ap.add_argument("-lr", "--learning_rate", default=0.1, type=float)
+    ap.add_argument("-dr", "--decay_rate", default=0.99, type=float)
+    ap.add_argument("-dg", "--decay_gap", default=2000, type=int)
+    ap.add_argument("-ac", "--act_rate", default=1.0, type=float)
+    ap.add_argument("--lattices", default=1, type=int, help="independent lattices stepped together")
+    ap.add_argument("--quiet", action="store_true")
+    args = ap.parse_args(argv)
+    side = int(np.ceil(np.sqrt(args.num_agents)))
+    assert side * side == args.num_agents, "num_agents must be a perfect square"
+    results = []
+    for ep in range(args.episode):
+        model = IsingMFQ(args.lattices, side, seed=13 + ep, lr=args.learning_rate)
+        N = model.N
+        gen = torch.Generator(device=model.device); gen.manual_seed(1000 + ep)
+        current_t, max_order, max_step, done_, t0 = 0.3, 0.0, 0, 0, time.time()
+        for t in range(args.time_steps):
+            if t % args.decay_gap == 0:
+                current_t *= args.decay_rate
+            if current_t < args.temperature:
+                current_t = args.temperature
+            mask = None
+            if args.act_rate < 1.0:   # a random act group of int(act_rate * N) sites (main_MFQ_Ising.py:126)
+                k = int(args.act_rate * N)
+                order = torch.rand((args.lattices, N), generator=gen, device=model.device).argsort(dim=1)
+                mask = torch.zeros((args.lattices, N), dtype=torch.uint8, device=model.device)
+                mask.scatter_(1, order[:, :k], 1)
+            n_up, rsum, mse = model.step(current_t, update_mask=mask)
+            order_param = float(model.order_param()[0])
+            ups = int(n_up[0])
+            if order_param > max_order:
+                max_order, max_step = order_param, t
+            done_ = done_ + 1 if abs(max_order - order_param) < 0.001 else 0
+            if done_ == 500:
+                break
+            if not args.quiet:
+                print("E: %d/%d, reward = %f, mse = %f, Order = %f, Up = %d, Down = %d"
+                      % (ep, t, float(rsum[0]), float(mse[0]), order_param, ups, N - ups))
+        print("Episode: %d, MaxO = %f at %d (%.1f site-steps/s)"
+              % (ep, max_order, max_step, (t + 1) * N * args.lattices / (time.time() - t0)))
+        results.append((max_order, max_step))
+    return results
+
+
+def ising_smoke():
+    """One small sweep on cuda:0 checked against the numpy oracle (used by __graft_entry__.smoke)."""
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.normpath(os.path.join(here, "..", "..", "..", "oracle")))
+    import ising_oracle
+    rng = np.random.RandomState(0)
+    B, L = 3, 20
+    spins = rng.randint(0, 2, size=(B, L, L)).astype(np.int8)
+    m = IsingMFQ(B, L, dtype=torch.float64, device="cuda:0", spins=torch.from_numpy(spins))
+    Q = np.zeros((B, 5, L * L, 2))
+    for t in range(10):
+        u = rng.random_sample((B, L * L))
+        m.step(0.8, uniforms=torch.from_numpy(u).cuda())
+        spins, Q, info = ising_oracle.step(spins, Q, 0.8, 0.1, u)
+        assert np.array_equal(m.spins.cpu().numpy(), spins), "ising spins mismatch at step %d" % t
+        assert np.allclose(m.Q.cpu().numpy(), Q, rtol=1e-12, atol=1e-15), "ising Q mismatch"
+    print("[smoke] ising: 10 sweeps x %d lattices (%dx%d, fp64) match the oracle" % (B, L, L))
+
+
+if __name__ == "__main__":
+    run()
