@@ -35,7 +35,10 @@ WORKLOADS = {
     "c4": dict(name="battle_80x80_512v512_128envs_per_gpu_uniform_actions (BASELINE configs[3] shard)",
                map_size=80, cap=512, envs=128, max_steps=400),
 }
+WORKLOADS["c5"] = dict(name="ising_256x256_x16384_lattices_mfq_T0.8 (BASELINE configs[4])", side=256,
+                       lattices=16384, temperature=0.8, lr=0.1)
 REF_SO = os.path.join(REPO, "oracle", "_ref", "libmagent_ref.so")
+BYTES_PER_SITE = 14   # fp32 Q pair read 8 + Q write 4 + int8 spin read 1 + write 1
 
 
 def placement(wl):
@@ -311,6 +314,111 @@ def run_ours(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# Ising (BASELINE configs[4]): 16384 lattices of 256x256 in total, strong-scaled over the GPUs
+# ------------------------------------------------------------------------------------------------
+def ising_cpu_sample(side, lattices, sweeps, T, lr):
+    """numpy restatement (oracle/ising_oracle.py) on one core: the reference itself is O(N^2) per step and
+    cannot run 256x256."""
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import numpy as np
+    import ising_oracle
+    rng = np.random.RandomState(13)
+    spins = rng.randint(0, 2, size=(lattices, side, side))
+    Q = np.zeros((lattices, 5, side * side, 2))
+    ising_oracle.step(spins, Q, T, lr, rng.random_sample((lattices, side * side)))
+    t0 = time.perf_counter()
+    for _ in range(sweeps):
+        spins, Q, _info = ising_oracle.step(spins, Q, T, lr, rng.random_sample((lattices, side * side)))
+    secs = time.perf_counter() - t0
+    return lattices * side * side * sweeps / secs, secs
+
+
+def run_ising(args):
+    import torch
+    import torch.distributed as dist
+    from mfmarl_b200 import IsingMFQ
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    wl = WORKLOADS["c5"]
+    total = args.envs or wl["lattices"]
+    B, L, T, K, W = total // world, wl["side"], wl["temperature"], args.steps, args.warmup
+    model = IsingMFQ(B, L, seed=13, lr=wl["lr"], lattice_base=rank * B, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(W):
+        model.step(T)
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        t0.record()
+        for _ in range(K):
+            model.step(T)
+        t1.record()
+        barrier()
+    ms = t0.elapsed_time(t1)
+    # e2e: the per-sweep result a driver loop reads (up counts -> order parameter) lands on the host each sweep
+    h_up = torch.empty((B,), dtype=torch.int32).pin_memory()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        n_up, _r, _m = model.step(T)
+        h_up.copy_(n_up, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        sites = B * world * L * L
+        achieved = B * L * L * BYTES_PER_SITE / (ms / K * 1e-3) / 1e9
+        line = {
+            "metric": "ising MFQ site-steps/sec", "value": sites * K / (ms * 1e-3), "unit": "site-steps/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "lattices_total": B * world, "lattices_per_gpu": B, "side": L,
+                       "temperature": T, "lr": wl["lr"], "rng": "philox(seed, lattice, column, band, step)",
+                       "l2": "Q + spins per GPU (%.1f GB) exceed the 126 MB L2" % (B * L * L * 41 / 1e9)},
+            "gpu_launches": K,
+            "roofline": {"bound": "hbm", "kernel": "k_ising", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": ncu_traffic("c5"), "peak_source": peak_src,
+                         "bytes_per_site": BYTES_PER_SITE, "sites_per_launch": B * L * L},
+            "e2e": {"value": sites * K / (e2e_ms * 1e-3), "unit": "site-steps/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": B * 4,
+                    "note": "temperature is a scalar argument; the up counts (order parameter) are read back "
+                            "to pinned host memory every sweep"},
+            "clocks": clocks.summary(),
+            "order_param_mean": float(model.order_param().mean()),
+        }
+        if world == 1 and not args.no_cpu:
+            v, secs = ising_cpu_sample(L, 4, 3, T, wl["lr"])
+            line["cpu_baseline"] = {"value": v, "unit": "site-steps/s", "cores": 1, "kind": "port",
+                                    "sample": "numpy restatement, 4 lattices of %dx%d x 3 sweeps, %.1f s (the "
+                                              "reference's own loop is O(N^2)/step: ~1e4 site-steps/s at 20x20)"
+                                              % (L, L, secs)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU engine on the host cores, same metric / config
 # ------------------------------------------------------------------------------------------------
 def run_reference(args):
@@ -319,6 +427,18 @@ def run_reference(args):
     if rank != 0:
         return
     wl = WORKLOADS[args.workload]
+    if args.workload == "c5":
+        v, secs = ising_cpu_sample(wl["side"], 4, max(1, min(args.steps, 5)), wl["temperature"], wl["lr"])
+        print(json.dumps({"impl": "reference", "metric": "ising MFQ site-steps/sec", "value": v,
+                          "unit": "site-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": secs * 1e3 / max(1, min(args.steps, 5)), "higher_is_better": True,
+                          "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": wl["name"]},
+                          "cpu_baseline": {"value": v, "unit": "site-steps/s", "cores": 1, "kind": "port",
+                                           "sample": "numpy restatement, 4 lattices x %d sweeps" % min(args.steps, 5)},
+                          "e2e": {"value": v, "unit": "site-steps/s", "h2d_bytes_per_step": 0,
+                                  "d2h_bytes_per_step": 0}}), flush=True)
+        return
     kind = cpu_kind()
     procs = os.cpu_count() or 1
     CHUNK = 32  # one reference "step" = every worker advances its own env by CHUNK lockstep steps
@@ -363,6 +483,8 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000),
                os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
+    if args.workload == "c5":
+        return run_ising(args)
     run_ours(args)
 
 
