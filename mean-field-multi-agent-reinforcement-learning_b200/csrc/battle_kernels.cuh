@@ -55,7 +55,7 @@ __device__ __forceinline__ int block_scan_flag(bool flag, int *s_warp, int &tota
 // K2: fused step
 // ----------------------------------------------------------------------------------------------
 struct StepSmem {  // byte offsets into dynamic shared memory
-    int pos, hp, nr, state, id, lr, att, aux, mv, mvt, grid, misc, total;
+    int pos, hp, nr, state, att, aux, mv, mvt, tag_a, tag_v, mvidx, grid, misc, total;
 };
 __host__ __device__ inline StepSmem step_smem_layout(int W, int H, int cap) {
     StepSmem L;
@@ -65,12 +65,13 @@ __host__ __device__ inline StepSmem step_smem_layout(int W, int H, int cap) {
     L.hp = o;    o += 4 * n;
     L.nr = o;    o += 4 * n;
     L.state = o; o += 4 * n;
-    L.id = o;    o += 4 * n;
-    L.lr = o;    o += 4 * n;
     L.att = o;   o += 4 * n;   // shuffled attack list: slot | attack index << 16
     L.aux = o;   o += 4 * n;   // shuffle scratch, then victim slot per attack (-1 = miss)
     L.mv = o;    o += 4 * n;   // move list: slot | move index << 16
-    L.mvt = o;   o += 4 * n;   // target cell per move (-1 = outside the board)
+    L.mvt = o;   o += 4 * n;   // target per move: packed (x, y), or -1 = outside the board
+    L.tag_a = o; o += 2 * n;   // batch tag: slot attacks in the current 32-attack batch
+    L.tag_v = o; o += 2 * n;   // batch tag: slot is attacked in the current batch
+    L.mvidx = o; o += 2 * n;   // 1 + index in the move list (0 = does not move this step)
     L.misc = o;  o += 4 * 64;  // warp totals [32], counters
     L.grid = o;  o += 2 * W * H;
     L.total = (o + 15) & ~15;
@@ -86,12 +87,13 @@ __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState
     float *s_hp = (float *)(smem_raw + L.hp);
     float *s_nr = (float *)(smem_raw + L.nr);
     uint32_t *s_state = (uint32_t *)(smem_raw + L.state);
-    int *s_id = (int *)(smem_raw + L.id);
-    float *s_lr = (float *)(smem_raw + L.lr);
     uint32_t *s_att = (uint32_t *)(smem_raw + L.att);
     int *s_aux = (int *)(smem_raw + L.aux);
     uint32_t *s_mv = (uint32_t *)(smem_raw + L.mv);
     int *s_mvt = (int *)(smem_raw + L.mvt);
+    uint16_t *s_tag_a = (uint16_t *)(smem_raw + L.tag_a);
+    uint16_t *s_tag_v = (uint16_t *)(smem_raw + L.tag_v);
+    uint16_t *s_mvidx = (uint16_t *)(smem_raw + L.mvidx);
     int *s_misc = (int *)(smem_raw + L.misc);
     uint16_t *s_grid = (uint16_t *)(smem_raw + L.grid);
 
@@ -105,7 +107,14 @@ __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState
     // ---- load: agent records -> smem, occupancy grid from walls + alive agents ----
     if (tid < 2) { s_misc[MISC_N + tid] = S.num[e * 2 + tid]; s_misc[MISC_DEAD + tid] = S.dead_ct[e * 2 + tid]; }
     const uint8_t *walls = S.walls + (size_t)e * P.wall_stride;
-    for (int c = tid; c < cells; c += nt) s_grid[c] = walls[c];
+    if ((cells & 3) == 0) {   // 4 wall bytes -> 4 u16 grid codes per thread
+        for (int c = tid; c < (cells >> 2); c += nt) {
+            const uint32_t w4 = ((const uint32_t *)walls)[c];
+            ((uint2 *)s_grid)[c] = make_uint2((w4 & 0xFFu) | ((w4 & 0xFF00u) << 8), ((w4 >> 16) & 0xFFu) | ((w4 >> 8) & 0xFF0000u));
+        }
+    } else {
+        for (int c = tid; c < cells; c += nt) s_grid[c] = walls[c];
+    }
     __syncthreads();
     const int n0 = s_misc[MISC_N], n1 = s_misc[MISC_N + 1];
     for (int s = tid; s < 2 * cap; s += nt) {
@@ -119,9 +128,10 @@ __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState
                 st = (st & 0xFF00FFFFu) | ((uint32_t)a << 16);
             }
             s_pos[s] = p; s_hp[s] = S.hp[ebase + s]; s_nr[s] = S.next_rew[ebase + s];
-            s_state[s] = st; s_id[s] = S.id[ebase + s]; s_lr[s] = S.last_rew[ebase + s];
+            s_state[s] = st;
             if (!st_dead(st)) s_grid[pos_y(p) * W + pos_x(p)] = (uint16_t)(2 + s);
         }
+        s_tag_a[s] = 0; s_tag_v[s] = 0; s_mvidx[s] = 0;
     }
     __syncthreads();
 
@@ -192,32 +202,58 @@ __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState
         }
         __syncthreads();
 
-        // ---- ordered attack resolve (GridWorld.cc:524-557 at one thread, Map::do_attack Map.cc:266-321) ----
-        if (tid == 0) {
-            for (int i = 0; i < nA; i++) {
-                const int k = s_att[i] & 0xFFFF;
-                if (st_dead(s_state[k])) continue;                         // attacker died earlier this step
-                const int v = s_aux[i];
-                if (v < 0 || st_dead(s_state[v])) {                         // blank / wall / team-mate / already dead
-                    s_nr[k] = s_nr[k] + P.attack_penalty;
-                    continue;
+        // ---- ordered attack resolve (GridWorld.cc:524-557 run single-threaded, Map::do_attack Map.cc:266-321) ----
+        // Sequential semantics, executed by warp 0 in batches of 32 consecutive attacks of the shuffled
+        // order.  An attack (k -> v) whose attacker is attacked by nobody else in the batch and whose victim
+        // neither is attacked by another lane nor attacks in this batch touches state no other lane of the
+        // batch reads or writes: those lanes run in parallel.  The rest ("complex") run one lane at a time
+        // in lane order, i.e. in the shuffled order; since the simple lanes commute with them the result is
+        // bit-identical to the one-by-one loop.
+        auto one_attack = [&](int k, int v) {
+            if (st_dead(s_state[k])) return;                               // attacker died earlier this step
+            if (v < 0 || st_dead(s_state[v])) {                            // blank / wall / team-mate / already dead
+                s_nr[k] = s_nr[k] + P.attack_penalty;
+                return;
+            }
+            const float hp = s_hp[v] - P.damage;                           // Agent::be_attack, GridWorld.h:208-214
+            s_hp[v] = hp;
+            float reward = 0.0f;
+            if (hp < 0.0f) {
+                s_state[v] |= 1u;
+                s_nr[v] = P.dead_penalty;
+                const int pv = s_pos[v];
+                s_grid[pos_y(pv) * W + pos_x(pv)] = 0;                     // Map::remove_agent
+                atomicAdd(&s_misc[MISC_DEAD + (v >= cap)], 1);
+                s_state[k] = st_with_op(s_state[k], OP_KILL);
+                s_hp[k] = fminf(P.hp, s_hp[k] + P.kill_supply);            // Agent::add_hp
+                reward = P.kill_reward;
+            } else {
+                s_state[k] = st_with_op(s_state[k], OP_ATTACK);
+            }
+            s_nr[k] = s_nr[k] + (reward + P.attack_penalty);               // GridWorld.cc:556
+        };
+        if (tid < 32) {
+            const int lane = tid;
+            for (int i0 = 0, bid = 1; i0 < nA; i0 += 32, bid++) {
+                const int i = i0 + lane;
+                const bool valid = i < nA;
+                const int k = valid ? (int)(s_att[i] & 0xFFFF) : 0;
+                const int v = valid ? s_aux[i] : -1;
+                if (valid) s_tag_a[k] = (uint16_t)bid;
+                if (v >= 0) s_tag_v[v] = (uint16_t)bid;
+                __syncwarp();
+                const unsigned same_v = __match_any_sync(0xFFFFFFFFu, v >= 0 ? v : -1 - lane);
+                const bool complex = valid && (s_tag_v[k] == bid ||
+                                               (v >= 0 && (__popc(same_v) > 1 || s_tag_a[v] == bid)));
+                if (valid && !complex) one_attack(k, v);
+                __syncwarp();
+                unsigned todo = __ballot_sync(0xFFFFFFFFu, complex);
+                while (todo) {
+                    const int l = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    if (lane == l) one_attack(k, v);
+                    __syncwarp();
                 }
-                const float hp = s_hp[v] - P.damage;                        // Agent::be_attack, GridWorld.h:208-214
-                s_hp[v] = hp;
-                float reward = 0.0f;
-                if (hp < 0.0f) {
-                    s_state[v] |= 1u;
-                    s_nr[v] = P.dead_penalty;
-                    const int pv = s_pos[v];
-                    s_grid[pos_y(pv) * W + pos_x(pv)] = 0;                  // Map::remove_agent
-                    s_misc[MISC_DEAD + (v >= cap)]++;
-                    s_state[k] = st_with_op(s_state[k], OP_KILL);
-                    s_hp[k] = fminf(P.hp, s_hp[k] + P.kill_supply);         // Agent::add_hp
-                    reward = P.kill_reward;
-                } else {
-                    s_state[k] = st_with_op(s_state[k], OP_ATTACK);
-                }
-                s_nr[k] = s_nr[k] + (reward + P.attack_penalty);            // GridWorld.cc:556
             }
         }
         __syncthreads();
@@ -238,31 +274,65 @@ __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState
                 }
             }
         }
-        // ---- move targets (Map::do_move bounds test, Map.cc:326,466-468) ----
+        // ---- move targets (Map::do_move bounds test, Map.cc:326,466-468) + who moves, and when ----
         for (int m = tid; m < nM; m += nt) {
             const uint32_t ent = s_mv[m];
             const int k = ent & 0xFFFF, a = ent >> 16, p = s_pos[k];
             const int nx = pos_x(p) + P.move_dx[a], ny = pos_y(p) + P.move_dy[a];
-            s_mvt[m] = (nx < 0 || ny < 0 || nx + 1 >= W || ny + 1 >= H) ? -1 : ny * W + nx;
+            s_mvt[m] = (nx < 0 || ny < 0 || nx + 1 >= W || ny + 1 >= H) ? -1 : pack_pos(nx, ny);
+            s_mvidx[k] = (uint16_t)(m + 1);
         }
         __syncthreads();
 
-        // ---- ordered moves, first come first served (GridWorld.cc:631-672, Map.cc:324-369) ----
-        if (tid == 0) {
-            for (int m = 0; m < nM; m++) {
-                const int k = s_mv[m] & 0xFFFF;
-                if (st_dead(s_state[k])) continue;
-                const int tc = s_mvt[m];
-                if (tc < 0) continue;
-                const int occ = s_grid[tc], self = 2 + k;
-                if (occ == 0 || occ == self) {
+        // ---- ordered moves, first come first served (GridWorld.cc:631-672, Map::do_move Map.cc:324-369) ----
+        // Same batching as the attacks.  A mover is simple when its target cell is targeted by no other lane
+        // of the batch and is either free at batch start (it moves) or held by something that cannot have
+        // left by its turn -- a wall, an agent that does not move, moves in a later batch, or sits at a higher
+        // lane (it is blocked).  It is complex when another lane shares its target or the occupant moves at a
+        // lower lane of this batch; complex lanes run in lane order against the live grid, except that an
+        // occupant from a higher lane still blocks them (it has not moved yet at their turn).
+        if (tid < 32) {
+            const int lane = tid;
+            for (int i0 = 0; i0 < nM; i0 += 32) {
+                const int m = i0 + lane;
+                const bool valid = m < nM;
+                const int k = valid ? (int)(s_mv[m] & 0xFFFF) : 0;
+                const int tgt = valid ? s_mvt[m] : -1;
+                const bool cand = valid && tgt >= 0 && !st_dead(s_state[k]);
+                const int tc = cand ? pos_y(tgt) * W + pos_x(tgt) : -1;
+                const int self = 2 + k;
+                const int occ = cand ? (int)s_grid[tc] : 1;
+                const unsigned same_t = __match_any_sync(0xFFFFFFFFu, cand ? tc : -1 - lane);
+                int occ_lane = 64;                      // lane at which the occupant moves (64 = it cannot leave in time)
+                if (cand && occ >= 2 && occ != self) {
+                    const int j = (int)s_mvidx[occ - 2] - 1;
+                    if (j >= i0 && j < i0 + 32) occ_lane = j - i0;
+                }
+                const bool free0 = occ == 0 || occ == self;
+                const bool complex = cand && (__popc(same_t) > 1 || (!free0 && occ_lane < lane));
+                auto commit_move = [&]() {
                     const int p = s_pos[k];
                     s_grid[pos_y(p) * W + pos_x(p)] = 0;
                     s_grid[tc] = (uint16_t)self;
-                    const int ny = tc / W;
-                    s_pos[k] = pack_pos(tc - ny * W, ny);
-                } else if (occ >= 2) {
-                    s_state[k] = st_with_op(s_state[k], OP_COLLIDE);        // no reward effect in the battle rules
+                    s_pos[k] = tgt;
+                };
+                if (cand && !complex) {
+                    if (free0) commit_move();
+                    else if (occ >= 2) s_state[k] = st_with_op(s_state[k], OP_COLLIDE);   // no reward effect in battle
+                }
+                __syncwarp();
+                unsigned todo = __ballot_sync(0xFFFFFFFFu, complex);
+                while (todo) {
+                    const int l = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    if (lane == l) {
+                        const int now = s_grid[tc];
+                        const bool held_by_later = !free0 && occ_lane > lane;   // occupant has not moved yet at this turn
+                        if (occ == 1) { /* wall: never free, and no collide object (Map.cc:498-513) */ }
+                        else if (!held_by_later && (now == 0 || now == self)) commit_move();
+                        else s_state[k] = st_with_op(s_state[k], OP_COLLIDE);
+                    }
+                    __syncwarp();
                 }
             }
         }
@@ -338,11 +408,14 @@ __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState
             for (int base = 0; base < ng; base += nt) {
                 const int i = base + tid, s = g * cap + i;
                 const bool keep = i < ng && !st_dead(s_state[s]);
+                // ids are read at the old index before the scan's barriers; survivors only move to lower or
+                // equal indices of rounds already consumed, so the in-place rewrite cannot clobber a pending read
+                const int my_id = keep ? S.id[ebase + s] : 0;
                 int tot;
                 const int p = block_scan_flag(keep, s_misc + MISC_WARP, tot);
                 if (keep) {
                     const size_t d = ebase + (size_t)g * cap + kept + p;
-                    S.pos[d] = s_pos[s]; S.hp[d] = s_hp[s]; S.id[d] = s_id[s];
+                    S.pos[d] = s_pos[s]; S.hp[d] = s_hp[s]; S.id[d] = my_id;
                     S.state[d] = make_state(0, OP_NULL, st_act(s_state[s]));   // Agent::init_reward
                     S.last_rew[d] = s_nr[s];
                     S.next_rew[d] = P.step_reward;
