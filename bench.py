@@ -201,7 +201,8 @@ def run_ours(args):
     E, cap, K, W = args.envs or wl["envs"], wl["cap"], args.steps, args.warmup
     left, right = placement(wl)
     env = BatchedGridWorld(E, map_size=wl["map_size"], capacity=cap, device=dev, rng="philox", seed=0,
-                           env_base=rank * E, max_steps=wl["max_steps"], auto_reset=True)
+                           env_base=rank * E, max_steps=wl["max_steps"], auto_reset=True,
+                           obs_tile_agents=args.obs_tile, step_threads=args.step_threads)
     env.reset(); env.add_agents(0, left); env.add_agents(1, right)
 
     # synthetic actions, uniform{0..20} from torch's Philox generator, resident in HBM: a pool the steps cycle through
@@ -471,6 +472,8 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's)")
     ap.add_argument("--cpu-steps", type=int, default=60000, help="timed steps per CPU-baseline worker")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--obs-tile", type=int, default=0, help="agents per k_obs CTA (tuning; 0 = engine default)")
+    ap.add_argument("--step-threads", type=int, default=0, help="threads per k_step CTA (tuning; 0 = auto)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

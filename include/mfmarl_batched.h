@@ -35,7 +35,7 @@ typedef struct mfb_config {
     int auto_reset;        /* re-place the armies when an episode ends (done or horizon)             */
     int device;            /* CUDA device ordinal, -1 = current                                      */
     int step_threads;      /* 0 = auto                                                               */
-    int obs_tile_agents;   /* agents per observation CTA, 0 = 64                                     */
+    int obs_tile_agents;   /* agents per observation CTA, 0 = auto: clamp(capacity, 64, 256)         */
     /* agent type (python/magent/builtin/config/battle.py:16-29) and the attack reward rules (:41-42) */
     float hp, speed, view_radius, attack_radius, damage, step_recover, kill_supply;
     float step_reward, kill_reward, dead_penalty, attack_penalty, attack_bonus[2];

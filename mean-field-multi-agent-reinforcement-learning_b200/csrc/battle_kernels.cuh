@@ -445,11 +445,11 @@ __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState
 // hands the chunk to a single cp.async.bulk shared->global store; two staging buffers keep a store
 // in flight while the next chunk is composed.
 //
-// Composition is incremental.  At CTA start every staging row is filled once with the BACKGROUND that
-// all agents of the group share (zeros + the two minimap channels).  For each agent its warp then only
-//   - scans the 169 view cells against the shared-memory occupancy grid (lane = cell, 6 passes),
-//   - writes the few cells that differ from the background (wall / own / other has+hp) and restores
-//     the ones the previous agent of that row had written (2-bit kind per cell kept in a register),
+// Composition is incremental.  At CTA start every staging row is filled once with the part all agents
+// of the group share (the two minimap channels).  For each agent its warp then only
+//   - looks the 169 view cells up in the shared-memory occupancy grid (lane = cell, 6 passes; the grid
+//     carries a 6-cell empty margin, so a window never needs a bounds test: one add + one 16-bit load),
+//   - rewrites the five occupancy channels (wall, own has/hp, other has/hp) of every cell,
 //   - moves the "+1" self marker of the two minimap channels.
 // All shared-memory stores are stride-7-word (coprime with the 32 banks): conflict-free.
 // The map is never re-read from HBM: occupancy/hp grid and both minimaps are rebuilt per CTA from the
@@ -461,15 +461,19 @@ constexpr int kObsStageBytes = kObsChunk * kViewRow * 4;       // 37 856, a mult
 constexpr int kObsPasses = (kViewCells + 31) / 32;             // 6
 static_assert(kObsChunk == kObsWarps, "one warp composes one row of a chunk");
 
-struct ObsSmem { int stage0, stage1, hp10, mini, cnt, kind, total; };
-__host__ __device__ inline ObsSmem obs_smem_layout(int W, int H) {
+constexpr int kPad = kView / 2;   // the smem grid carries a 6-cell empty margin: view windows never need a bounds test
+
+struct ObsSmem { int stage0, stage1, rec, hp10, mini, cnt, code, total; };
+constexpr int kObsMaxTile = 256;   // agents per CTA tile, upper bound (record staging)
+__host__ __device__ inline ObsSmem obs_smem_layout(int W, int H, int cap) {
     ObsSmem L; int o = 0;
     L.stage0 = o; o += kObsStageBytes;
     L.stage1 = o; o += kObsStageBytes;
-    L.hp10 = o;   o += 4 * W * H;
+    L.rec = o;    o += 16 * kObsMaxTile;                              // (pos, id, state, last_rew) of the tile's agents
+    L.hp10 = o;   o += 4 * 2 * cap;                                   // hp / max_hp per agent slot
     L.mini = o;   o += 4 * 2 * kViewCells;
     L.cnt = o;    o += 4 * 2 * kViewCells;
-    L.kind = o;   o += (W * H + 3) & ~3;
+    L.code = o;   o += (2 * (W + 2 * kPad) * (H + 2 * kPad) + 3) & ~3;  // u16 per padded cell: kind << 14 | slot
     L.total = (o + 127) & ~127;
     return L;
 }
@@ -496,153 +500,154 @@ enum : uint32_t { KIND_EMPTY = 0, KIND_WALL = 1, KIND_OWN = 2, KIND_OTHER = 3 };
 __global__ void __launch_bounds__(kObsThreads, 2)
 k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO io) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const ObsSmem L = obs_smem_layout(P.W, P.H);
+    const ObsSmem L = obs_smem_layout(P.W, P.H, P.cap);
     float *const s_stage0 = (float *)(smem_raw + L.stage0), *const s_stage1 = (float *)(smem_raw + L.stage1);
+    int4 *s_rec = (int4 *)(smem_raw + L.rec);
     float *s_hp10 = (float *)(smem_raw + L.hp10);
     float *s_mini = (float *)(smem_raw + L.mini);
     int *s_cnt = (int *)(smem_raw + L.cnt);
-    uint8_t *s_kind = smem_raw + L.kind;
+    uint16_t *s_code = (uint16_t *)(smem_raw + L.code);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int W = P.W, H = P.H, cap = P.cap, cells = W * H;
-
-    // tile -> (env, group, first agent)
-    int t = blockIdx.x;
-    const int tile = t % io.tiles_per_group; t /= io.tiles_per_group;
-    int g, e;
-    if (io.group_mask == 3) { g = t & 1; e = t >> 1; } else { g = io.group_mask >> 1; e = t; }
-    const int n0 = S.num[e * 2], n1 = S.num[e * 2 + 1];
-    const int ng = g ? n1 : n0;
-    const int a_begin = tile * io.tile_agents;
-    if (a_begin >= ng) return;
-    const int a_end = min(ng, a_begin + io.tile_agents);
-    const size_t ebase = (size_t)e * 2 * cap;
-    const size_t gbase = ebase + (size_t)g * cap;
-
-    // ---- occupancy grid (kind per cell), hp/10 per cell, minimap counts ----
-    const uint8_t *walls = S.walls + (size_t)e * P.wall_stride;
-    if ((cells & 3) == 0) {
-        for (int c = tid; c < (cells >> 2); c += kObsThreads)
-            ((uint32_t *)s_kind)[c] = ((const uint32_t *)walls)[c];
-    } else {
-        for (int c = tid; c < cells; c += kObsThreads) s_kind[c] = walls[c];
-    }
-    for (int c = tid; c < 2 * kViewCells; c += kObsThreads) s_cnt[c] = 0;
-    __syncthreads();
+    const int W = P.W, H = P.H, cap = P.cap;
+    const int PW = W + 2 * kPad, pcells = PW * (H + 2 * kPad);
+    const int FS = P.feature_size, emb = P.embedding_size, n_action = P.n_move + P.n_attack;
     const uint8_t *lut = S.mini_lut;   // [W] x / scale_w, then [H] (y / scale_h) * 13
-    for (int s = tid; s < 2 * cap; s += kObsThreads) {
-        const int gg = s >= cap, i = s - gg * cap;
-        if (i < (gg ? n1 : n0)) {
-            const int p = S.pos[ebase + s], x = pos_x(p), y = pos_y(p);
-            // minimap counts every agent still in the list, dead or not (GridWorld.cc:359-370)
-            atomicAdd(&s_cnt[gg * kViewCells + lut[W + y] + lut[x]], 1);
-            if (!st_dead(S.state[ebase + s])) {
-                s_kind[y * W + x] = (uint8_t)(gg == g ? KIND_OWN : KIND_OTHER);
-                s_hp10[y * W + x] = __fdiv_rn(S.hp[ebase + s], P.hp);   // Map.cc:208
-            }
-        }
-    }
-    __syncthreads();
-    for (int c = tid; c < 2 * kViewCells; c += kObsThreads) {
-        const int gg = c >= kViewCells;
-        s_mini[c] = __fdiv_rn((float)s_cnt[c], (float)(gg ? n1 : n0));  // GridWorld.cc:372-377
-    }
-    __syncthreads();
-    const float *mini_own = s_mini + g * kViewCells, *mini_oth = s_mini + (1 - g) * kViewCells;
 
-    // ---- per-lane view geometry: cell c = pass * 32 + lane -> (dx, dy) relative to the agent, disc bit ----
-    int rel[kObsPasses];
+    // ---- per-lane view geometry: cell c = pass * 32 + lane -> offset in the padded grid relative to the
+    //      window's top-left corner; cells outside the view disc keep offset 0 with the disc bit cleared ----
+    int off[kObsPasses];
     uint32_t disc = 0;
 #pragma unroll
     for (int it = 0; it < kObsPasses; it++) {
         const int c = it * 32 + lane;
         const int vy = c / kView, vx = c - vy * kView;
-        rel[it] = ((vx - kView / 2) & 0xFFFF) | ((vy - kView / 2) << 16);
-        if (c < kViewCells && ((P.disc[it] >> lane) & 1u)) disc |= 1u << it;
+        const bool in = c < kViewCells && ((P.disc[it] >> lane) & 1u);
+        off[it] = in ? vy * PW + vx : 0;
+        if (in) disc |= 1u << it;
     }
 
-    // ---- background: this warp's row of both staging buffers = zeros + minimap channels ----
-#pragma unroll
-    for (int b = 0; b < 2; b++) {
-        float *row = (b ? s_stage1 : s_stage0) + warp * kViewRow;
-#pragma unroll
-        for (int it = 0; it < kObsPasses; it++) {
-            const int c = it * 32 + lane;
-            if (c < kViewCells) {
-                float *o = row + c * kChan;
-                o[0] = 0.0f; o[1] = 0.0f; o[2] = 0.0f; o[4] = 0.0f; o[5] = 0.0f;
-                o[3] = mini_own[c]; o[6] = mini_oth[c];
-            }
-        }
-    }
-
-    // ---- stream the tile: compose (delta vs previous occupant of the row), bulk-store ----
-    const int FS = P.feature_size, emb = P.embedding_size, n_action = P.n_move + P.n_attack;
-    float *vout = io.view + gbase * kViewRow;
-    float *fout = io.feature + gbase * FS;
-    uint32_t kinds_prev1 = 0, kinds_prev2 = 0;   // 2-bit kind per pass, for the row in the other / this buffer
-    int self_prev1 = -1, self_prev2 = -1;
+    // Persistent CTAs: each loops over work items (env, group, tile).  The bulk stores are asynchronous, so
+    // the grid rebuild of the next item overlaps the drain of this item's last chunks, and the staging-buffer
+    // parity simply carries on across items.
     int buf = 0;
-    for (int c0 = a_begin; c0 < a_end; c0 += kObsChunk, buf ^= 1) {
-        const int cn = min(kObsChunk, a_end - c0);
-        // the store issued two chunks ago read this buffer: wait until its smem reads are done
-        if (tid == 0) bulk_wait_read<1>();
+    const int groups_per_env = io.group_mask == 3 ? 2 : 1;
+    const int n_items = P.E * groups_per_env * io.tiles_per_group;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int t = item;
+        const int tile = t % io.tiles_per_group; t /= io.tiles_per_group;
+        int g, e;
+        if (io.group_mask == 3) { g = t & 1; e = t >> 1; } else { g = io.group_mask >> 1; e = t; }
+        const int n0 = S.num[e * 2], n1 = S.num[e * 2 + 1];
+        const int ng = g ? n1 : n0;
+        const int a_begin = tile * io.tile_agents;
+        if (a_begin >= ng) continue;                      // uniform across the CTA
+        const int a_end = min(ng, a_begin + io.tile_agents);
+        const size_t ebase = (size_t)e * 2 * cap;
+        const size_t gbase = ebase + (size_t)g * cap;
+
+        // ---- padded occupancy grid (kind << 14 | slot per cell), hp/10 per slot, minimap counts ----
+        __syncthreads();                                  // every warp is done reading the previous item's grid
+        {
+            const uint4 *tmpl = (const uint4 *)S.grid_template;   // padded grid with the walls, built at commit
+            for (int c = tid; c < (pcells * 2 + 15) / 16; c += kObsThreads) ((uint4 *)s_code)[c] = tmpl[c];
+        }
+        for (int c = tid; c < 2 * kViewCells; c += kObsThreads) s_cnt[c] = 0;
+        for (int a = tid; a < a_end - a_begin; a += kObsThreads) {   // the tile's agent records
+            const size_t s = gbase + a_begin + a;
+            s_rec[a] = make_int4(S.pos[s], S.id[s], (int)S.state[s], __float_as_int(S.last_rew[s]));
+        }
         __syncthreads();
-        uint32_t kinds_new = 0;
-        int self_new = -1;
-        if (warp < cn) {
-            const size_t s = gbase + c0 + warp;
-            const int p = S.pos[s], ax = pos_x(p), ay = pos_y(p);
-            const int id = S.id[s];
-            const uint32_t st = S.state[s];
-            const float last_rew = S.last_rew[s];
-            float *row = (buf ? s_stage1 : s_stage0) + warp * kViewRow;
-#pragma unroll
-            for (int it = 0; it < kObsPasses; it++) {
-                const int x = ax + (int)(short)(rel[it] & 0xFFFF), y = ay + (rel[it] >> 16);
-                const bool in = ((disc >> it) & 1u) && (unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H;
-                const int cell = in ? y * W + x : 0;
-                const uint32_t k = in ? (uint32_t)s_kind[cell] : (uint32_t)KIND_EMPTY;
-                const float hp = s_hp10[cell];
-                const uint32_t old = (kinds_prev2 >> (2 * it)) & 3u;
-                float *o = row + (it * 32 + lane) * kChan;
-                if (old == KIND_WALL || k == KIND_WALL) o[0] = k == KIND_WALL ? 1.0f : 0.0f;
-                if (old == KIND_OWN || k == KIND_OWN) { o[1] = k == KIND_OWN ? 1.0f : 0.0f; o[2] = k == KIND_OWN ? hp : 0.0f; }
-                if (old == KIND_OTHER || k == KIND_OTHER) { o[4] = k == KIND_OTHER ? 1.0f : 0.0f; o[5] = k == KIND_OTHER ? hp : 0.0f; }
-                kinds_new |= k << (2 * it);
-            }
-            // self marker in BOTH minimap channels (GridWorld.cc:396-408): move it
-            self_new = lut[W + ay] + lut[ax];
-            if (lane == 0) {
-                if (self_prev2 >= 0) {
-                    row[self_prev2 * kChan + 3] = mini_own[self_prev2];
-                    row[self_prev2 * kChan + 6] = mini_oth[self_prev2];
+        for (int s = tid; s < 2 * cap; s += kObsThreads) {
+            const int gg = s >= cap, i = s - gg * cap;
+            if (i < (gg ? n1 : n0)) {
+                const int p = S.pos[ebase + s], x = pos_x(p), y = pos_y(p);
+                // minimap counts every agent still in the list, dead or not (GridWorld.cc:359-370)
+                atomicAdd(&s_cnt[gg * kViewCells + lut[W + y] + lut[x]], 1);
+                if (!st_dead(S.state[ebase + s])) {
+                    s_code[(y + kPad) * PW + x + kPad] = (uint16_t)(((gg == g ? KIND_OWN : KIND_OTHER) << 14) | s);
+                    s_hp10[s] = __fdiv_rn(S.hp[ebase + s], P.hp);       // Map.cc:208
                 }
-                row[self_new * kChan + 3] = mini_own[self_new] + 1.0f;
-                row[self_new * kChan + 6] = mini_oth[self_new] + 1.0f;
-            }
-            // features (GridWorld.cc:411-421): id bits LSB first, one-hot last action, last reward, x/W, y/H
-            float *f = fout + (size_t)(c0 + warp) * FS;
-            for (int k = lane; k < FS; k += 32) {
-                float v;
-                if (k < emb) v = (float)((id >> k) & 1);                      // GridWorld.h:162-171
-                else if (k < emb + n_action) v = ((int)st_act(st) == k - emb) ? 1.0f : 0.0f;
-                else if (k == emb + n_action) v = last_rew;
-                else if (k == emb + n_action + 1) v = __fdiv_rn((float)ax, (float)W);
-                else v = __fdiv_rn((float)ay, (float)H);
-                f[k] = v;
             }
         }
-        kinds_prev2 = kinds_prev1; kinds_prev1 = kinds_new;
-        self_prev2 = self_prev1; self_prev1 = self_new;
-        fence_proxy_async_smem();   // make the generic-proxy smem writes visible to the async proxy
         __syncthreads();
-        if (tid == 0) {
-            // rows are 4732 B (= 12 mod 16): a ragged tail is rounded up to 16 B; the <= 12 spill bytes land
-            // in the next, unused row of the same [cap] block (cap is a multiple of 4, see engine.cu)
-            const uint32_t bytes = ((uint32_t)cn * kViewRow * 4 + 15u) & ~15u;
-            bulk_store_s2g(vout + (size_t)c0 * kViewRow, buf ? s_stage1 : s_stage0, bytes);
-            bulk_commit();
+        for (int c = tid; c < 2 * kViewCells; c += kObsThreads) {
+            const int gg = c >= kViewCells;
+            s_mini[c] = __fdiv_rn((float)s_cnt[c], (float)(gg ? n1 : n0));   // GridWorld.cc:372-377
+        }
+        // (the barrier at the top of the first chunk orders s_mini before its readers)
+        const float *mini_own = s_mini + g * kViewCells, *mini_oth = s_mini + (1 - g) * kViewCells;
+
+        // ---- stream the tile: compose, bulk-store ----
+        float *vout = io.view + gbase * kViewRow;
+        float *fout = io.feature + gbase * FS;
+        int self_prev1 = -1, self_prev2 = -1;   // self-marker cell of the row in the other / this buffer
+        int stale = 2;                          // staging buffers whose minimap channels belong to another item
+        for (int c0 = a_begin; c0 < a_end; c0 += kObsChunk, buf ^= 1) {
+            const int cn = min(kObsChunk, a_end - c0);
+            // the store issued two chunks ago read this buffer: wait until its smem reads are done
+            if (tid == 0) bulk_wait_read<1>();
+            __syncthreads();
+            int self_new = -1;
+            if (warp < cn && !(io.debug & 1)) {
+                const int4 rec = s_rec[c0 - a_begin + warp];
+                const int p = rec.x, ax = pos_x(p), ay = pos_y(p);
+                const int id = rec.y;
+                const uint32_t st = (uint32_t)rec.z;
+                const float last_rew = __int_as_float(rec.w);
+                float *row = (buf ? s_stage1 : s_stage0) + warp * kViewRow;
+                // window top-left corner (ax - 6, ay - 6) in padded coordinates is simply (ax, ay)
+                const uint16_t *win = s_code + ay * PW + ax;
+#pragma unroll
+                for (int it = 0; it < kObsPasses; it++) {
+                    const int c = it * 32 + lane;
+                    if (c < kViewCells) {               // compile-time true for passes 0..4
+                        const uint32_t code = ((disc >> it) & 1u) ? (uint32_t)win[off[it]] : 0u;
+                        const uint32_t k = code >> 14;
+                        const float hp = s_hp10[code & 0x3FFFu];
+                        float *o = row + c * kChan;
+                        o[0] = k == KIND_WALL ? 1.0f : 0.0f;
+                        o[1] = k == KIND_OWN ? 1.0f : 0.0f;
+                        o[2] = k == KIND_OWN ? hp : 0.0f;
+                        o[4] = k == KIND_OTHER ? 1.0f : 0.0f;
+                        o[5] = k == KIND_OTHER ? hp : 0.0f;
+                        if (stale > 0) { o[3] = mini_own[c]; o[6] = mini_oth[c]; }   // new item: refresh the shared part
+                    }
+                }
+                // self marker in BOTH minimap channels (GridWorld.cc:396-408): move it
+                self_new = lut[W + ay] + lut[ax];
+                __syncwarp();
+                if (lane == 0) {
+                    if (stale <= 0 && self_prev2 >= 0) {
+                        row[self_prev2 * kChan + 3] = mini_own[self_prev2];
+                        row[self_prev2 * kChan + 6] = mini_oth[self_prev2];
+                    }
+                    row[self_new * kChan + 3] = mini_own[self_new] + 1.0f;
+                    row[self_new * kChan + 6] = mini_oth[self_new] + 1.0f;
+                }
+                // features (GridWorld.cc:411-421): id bits LSB first, one-hot last action, last reward, x/W, y/H
+                const float fx = __fdiv_rn((float)ax, (float)W), fy = __fdiv_rn((float)ay, (float)H);
+                const int act = (int)st_act(st);
+                float *f = fout + (size_t)(c0 + warp) * FS;
+                for (int k = lane; k < FS; k += 32) {
+                    float v = (k < emb) ? (float)((id >> k) & 1) : ((k - emb == act) ? 1.0f : 0.0f);   // GridWorld.h:162-171
+                    v = k == emb + n_action ? last_rew : v;
+                    v = k == emb + n_action + 1 ? fx : v;
+                    v = k == emb + n_action + 2 ? fy : v;
+                    f[k] = v;
+                }
+            }
+            self_prev2 = self_prev1; self_prev1 = self_new;
+            stale--;
+            fence_proxy_async_smem();   // make the generic-proxy smem writes visible to the async proxy
+            __syncthreads();
+            if (tid == 0) {
+                // rows are 4732 B (= 12 mod 16): a ragged tail is rounded up to 16 B; the <= 12 spill bytes land
+                // in the next, unused row of the same [cap] block (cap is a multiple of 4, see engine.cu)
+                const uint32_t bytes = ((uint32_t)cn * kViewRow * 4 + 15u) & ~15u;
+                bulk_store_s2g(vout + (size_t)c0 * kViewRow, buf ? s_stage1 : s_stage0, bytes);
+                bulk_commit();
+            }
         }
     }
     if (tid == 0) bulk_wait<0>();

@@ -71,6 +71,7 @@ struct BattleState {   // device pointers
     int32_t *pos; float *hp; int32_t *id; uint32_t *state; float *next_rew; float *last_rew;
     int32_t *num; int32_t *dead_ct; uint32_t *rng; int32_t *step_ct; int32_t *id_counter;
     uint8_t *walls;
+    uint16_t *grid_template;           // [(H+12)*(W+12)] padded occupancy grid holding only the walls (kind << 14)
     uint8_t *mini_lut;                 // [W] x / scale_w, then [H] (y / scale_h) * view: minimap cell of a position
     unsigned long long *agent_steps;   // [E] running count of agents taken through a step (statistic)
     // episode template for auto-reset
@@ -95,6 +96,7 @@ struct ObsIO {
     int group_mask;  // which groups to produce
     int tile_agents; // agents per CTA tile
     int tiles_per_group;
+    int debug;       // profiling experiments only (MFMARL_OBS_DEBUG): 1 = skip row composition
 };
 
 }  // namespace mfmarl

@@ -108,6 +108,7 @@ Engine::Engine(const EngineConfig &cfg) : cfg_(cfg) {
     MF_CUDA(cudaMalloc(&S_.id_counter, E * sizeof(int32_t)));
     MF_CUDA(cudaMalloc(&S_.walls, (size_t)P_.W * P_.H));
     MF_CUDA(cudaMalloc(&S_.init_num, 2 * sizeof(int32_t)));
+    MF_CUDA(cudaMalloc(&S_.grid_template, grid_template_bytes()));
     {   // minimap cell of a position, as a table: the kernels never divide by the runtime scale
         if ((P_.H - 1) / P_.scale_h * kView + (P_.W - 1) / P_.scale_w > 255) throw Fatal("minimap table overflow");
         std::vector<uint8_t> lut((size_t)P_.W + P_.H);
@@ -131,11 +132,16 @@ Engine::Engine(const EngineConfig &cfg) : cfg_(cfg) {
 Engine::~Engine() {
     free_state();
     cudaFree(S_.num); cudaFree(S_.dead_ct); cudaFree(S_.rng); cudaFree(S_.step_ct);
-    cudaFree(S_.id_counter); cudaFree(S_.walls); cudaFree(S_.init_num); cudaFree(S_.agent_steps); cudaFree(S_.mini_lut);
+    cudaFree(S_.id_counter); cudaFree(S_.walls); cudaFree(S_.init_num); cudaFree(S_.agent_steps); cudaFree(S_.mini_lut); cudaFree(S_.grid_template);
+}
+
+size_t Engine::grid_template_bytes() const {
+    const size_t cells = (size_t)(P_.W + 2 * (kView / 2)) * (P_.H + 2 * (kView / 2));
+    return (cells * 2 + 15) / 16 * 16;
 }
 
 void Engine::alloc_state(int cap) {
-    if (2 * cap + 2 > 65535) throw Fatal("capacity too large for the 16-bit occupancy grid");
+    if (2 * cap > 0x3FFF) throw Fatal("capacity too large for the 14-bit slot field of the occupancy grid");
     P_.cap = cap;
     const size_t n = slots();
     MF_CUDA(cudaMalloc(&S_.pos, n * 4)); MF_CUDA(cudaMalloc(&S_.hp, n * 4));
@@ -320,6 +326,13 @@ void Engine::commit(cudaStream_t st) {
     MF_CUDA(cudaMemcpyAsync(S_.init_pos, tmpl.data(), tmpl.size() * 4, cudaMemcpyHostToDevice, st));
     MF_CUDA(cudaMemcpyAsync(S_.init_num, num, 8, cudaMemcpyHostToDevice, st));
     MF_CUDA(cudaMemcpyAsync(S_.walls, h_walls_.data(), h_walls_.size(), cudaMemcpyHostToDevice, st));
+    // the observation kernel's shared-memory grid starts from this image: walls only, 6-cell empty margin
+    std::vector<uint16_t> gtmpl(grid_template_bytes() / 2, 0);
+    const int PW = P_.W + 2 * (kView / 2);
+    for (int y = 0; y < P_.H; y++)
+        for (int x = 0; x < P_.W; x++)
+            if (h_walls_[(size_t)y * P_.W + x]) gtmpl[(size_t)(y + kView / 2) * PW + x + kView / 2] = (uint16_t)(1u << 14);
+    MF_CUDA(cudaMemcpyAsync(S_.grid_template, gtmpl.data(), gtmpl.size() * 2, cudaMemcpyHostToDevice, st));
     MF_CUDA(cudaStreamSynchronize(st));
     k_place<<<P_.E, 128, 0, st>>>(P_, S_);
     MF_CUDA(cudaGetLastError());
@@ -341,14 +354,19 @@ void Engine::observe(float *d_view, float *d_feature, int group_mask, cudaStream
     if (group_mask < 1 || group_mask > 3) throw Fatal("observe: bad group mask");
     ObsIO io;
     io.view = d_view; io.feature = d_feature; io.group_mask = group_mask;
-    io.tile_agents = std::max(kObsChunk, round_up(cfg_.obs_tile_agents, kObsChunk));
+    // tile: amortise the per-CTA grid rebuild over more agents when groups are large (measured: 256 at cap 512)
+    const int want_tile = cfg_.obs_tile_agents > 0 ? cfg_.obs_tile_agents : std::min(256, std::max(64, P_.cap));
+    io.tile_agents = std::min(kObsMaxTile, std::max(kObsChunk, round_up(want_tile, kObsChunk)));
     io.tiles_per_group = (P_.cap + io.tile_agents - 1) / io.tile_agents;
-    const ObsSmem L = obs_smem_layout(P_.W, P_.H);
+    { const char *dbg = getenv("MFMARL_OBS_DEBUG"); io.debug = dbg ? atoi(dbg) : 0; }
+    const ObsSmem L = obs_smem_layout(P_.W, P_.H, P_.cap);
     if (obs_attr_ != L.total) {
         MF_CUDA(cudaFuncSetAttribute(k_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
         obs_attr_ = L.total;
     }
-    const unsigned grid = (unsigned)((size_t)P_.E * (group_mask == 3 ? 2 : 1) * io.tiles_per_group);
+    // persistent CTAs: two per SM (shared-memory bound), each loops over (env, group, tile) work items
+    const size_t items = (size_t)P_.E * (group_mask == 3 ? 2 : 1) * io.tiles_per_group;
+    const unsigned grid = (unsigned)std::min<size_t>(items, (size_t)2 * n_sm_);
     k_obs<<<grid, kObsThreads, L.total, st>>>(P_, S_, io);
     MF_CUDA(cudaGetLastError());
 }

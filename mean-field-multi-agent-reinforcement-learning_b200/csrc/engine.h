@@ -43,7 +43,7 @@ struct AgentTypeParams {   // the attributes of AgentType.h:21-45 that reach the
 struct EngineConfig {
     int n_envs = 1, width = 40, height = 40, capacity = 64, embedding_size = 10;
     int rng_mode = RNG_MINSTD, max_steps = 0, env_base = 0, device = -1 /* current */;
-    int step_threads = 0 /* auto */, obs_tile_agents = 64;
+    int step_threads = 0 /* auto */, obs_tile_agents = 0 /* auto: clamp(cap, 64, 256) */;
     unsigned seed = 0;
     AgentTypeParams type;
     float attack_bonus[kGroups] = {0.2f, 0.2f};
@@ -91,6 +91,7 @@ public:
 
 private:
     void alloc_state(int cap);
+    size_t grid_template_bytes() const;
     void free_state();
     void grow(int need_cap);
     void late_add_sync_down();   // E == 1 only: device state -> host records

@@ -25,7 +25,7 @@ def _stream():
 
 class BatchedGridWorld:
     def __init__(self, n_envs, map_size=40, capacity=64, device=None, rng="minstd", seed=0, env_base=0,
-                 max_steps=0, auto_reset=False, step_threads=0, obs_tile_agents=64, **type_overrides):
+                 max_steps=0, auto_reset=False, step_threads=0, obs_tile_agents=0, **type_overrides):
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedGridWorld needs a CUDA device: there is no CPU fallback")
         self.lib = load_library()
