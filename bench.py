@@ -241,28 +241,41 @@ def run_ours(args):
     obs_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / K
     step_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / K
 
-    # ---- e2e: actions from pinned host memory each step, results read back to the host each step ----
+    # ---- e2e: actions from pinned host memory each step, results read back to pinned host memory each step.
+    #      Pipelined like an actor loop: the upload of step t and the download of step t-1 ride on copy
+    #      streams under k_obs; a step's results are consumed (waited for) before its buffers are reused ----
     h_act = [p.cpu().pin_memory() for p in pool]
     n_act = env.sizes["n_action"]
-    h_reward = torch.empty((E, 2, cap), dtype=torch.float32).pin_memory()
-    h_alive = torch.empty((E, 2, cap), dtype=torch.uint8).pin_memory()
-    h_mean = torch.empty((E, 2, n_act), dtype=torch.float32).pin_memory()
-    h_done = torch.empty((E,), dtype=torch.int32).pin_memory()
-    for k in range(min(W, 3)):
-        env.observe(); env.step_host(h_act[k % POOL], h_reward, h_alive, h_mean, h_done)
+
+    def result_set():
+        return (torch.empty((E, 2, cap), dtype=torch.float32).pin_memory(),
+                torch.empty((E, 2, cap), dtype=torch.uint8).pin_memory(),
+                torch.empty((E, 2, n_act), dtype=torch.float32).pin_memory(),
+                torch.empty((E,), dtype=torch.int32).pin_memory())
+
+    results = [result_set(), result_set()]
+    for k in range(min(W, 4)):
+        env.observe()
+        env.host_wait(env.step_host_async(h_act[k % POOL], *results[k & 1]))
     as1 = int(env.get("agent_steps").sum())
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    checksum = 0.0
     e0.record()
     for k in range(K):
         env.observe()
-        env.step_host(h_act[k % POOL], h_reward, h_alive, h_mean, h_done)   # H2D + k_step + D2H + sync
+        ticket = env.step_host_async(h_act[k % POOL], *results[k & 1])   # H2D + k_step + D2H enqueued
+        if k >= 1:                                                       # consume step k-1's results on the host
+            env.host_wait(ticket ^ 1)
+            checksum += float(results[(k - 1) & 1][0][0, 0, 0])
+    env.host_wait(ticket)
+    checksum += float(results[(K - 1) & 1][0][0, 0, 0])
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
     e2e_agent_steps = int(env.get("agent_steps").sum()) - as1
     h2d = h_act[0].numel() * 4
-    d2h = h_reward.numel() * 4 + h_alive.numel() + h_mean.numel() * 4 + h_done.numel() * 4
+    d2h = sum(t.numel() * t.element_size() for t in results[0])
 
     if world > 1:
         t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
@@ -298,8 +311,9 @@ def run_ours(args):
                          "whole_step_frac": (agent_steps / K) * BYTES_PER_AGENT_STEP / (ms / K * 1e-3) / 1e9 / peak},
             "e2e": {"value": e2e_all / (e2e_ms * 1e-3), "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h,
-                    "note": "mfb_step_host: actions from pinned host memory, rewards/alive/done/mean action read "
-                            "back; observations stay in HBM for the policy network"},
+                    "note": "mfb_step_host_async: actions from pinned host memory, rewards/alive/done/mean action "
+                            "copied back to pinned host memory and waited for every step (copies pipelined under "
+                            "k_obs); observations stay in HBM for the policy network"},
             "clocks": clocks.summary(),
         }
         if world == 1 and not args.no_cpu:

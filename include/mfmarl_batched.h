@@ -89,6 +89,15 @@ int mfb_num_device_ptr(mfb_engine *eng, const int32_t **out);
 int mfb_step_host(mfb_engine *eng, const int32_t *h_actions, float *h_reward, uint8_t *h_alive,
                   float *h_mean_action, int32_t *h_done, void *stream);
 
+/* Pipelined variant: returns as soon as the work is enqueued.  The action upload runs on an internal copy
+ * stream (so it overlaps kernels already queued on `stream`, e.g. mfb_observe), k_step runs on `stream`, and
+ * the results are copied to the pinned host buffers on a second copy stream (overlapping the next
+ * mfb_observe).  Two internal staging sets alternate: *ticket (0/1) names the one used; the host buffers
+ * of a call are valid after mfb_host_wait(eng, ticket) and must not be reused before it. */
+int mfb_step_host_async(mfb_engine *eng, const int32_t *h_actions, float *h_reward, uint8_t *h_alive,
+                        float *h_mean_action, int32_t *h_done, void *stream, int *ticket);
+int mfb_host_wait(mfb_engine *eng, int ticket);
+
 const char *mfb_last_error(void);
 
 /* ---- K6: Ising tabular mean-field Q-learning, one fused sweep over a batch of lattices -----------------

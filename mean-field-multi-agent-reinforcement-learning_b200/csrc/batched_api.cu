@@ -16,8 +16,26 @@ struct mfb_engine {
     float *d_reward = nullptr, *d_mean = nullptr;
     uint8_t *d_alive = nullptr;
     size_t staged_slots = 0;
+    // pipelined host path (mfb_step_host_async): two staging sets, copy streams, events
+    struct Slot {
+        int32_t *d_actions = nullptr, *d_done = nullptr; float *d_reward = nullptr, *d_mean = nullptr;
+        uint8_t *d_alive = nullptr;
+        cudaEvent_t in_done = nullptr, step_done = nullptr, out_done = nullptr;
+        bool used = false;
+    } slot[2];
+    cudaStream_t cs_in = nullptr, cs_out = nullptr;
+    size_t async_slots = 0;
+    unsigned long long async_calls = 0;
     ~mfb_engine() {
         cudaFree(d_actions); cudaFree(d_done); cudaFree(d_reward); cudaFree(d_mean); cudaFree(d_alive);
+        for (Slot &s : slot) {
+            cudaFree(s.d_actions); cudaFree(s.d_done); cudaFree(s.d_reward); cudaFree(s.d_mean); cudaFree(s.d_alive);
+            if (s.in_done) cudaEventDestroy(s.in_done);
+            if (s.step_done) cudaEventDestroy(s.step_done);
+            if (s.out_done) cudaEventDestroy(s.out_done);
+        }
+        if (cs_in) cudaStreamDestroy(cs_in);
+        if (cs_out) cudaStreamDestroy(cs_out);
     }
 };
 
@@ -206,6 +224,68 @@ int mfb_step_host(mfb_engine *h, const int32_t *h_actions, float *h_reward, uint
     if (h_done) MF_CUDA(cudaMemcpyAsync(h_done, h->d_done, ne * 4, cudaMemcpyDeviceToHost, st));
     MF_CUDA(cudaStreamSynchronize(st));
     MFB_END("mfb_step_host")
+}
+
+int mfb_step_host_async(mfb_engine *h, const int32_t *h_actions, float *h_reward, uint8_t *h_alive,
+                        float *h_mean_action, int32_t *h_done, void *stream, int *ticket) {
+    MFB_BEGIN
+    Engine &e = E(h);
+    cudaStream_t st = (cudaStream_t)stream;
+    e.commit(st);
+    const size_t n = e.slots(), ne = (size_t)e.n_envs(), na = (size_t)e.n_action();
+    if (!h->cs_in) {
+        MF_CUDA(cudaStreamCreateWithFlags(&h->cs_in, cudaStreamNonBlocking));
+        MF_CUDA(cudaStreamCreateWithFlags(&h->cs_out, cudaStreamNonBlocking));
+        for (mfb_engine::Slot &s : h->slot) {
+            MF_CUDA(cudaEventCreateWithFlags(&s.in_done, cudaEventDisableTiming));
+            MF_CUDA(cudaEventCreateWithFlags(&s.step_done, cudaEventDisableTiming));
+            MF_CUDA(cudaEventCreateWithFlags(&s.out_done, cudaEventDisableTiming));
+        }
+    }
+    if (h->async_slots != n) {
+        MF_CUDA(cudaDeviceSynchronize());
+        for (mfb_engine::Slot &s : h->slot) {
+            cudaFree(s.d_actions); cudaFree(s.d_done); cudaFree(s.d_reward); cudaFree(s.d_mean); cudaFree(s.d_alive);
+            MF_CUDA(cudaMalloc(&s.d_actions, n * 4)); MF_CUDA(cudaMalloc(&s.d_reward, n * 4));
+            MF_CUDA(cudaMalloc(&s.d_alive, n)); MF_CUDA(cudaMalloc(&s.d_mean, ne * 2 * na * 4));
+            MF_CUDA(cudaMalloc(&s.d_done, ne * 4));
+            s.used = false;
+        }
+        h->async_slots = n;
+    }
+    const int which = (int)(h->async_calls++ & 1);
+    mfb_engine::Slot &s = h->slot[which];
+    // inputs: this slot's action buffer is free once the k_step that read it two calls ago has finished
+    if (s.used) MF_CUDA(cudaStreamWaitEvent(h->cs_in, s.step_done, 0));
+    MF_CUDA(cudaMemcpyAsync(s.d_actions, h_actions, n * 4, cudaMemcpyHostToDevice, h->cs_in));
+    MF_CUDA(cudaEventRecord(s.in_done, h->cs_in));
+    // step: after the actions landed, and after this slot's previous results were copied out
+    MF_CUDA(cudaStreamWaitEvent(st, s.in_done, 0));
+    if (s.used) MF_CUDA(cudaStreamWaitEvent(st, s.out_done, 0));
+    StepIO io{};
+    io.actions = s.d_actions; io.reward = s.d_reward; io.alive = s.d_alive; io.mean_action = s.d_mean; io.done = s.d_done;
+    io.phases = PH_SETACT | PH_STEP | PH_EXPORT | PH_CLEAR | (h->auto_reset ? PH_AUTORESET : 0);
+    io.setact_mask = 3; io.group_seq[0] = 0; io.group_seq[1] = 1;
+    e.step(io, st);
+    MF_CUDA(cudaEventRecord(s.step_done, st));
+    // outputs: on the second copy stream, overlapping whatever the caller launches next on `stream`
+    MF_CUDA(cudaStreamWaitEvent(h->cs_out, s.step_done, 0));
+    if (h_reward) MF_CUDA(cudaMemcpyAsync(h_reward, s.d_reward, n * 4, cudaMemcpyDeviceToHost, h->cs_out));
+    if (h_alive) MF_CUDA(cudaMemcpyAsync(h_alive, s.d_alive, n, cudaMemcpyDeviceToHost, h->cs_out));
+    if (h_mean_action) MF_CUDA(cudaMemcpyAsync(h_mean_action, s.d_mean, ne * 2 * na * 4, cudaMemcpyDeviceToHost, h->cs_out));
+    if (h_done) MF_CUDA(cudaMemcpyAsync(h_done, s.d_done, ne * 4, cudaMemcpyDeviceToHost, h->cs_out));
+    MF_CUDA(cudaEventRecord(s.out_done, h->cs_out));
+    s.used = true;
+    if (ticket) *ticket = which;
+    MFB_END("mfb_step_host_async")
+}
+
+int mfb_host_wait(mfb_engine *h, int ticket) {
+    MFB_BEGIN
+    E(h);
+    if (ticket < 0 || ticket > 1) throw Fatal("mfb_host_wait: bad ticket");
+    if (h->slot[ticket].used) MF_CUDA(cudaEventSynchronize(h->slot[ticket].out_done));
+    MFB_END("mfb_host_wait")
 }
 
 const char *mfb_last_error(void) { return last_error(); }

@@ -140,6 +140,18 @@ class BatchedGridWorld:
             check(self.lib.mfb_step_host(self._h, _ptr(h_actions), _ptr(h_reward), _ptr(h_alive),
                                          _ptr(h_mean), _ptr(h_done), _stream()))
 
+    def step_host_async(self, h_actions, h_reward, h_alive, h_mean, h_done):
+        """Pipelined end-to-end step: enqueue upload + k_step + download and return a ticket (0/1); the
+        pinned result tensors are valid after host_wait(ticket)."""
+        ticket = ctypes.c_int()
+        with torch.cuda.device(self.device):
+            check(self.lib.mfb_step_host_async(self._h, _ptr(h_actions), _ptr(h_reward), _ptr(h_alive),
+                                               _ptr(h_mean), _ptr(h_done), _stream(), ctypes.byref(ticket)))
+        return ticket.value
+
+    def host_wait(self, ticket):
+        check(self.lib.mfb_host_wait(self._h, ticket))
+
     # ------------------------------------------------------------ read-back
     _GET = {"num": ("i4", lambda E, c: (E, 2)), "dead_ct": ("i4", lambda E, c: (E, 2)),
             "pos": ("i4", lambda E, c: (E, 2, c, 2)), "hp": ("f4", lambda E, c: (E, 2, c)),

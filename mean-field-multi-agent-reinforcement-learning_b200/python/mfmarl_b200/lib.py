@@ -50,6 +50,8 @@ def load_library(path=None):
         "mfb_get": [vp, cp, vp, vp],
         "mfb_num_device_ptr": [vp, ctypes.POINTER(vp)],
         "mfb_step_host": [vp, vp, vp, vp, vp, vp, vp],
+        "mfb_step_host_async": [vp, vp, vp, vp, vp, vp, vp, ctypes.POINTER(ci)],
+        "mfb_host_wait": [vp, ci],
     }
     for name, argtypes in sig.items():
         fn = getattr(lib, name)

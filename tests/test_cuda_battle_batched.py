@@ -214,3 +214,57 @@ def test_full_size_properties_4096_envs():
         for e in (0, 1, E // 2, E - 1):
             live = np.concatenate([cells[e, g, :num2[e, g]] for g in range(2)])
             assert len(np.unique(live)) == len(live), "two agents in one cell"
+
+
+def test_host_buffer_paths_match_the_device_path():
+    """mfb_step_host (synchronous) and mfb_step_host_async (pipelined, two staging sets) give the results of
+    mfb_step bit for bit (rows beyond num are unspecified and not compared)."""
+    from mfmarl_b200 import BatchedGridWorld
+    left, right = generate_map_positions(40)
+    E = 5
+    envs = []
+    for _ in range(3):
+        env = BatchedGridWorld(E, rng="philox", seed=3)
+        env.reset(); env.add_agents(0, left); env.add_agents(1, right)
+        envs.append(env)
+    dev, sync_env, async_env = envs
+
+    def pinned_set():
+        return (torch.empty((E, 2, 64), dtype=torch.float32).pin_memory(),
+                torch.empty((E, 2, 64), dtype=torch.uint8).pin_memory(),
+                torch.empty((E, 2, 21), dtype=torch.float32).pin_memory(),
+                torch.empty((E,), dtype=torch.int32).pin_memory())
+
+    def same(got, want, num):
+        for e in range(E):
+            for g in range(2):
+                n = num[e, g]
+                assert torch.equal(got[0][e, g, :n], want[0][e, g, :n])
+                assert torch.equal(got[1][e, g, :n], want[1][e, g, :n])
+        assert torch.equal(got[2], want[2]) and torch.equal(got[3], want[3])
+
+    sync_out, async_out = pinned_set(), [pinned_set(), pinned_set()]
+    rng = np.random.RandomState(12)
+    prev, deaths, ticket = None, 0, 0
+    for s in range(80):
+        pos, num = dev.get("pos"), dev.get_num()
+        acts = np.zeros((E, 2, 64), np.int32)
+        for e in range(E):
+            for g in range(2):
+                acts[e, g, :num[e, g]] = fight_actions(rng, pos[e, g, :num[e, g]], 40)
+        h_act = torch.from_numpy(acts).pin_memory()
+        r, a, d, m = dev.step(h_act.cuda())
+        cur = tuple(t.cpu().clone() for t in (r, a, m, d))
+        sync_env.step_host(h_act, *sync_out)
+        same(sync_out, cur, num)
+        ticket = async_env.step_host_async(h_act, *async_out[s & 1])
+        if prev is not None:             # consume the previous step while this one is in flight
+            async_env.host_wait(ticket ^ 1)
+            same(async_out[(s - 1) & 1], prev[0], prev[1])
+        prev = (cur, num.copy())
+        for e in range(E):
+            for g in range(2):
+                deaths += int((cur[1][e, g, :num[e, g]] == 0).sum())
+    async_env.host_wait(ticket)
+    same(async_out[79 & 1], prev[0], prev[1])
+    assert deaths > 10
