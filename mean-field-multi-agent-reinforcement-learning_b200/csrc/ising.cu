@@ -225,6 +225,209 @@ static void launch_ising(const IsingArgs<T> &A, cudaStream_t st) {
     MF_CUDA(cudaGetLastError());
 }
 
+
+// ----------------------------------------------------------------------------------------------
+// K6r: RESIDENT variant -- K sweeps per launch with the Q table in shared memory.
+//
+// The streaming kernel above moves every site's Q pair through HBM once per sweep (14 B/site-step
+// algorithmic, 45-60 B real in the disordered phase because the plane index s is data dependent and
+// 32-byte sectors are only partly used).  Here a lattice is cut into C horizontal strips, one CTA each,
+// the C CTAs forming one thread-block cluster; a CTA keeps its strip of Q ([5][rows*L][2], up to 160 KB) and
+// both bit-packed spin buffers in shared memory for all K sweeps and reads the neighbour strips' boundary
+// rows through distributed shared memory.  One cluster barrier per sweep suffices: a sweep reads the "old"
+// buffer (own + halo) and writes only its own "new" buffer, the buffers swap every sweep, and a CTA can
+// only be one barrier ahead of its neighbours.  HBM traffic drops to (80 B load + 80 B store) / K per
+// site-step.  Draws use the same Philox keys as the streaming kernel -- (seed, lattice) x (column, global
+// row band, step) -- so K resident sweeps equal K streaming launches bit for bit.
+// C = 1 covers lattices whose whole Q fits one CTA (L <= 64 in fp32; the reference's 20 x 20 case);
+// 256 x 256 uses C = 16 (16 rows per CTA, 1024 threads = 256 columns x 4 bands).
+// ----------------------------------------------------------------------------------------------
+}  // namespace mfmarl
+#include <cooperative_groups.h>
+namespace mfmarl {
+namespace cg = cooperative_groups;
+
+template <typename T>
+struct IsingRunArgs {
+    int B, L, K, rows_per;         // lattices, side, sweeps, rows per CTA (= L / cluster size)
+    int8_t *spins; T *Q;
+    const T *temperatures;          // [K] device
+    T lr;
+    const T *u;                     // optional injected uniforms [K][B][L*L]
+    uint32_t seed, lattice_base, step0;
+    int32_t *n_up;                  // [K][B] out, must be zeroed by the caller
+    T *reward_sum;                  // [K][B] out or null, zeroed by the caller
+};
+
+template <typename T>
+__global__ void __launch_bounds__(1024, 1) k_ising_resident(const IsingRunArgs<T> A) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int L = A.L, N = L * L, wpr = (L + 31) >> 5, LP = wpr * 32, rows = A.rows_per;
+    const int b = blockIdx.x / C, row0 = rank * rows;
+    const int strip = rows * L;                          // sites in this CTA's strip
+
+    T *s_q = (T *)s_raw;                                 // [5][strip][2]
+    uint32_t *s_bits = (uint32_t *)(s_raw + (size_t)5 * strip * 2 * sizeof(T));   // [2][rows][wpr]
+    __shared__ int s_red_i;
+    __shared__ T s_red_r;
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int x = tid % LP, band = tid / LP, w = x >> 5;  // column, band (4 rows) inside the strip
+    const bool active = x < L;
+    const int xl = x == 0 ? L - 1 : x - 1, xr = x == L - 1 ? 0 : x + 1;
+    const size_t lbase = (size_t)b * N;
+
+    // ---- load: Q strip (5 contiguous plane slices) and spins -> bits ----
+    for (int sp = 0; sp < 5; sp++) {
+        const T *src = A.Q + (lbase * 5 + (size_t)sp * N + (size_t)row0 * L) * 2;
+        T *dst = s_q + (size_t)sp * strip * 2;
+        for (int i = tid; i < strip * 2; i += blockDim.x) dst[i] = src[i];
+    }
+#pragma unroll
+    for (int j = 0; j < kIsingRB; j++) {
+        const int r = band * kIsingRB + j;
+        int v = 0;
+        if (r < rows && active) v = A.spins[lbase + (size_t)(row0 + r) * L + x];
+        const uint32_t word = __ballot_sync(0xFFFFFFFFu, v != 0);
+        if (r < rows && lane == 0) s_bits[r * wpr + w] = word;
+    }
+    cluster.sync();
+
+    const int up_rank = (rank + C - 1) % C, dn_rank = (rank + 1) % C;
+    int cur = 0;                                          // which bit buffer holds the current lattice
+    for (int k = 0; k < A.K; k++, cur ^= 1) {
+        const uint32_t *old_own = s_bits + cur * rows * wpr;
+        uint32_t *new_own = s_bits + (cur ^ 1) * rows * wpr;
+        const uint32_t *old_up = cluster.map_shared_rank(s_bits, up_rank) + cur * rows * wpr + (rows - 1) * wpr;
+        const uint32_t *old_dn = cluster.map_shared_rank(s_bits, dn_rank) + cur * rows * wpr;
+        const T temperature = A.temperatures[k];
+        if (tid == 0) { s_red_i = 0; s_red_r = (T)0; }
+
+        // ---- phase 1: neighbour counts on the old lattice, Boltzmann draw, publish new bits ----
+        T keep_q[kIsingRB]; int keep_sa[kIsingRB];
+        T uu[kIsingRB];
+        const int gband = (row0 >> 2) + band;             // global band index: same Philox counter as k_ising
+        if (A.u != nullptr) {
+#pragma unroll
+            for (int j = 0; j < kIsingRB; j++) {
+                const int r = band * kIsingRB + j;
+                uu[j] = (r < rows && active) ? A.u[((size_t)k * A.B + b) * N + (size_t)(row0 + r) * L + x] : (T)0;
+            }
+        } else if (sizeof(T) == 4) {
+            const uint4 rnd = philox4x32_10(make_uint4((uint32_t)x, (uint32_t)gband, A.step0 + (uint32_t)k, 0u),
+                                            make_uint2(A.seed, A.lattice_base + (uint32_t)b));
+            uu[0] = uniform_from_bits<T>(rnd.x, 0); uu[1] = uniform_from_bits<T>(rnd.y, 0);
+            uu[2] = uniform_from_bits<T>(rnd.z, 0); uu[3] = uniform_from_bits<T>(rnd.w, 0);
+        } else {
+            const uint2 key = make_uint2(A.seed, A.lattice_base + (uint32_t)b);
+            const uint4 r1 = philox4x32_10(make_uint4((uint32_t)x, (uint32_t)gband, A.step0 + (uint32_t)k, 0u), key);
+            const uint4 r2 = philox4x32_10(make_uint4((uint32_t)x, (uint32_t)gband, A.step0 + (uint32_t)k, 1u), key);
+            uu[0] = uniform_from_bits<T>(r1.x, r1.y); uu[1] = uniform_from_bits<T>(r1.z, r1.w);
+            uu[2] = uniform_from_bits<T>(r2.x, r2.y); uu[3] = uniform_from_bits<T>(r2.z, r2.w);
+        }
+#pragma unroll
+        for (int j = 0; j < kIsingRB; j++) {
+            const int r = band * kIsingRB + j;
+            int a = 0, sv = 0; T q0 = (T)0, q1 = (T)0;
+            if (r < rows && active) {
+                const int up = r == 0 ? (int)((old_up[x >> 5] >> (x & 31)) & 1u) : bit_at(old_own, wpr, r - 1, x);
+                const int dn = r == rows - 1 ? (int)((old_dn[x >> 5] >> (x & 31)) & 1u) : bit_at(old_own, wpr, r + 1, x);
+                sv = up + dn + bit_at(old_own, wpr, r, xl) + bit_at(old_own, wpr, r, xr);
+                const typename Pair<T>::type pr = *(const typename Pair<T>::type *)(s_q + ((size_t)sv * strip + r * L + x) * 2);
+                q0 = pr.x; q1 = pr.y;
+                a = uu[j] >= action_threshold(q0, q1, temperature) ? 1 : 0;
+            }
+            const uint32_t word = __ballot_sync(0xFFFFFFFFu, a != 0);
+            if (r < rows && lane == 0) new_own[r * wpr + w] = word;
+            keep_q[j] = a ? q1 : q0;
+            keep_sa[j] = sv | (a << 3);
+        }
+        cluster.sync();   // every strip's new bits are published (and the reduction cells are reset)
+
+        // ---- phase 2: reward on the new lattice, Q update in shared memory ----
+        const uint32_t *new_up = cluster.map_shared_rank(s_bits, up_rank) + (cur ^ 1) * rows * wpr + (rows - 1) * wpr;
+        const uint32_t *new_dn = cluster.map_shared_rank(s_bits, dn_rank) + (cur ^ 1) * rows * wpr;
+        int nup = 0; T rsum = (T)0;
+#pragma unroll
+        for (int j = 0; j < kIsingRB; j++) {
+            const int r = band * kIsingRB + j;
+            if (r < rows && active) {
+                const int s = keep_sa[j] & 7, a = keep_sa[j] >> 3;
+                const int up = r == 0 ? (int)((new_up[x >> 5] >> (x & 31)) & 1u) : bit_at(new_own, wpr, r - 1, x);
+                const int dn = r == rows - 1 ? (int)((new_dn[x >> 5] >> (x & 31)) & 1u) : bit_at(new_own, wpr, r + 1, x);
+                const int ups = up + dn + bit_at(new_own, wpr, r, xl) + bit_at(new_own, wpr, r, xr);
+                const T reward = (T)0.5 * (T)(2 * a - 1) * (T)(2 * ups - 4);
+                s_q[((size_t)s * strip + r * L + x) * 2 + a] = keep_q[j] + A.lr * (reward - keep_q[j]);
+                nup += a; rsum += reward;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            nup += __shfl_xor_sync(0xFFFFFFFFu, nup, o);
+            rsum += __shfl_xor_sync(0xFFFFFFFFu, rsum, o);
+        }
+        if (lane == 0) { atomicAdd(&s_red_i, nup); if (A.reward_sum) atomicAdd(&s_red_r, rsum); }
+        __syncthreads();
+        if (tid == 0) {
+            atomicAdd(&A.n_up[(size_t)k * A.B + b], s_red_i);
+            if (A.reward_sum) atomicAdd(&A.reward_sum[(size_t)k * A.B + b], s_red_r);
+        }
+        __syncthreads();   // s_red_* are rewritten at the top of the next sweep
+    }
+
+    // ---- store: Q strip and the final spins ----
+    for (int sp = 0; sp < 5; sp++) {
+        T *dst = A.Q + (lbase * 5 + (size_t)sp * N + (size_t)row0 * L) * 2;
+        const T *src = s_q + (size_t)sp * strip * 2;
+        for (int i = tid; i < strip * 2; i += blockDim.x) dst[i] = src[i];
+    }
+    const uint32_t *fin = s_bits + cur * rows * wpr;
+#pragma unroll
+    for (int j = 0; j < kIsingRB; j++) {
+        const int r = band * kIsingRB + j;
+        if (r < rows && active) A.spins[lbase + (size_t)(row0 + r) * L + x] = (int8_t)bit_at(fin, wpr, r, x);
+    }
+    cluster.sync();       // nobody leaves while a neighbour may still read its shared memory
+}
+
+// cluster size for a lattice side, 0 = the resident kernel does not apply
+template <typename T>
+static int resident_cluster_size(int L) {
+    const int wpr = (L + 31) >> 5, LP = wpr * 32;
+    for (int C = 1; C <= 16; C *= 2) {
+        if (L % C) continue;
+        const int rows = L / C;
+        if (C > 1 && rows % kIsingRB) continue;
+        const int bands = (rows + kIsingRB - 1) / kIsingRB;
+        const size_t smem = (size_t)5 * rows * L * 2 * sizeof(T) + (size_t)2 * rows * wpr * 4;
+        if (LP * bands <= 1024 && smem <= 200 * 1024) return C;
+    }
+    return 0;
+}
+
+template <typename T>
+static void launch_ising_resident(const IsingRunArgs<T> &A0, cudaStream_t st) {
+    IsingRunArgs<T> A = A0;
+    const int L = A.L, wpr = (L + 31) >> 5, LP = wpr * 32;
+    const int C = resident_cluster_size<T>(L);
+    if (C == 0) throw Fatal("ising resident kernel: lattice side " + std::to_string(L) + " not supported (use mfi_step)");
+    A.rows_per = L / C;
+    const int bands = (A.rows_per + kIsingRB - 1) / kIsingRB;
+    const size_t smem = (size_t)5 * A.rows_per * L * 2 * sizeof(T) + (size_t)2 * A.rows_per * wpr * 4;
+    MF_CUDA(cudaFuncSetAttribute(k_ising_resident<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (C > 8) MF_CUDA(cudaFuncSetAttribute(k_ising_resident<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(A.B * C)); cfg.blockDim = dim3((unsigned)(LP * bands));
+    cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    MF_CUDA(cudaLaunchKernelEx(&cfg, k_ising_resident<T>, A));
+}
+
 }  // namespace mfmarl
 
 using namespace mfmarl;
@@ -247,6 +450,33 @@ extern "C" int mfi_step(int dtype, int n_lattices, int side, int8_t *d_spins, vo
         } else throw Fatal("mfi_step: dtype must be 0 (f32) or 1 (f64)");
     } catch (const std::exception &ex) {
         set_last_error(std::string("mfi_step: ") + ex.what());
+        return -1;
+    }
+    return 0;
+}
+
+extern "C" int mfi_resident_cluster_size(int dtype, int side) {
+    return dtype == 1 ? resident_cluster_size<double>(side) : resident_cluster_size<float>(side);
+}
+
+extern "C" int mfi_run(int dtype, int n_lattices, int side, int n_sweeps, int8_t *d_spins, void *d_q,
+                       const void *d_temperatures, double lr, const void *d_uniforms, unsigned seed,
+                       unsigned lattice_base, unsigned step0, int32_t *d_n_up, void *d_reward_sum, void *stream) {
+    try {
+        if (n_sweeps < 1 || n_lattices < 1) throw Fatal("mfi_run: need at least one sweep and one lattice");
+        if (dtype == 0) {
+            IsingRunArgs<float> A{n_lattices, side, n_sweeps, 0, d_spins, (float *)d_q, (const float *)d_temperatures,
+                                  (float)lr, (const float *)d_uniforms, seed, lattice_base, step0, d_n_up,
+                                  (float *)d_reward_sum};
+            launch_ising_resident(A, (cudaStream_t)stream);
+        } else if (dtype == 1) {
+            IsingRunArgs<double> A{n_lattices, side, n_sweeps, 0, d_spins, (double *)d_q, (const double *)d_temperatures,
+                                   lr, (const double *)d_uniforms, seed, lattice_base, step0, d_n_up,
+                                   (double *)d_reward_sum};
+            launch_ising_resident(A, (cudaStream_t)stream);
+        } else throw Fatal("mfi_run: dtype must be 0 (f32) or 1 (f64)");
+    } catch (const std::exception &ex) {
+        set_last_error(std::string("mfi_run: ") + ex.what());
         return -1;
     }
     return 0;

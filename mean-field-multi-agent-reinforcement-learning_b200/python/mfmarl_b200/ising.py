@@ -33,6 +33,13 @@ class IsingMFQ:
                                       ctypes.c_uint, ctypes.c_uint, ctypes.c_uint, ctypes.c_void_p,
                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         self.lib.mfi_step.restype = ctypes.c_int
+        self.lib.mfi_run.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p,
+                                     ctypes.c_uint, ctypes.c_uint, ctypes.c_uint, ctypes.c_void_p, ctypes.c_void_p,
+                                     ctypes.c_void_p]
+        self.lib.mfi_run.restype = ctypes.c_int
+        self.lib.mfi_resident_cluster_size.argtypes = [ctypes.c_int, ctypes.c_int]
+        self.lib.mfi_resident_cluster_size.restype = ctypes.c_int
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         self.B, self.L, self.N = n_lattices, side, side * side
         self.dtype, self.seed, self.lr, self.lattice_base = dtype, seed, lr, lattice_base
@@ -64,6 +71,40 @@ class IsingMFQ:
                                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
         self.t += 1
         return self.n_up, self.reward_sum, self.mse
+
+    @property
+    def resident_cluster(self):
+        """CTAs per lattice of the shared-memory-resident kernel, 0 if this shape only streams."""
+        return self.lib.mfi_resident_cluster_size(_DTYPES[self.dtype], self.L)
+
+    def run(self, temperatures, uniforms=None, resident=None):
+        """len(temperatures) sweeps.  With the resident kernel (default when the shape allows) they run in ONE
+        launch with Q in shared memory; otherwise one streaming launch per sweep.  Both give the same bits.
+        Returns (n_up int32 [K, B], reward_sum [K, B])."""
+        temps = torch.as_tensor(temperatures, dtype=self.dtype, device=self.device).contiguous()
+        K = int(temps.numel())
+        if resident is None:
+            resident = self.resident_cluster > 0
+        n_up = torch.zeros((K, self.B), dtype=torch.int32, device=self.device)
+        rsum = torch.zeros((K, self.B), dtype=self.dtype, device=self.device)
+        if uniforms is not None:
+            assert uniforms.dtype == self.dtype and uniforms.is_cuda and uniforms.is_contiguous()
+            assert tuple(uniforms.shape) == (K, self.B, self.N)
+        if resident:
+            with torch.cuda.device(self.device):
+                check(self.lib.mfi_run(_DTYPES[self.dtype], self.B, self.L, K, _ptr(self.spins), _ptr(self.Q),
+                                       _ptr(temps), float(self.lr), _ptr(uniforms), self.seed, self.lattice_base,
+                                       self.t, _ptr(n_up), _ptr(rsum),
+                                       ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            self.t += K
+            self.n_up.copy_(n_up[-1])
+        else:
+            host_t = temps.cpu().tolist()
+            for k in range(K):
+                self.step(host_t[k], uniforms=None if uniforms is None else uniforms[k])
+                n_up[k].copy_(self.n_up)
+                rsum[k].copy_(self.reward_sum)
+        return n_up, rsum
 
     def order_param(self):
         """|n_up - n_down| / N per lattice (core.py:106-110), from the last step's up counts."""

@@ -136,3 +136,41 @@ def test_full_size_256x256_properties():
         sig = (2 * s - 1).to(torch.float32)
         bonds = (sig * torch.roll(sig, 1, 1)).sum(dim=(1, 2)) + (sig * torch.roll(sig, 1, 2)).sum(dim=(1, 2))
         assert torch.allclose(m.reward_sum, bonds, rtol=1e-5, atol=1e-2)
+
+
+@pytest.mark.parametrize("L,B,K", [(20, 5, 30), (64, 3, 12), (128, 2, 8), (256, 3, 6)])
+def test_resident_kernel_equals_streaming_bit_for_bit(L, B, K):
+    """K sweeps in one launch with Q resident in shared memory (cluster of 1 / 1 / 4 / 16 CTAs per lattice,
+    DSMEM halos) give exactly the spins, Q and per-sweep statistics of K streaming launches (same Philox keys)."""
+    from mfmarl_b200 import IsingMFQ
+    rng = np.random.RandomState(L)
+    spins = torch.from_numpy(rng.randint(0, 2, size=(B, L, L)).astype(np.int8))
+    a = IsingMFQ(B, L, seed=21, spins=spins)
+    b = IsingMFQ(B, L, seed=21, spins=spins)
+    assert a.resident_cluster == {20: 1, 64: 1, 128: 4, 256: 16}[L]
+    temps = [max(0.8, 0.3 * 0.99)] * K
+    for rounds in range(2):            # two launches: state carries over (step counter, spins, Q)
+        n_res, r_res = a.run(temps, resident=True)
+        n_str, r_str = b.run(temps, resident=False)
+        assert torch.equal(a.spins, b.spins)
+        assert torch.equal(a.Q, b.Q)
+        assert torch.equal(n_res, n_str)
+        assert torch.allclose(r_res, r_str, rtol=1e-6, atol=1e-3)   # float sums, different reduction order
+    assert not torch.equal(a.spins[0], spins[0].cuda())
+
+
+def test_resident_kernel_matches_oracle_fp64_with_injected_uniforms():
+    from mfmarl_b200 import IsingMFQ
+    B, L, K, T = 3, 20, 25, 0.8
+    rng = np.random.RandomState(77)
+    spins = rng.randint(0, 2, size=(B, L, L)).astype(np.int8)
+    m = IsingMFQ(B, L, dtype=torch.float64, spins=torch.from_numpy(spins))
+    u = rng.random_sample((K, B, L * L))
+    n_up, rsum = m.run([T] * K, uniforms=torch.from_numpy(u).cuda(), resident=True)
+    Q = np.zeros((B, 5, L * L, 2))
+    for k in range(K):
+        spins, Q, info = ising_oracle.step(spins, Q, T, 0.1, u[k])
+        assert np.array_equal(n_up[k].cpu().numpy(), info["n_up"])
+        np.testing.assert_allclose(rsum[k].cpu().numpy(), info["reward_sum"], rtol=1e-12, atol=1e-12)
+    assert np.array_equal(m.spins.cpu().numpy(), spins)
+    np.testing.assert_allclose(m.Q.cpu().numpy(), Q, rtol=1e-13, atol=1e-15)
