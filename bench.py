@@ -200,16 +200,28 @@ def run_ours(args):
     wl = WORKLOADS[args.workload]
     E, cap, K, W = args.envs or wl["envs"], wl["cap"], args.steps, args.warmup
     left, right = placement(wl)
-    env = BatchedGridWorld(E, map_size=wl["map_size"], capacity=cap, device=dev, rng="philox", seed=0,
-                           env_base=rank * E, max_steps=wl["max_steps"], auto_reset=True,
-                           obs_tile_agents=args.obs_tile, step_threads=args.step_threads)
-    env.reset(); env.add_agents(0, left); env.add_agents(1, right)
+    # --pipeline P: the GPU's envs are split into P engines on P streams, so that the latency-bound k_step of one
+    # part runs under the bandwidth-bound k_obs of the next (what a double-buffered actor loop does).  P = 1: one
+    # engine, kernels back to back on one stream.
+    P = max(1, args.pipeline)
+    assert E % P == 0
+    Eh = E // P
+    envs = []
+    for h in range(P):
+        env = BatchedGridWorld(Eh, map_size=wl["map_size"], capacity=cap, device=dev, rng="philox", seed=0,
+                               env_base=rank * E + h * Eh, max_steps=wl["max_steps"], auto_reset=True,
+                               obs_tile_agents=args.obs_tile, step_threads=args.step_threads)
+        env.reset(); env.add_agents(0, left); env.add_agents(1, right)
+        envs.append(env)
+    streams = [torch.cuda.current_stream()] if P == 1 else [torch.cuda.Stream(device=dev) for _ in range(P)]
 
     # synthetic actions, uniform{0..20} from torch's Philox generator, resident in HBM: a pool the steps cycle through
     gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
     POOL = 8
-    pool = [torch.randint(0, 21, (E, 2, cap), generator=gen, device=dev, dtype=torch.int32) for _ in range(POOL)]
-    view, feat = env.observe()        # allocates the observation block (E*2*cap*4868 B)
+    pool = [[torch.randint(0, 21, (Eh, 2, cap), generator=gen, device=dev, dtype=torch.int32) for _ in range(POOL)]
+            for _ in range(P)]
+    for env in envs:
+        env.observe()                 # allocates the observation block (E*2*cap*4868 B in total)
 
     def barrier():
         torch.cuda.synchronize()
@@ -217,65 +229,85 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    def agent_steps_total():
+        return sum(int(env.get("agent_steps").sum()) for env in envs)
+
     for k in range(W):
-        env.observe(); env.step(pool[k % POOL])
+        for h, env in enumerate(envs):
+            with torch.cuda.stream(streams[h]):
+                env.observe(); env.step(pool[h][k % POOL])
     barrier()
 
-    # ---- timed region: exactly K steps, CUDA events on the launching stream ----
-    as0 = int(env.get("agent_steps").sum())
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # ---- timed region: exactly K steps, CUDA events on the launching streams ----
+    as0 = agent_steps_total()
+    ev = [[[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)] for _ in range(P)]
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = [torch.cuda.Event(enable_timing=True) for _ in range(P)]
     barrier()
     with ClockSampler(local) as clocks:
         t0.record()
+        for h in range(P):
+            streams[h].wait_event(t0)
         for k in range(K):
-            ev[k][0].record()
-            env.observe()
-            ev[k][1].record()
-            env.step(pool[k % POOL])
-            ev[k][2].record()
-        t1.record()
+            for h, env in enumerate(envs):
+                with torch.cuda.stream(streams[h]):
+                    ev[h][k][0].record(streams[h])
+                    env.observe()
+                    ev[h][k][1].record(streams[h])
+                    env.step(pool[h][k % POOL])
+                    ev[h][k][2].record(streams[h])
+        for h in range(P):
+            t1[h].record(streams[h])
         barrier()
-    ms = t0.elapsed_time(t1)
-    agent_steps = int(env.get("agent_steps").sum()) - as0
-    obs_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / K
-    step_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / K
+    ms = max(t0.elapsed_time(t) for t in t1)
+    agent_steps = agent_steps_total() - as0
+    obs_ms = sum(e[0].elapsed_time(e[1]) for evh in ev for e in evh) / (K * P)     # per k_obs launch
+    step_ms = sum(e[1].elapsed_time(e[2]) for evh in ev for e in evh) / (K * P)    # per k_step launch
 
     # ---- e2e: actions from pinned host memory each step, results read back to pinned host memory each step.
     #      Pipelined like an actor loop: the upload of step t and the download of step t-1 ride on copy
     #      streams under k_obs; a step's results are consumed (waited for) before its buffers are reused ----
-    h_act = [p.cpu().pin_memory() for p in pool]
-    n_act = env.sizes["n_action"]
+    h_act = [[p.cpu().pin_memory() for p in pool[h]] for h in range(P)]
+    n_act = envs[0].sizes["n_action"]
 
     def result_set():
-        return (torch.empty((E, 2, cap), dtype=torch.float32).pin_memory(),
-                torch.empty((E, 2, cap), dtype=torch.uint8).pin_memory(),
-                torch.empty((E, 2, n_act), dtype=torch.float32).pin_memory(),
-                torch.empty((E,), dtype=torch.int32).pin_memory())
+        return (torch.empty((Eh, 2, cap), dtype=torch.float32).pin_memory(),
+                torch.empty((Eh, 2, cap), dtype=torch.uint8).pin_memory(),
+                torch.empty((Eh, 2, n_act), dtype=torch.float32).pin_memory(),
+                torch.empty((Eh,), dtype=torch.int32).pin_memory())
 
-    results = [result_set(), result_set()]
+    results = [[result_set(), result_set()] for _ in range(P)]
     for k in range(min(W, 4)):
-        env.observe()
-        env.host_wait(env.step_host_async(h_act[k % POOL], *results[k & 1]))
-    as1 = int(env.get("agent_steps").sum())
+        for h, env in enumerate(envs):
+            with torch.cuda.stream(streams[h]):
+                env.observe()
+                env.host_wait(env.step_host_async(h_act[h][k % POOL], *results[h][k & 1]))
+    as1 = agent_steps_total()
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = [torch.cuda.Event(enable_timing=True) for _ in range(P)]
     checksum = 0.0
     e0.record()
+    for h in range(P):
+        streams[h].wait_event(e0)
+    tickets = [0] * P
     for k in range(K):
-        env.observe()
-        ticket = env.step_host_async(h_act[k % POOL], *results[k & 1])   # H2D + k_step + D2H enqueued
-        if k >= 1:                                                       # consume step k-1's results on the host
-            env.host_wait(ticket ^ 1)
-            checksum += float(results[(k - 1) & 1][0][0, 0, 0])
-    env.host_wait(ticket)
-    checksum += float(results[(K - 1) & 1][0][0, 0, 0])
-    e1.record()
+        for h, env in enumerate(envs):
+            with torch.cuda.stream(streams[h]):
+                env.observe()
+                tickets[h] = env.step_host_async(h_act[h][k % POOL], *results[h][k & 1])   # H2D + k_step + D2H enqueued
+            if k >= 1:                                                  # consume step k-1's results on the host
+                env.host_wait(tickets[h] ^ 1)
+                checksum += float(results[h][(k - 1) & 1][0][0, 0, 0])
+    for h, env in enumerate(envs):
+        env.host_wait(tickets[h])
+        checksum += float(results[h][(K - 1) & 1][0][0, 0, 0])
+        e1[h].record(streams[h])
     barrier()
-    e2e_ms = e0.elapsed_time(e1)
-    e2e_agent_steps = int(env.get("agent_steps").sum()) - as1
-    h2d = h_act[0].numel() * 4
-    d2h = sum(t.numel() * t.element_size() for t in results[0])
+    e2e_ms = max(e0.elapsed_time(t) for t in e1)
+    e2e_agent_steps = agent_steps_total() - as1
+    h2d = P * h_act[0][0].numel() * 4
+    d2h = P * sum(t.numel() * t.element_size() for t in results[0][0])
 
     if world > 1:
         t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
@@ -289,7 +321,7 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        agents_per_launch = agent_steps / K
+        agents_per_launch = agent_steps / (K * P)
         achieved = agents_per_launch * BYTES_PER_AGENT_OBS / (obs_ms * 1e-3) / 1e9
         line = {
             "metric": "battle agent-steps/sec incl. obs+mean-action",
@@ -302,8 +334,9 @@ def run_ours(args):
                        "rng": "philox(seed, env, step)", "auto_reset": "done or %d steps" % wl["max_steps"],
                        "l2": "outputs per step (%.2f GB) exceed the 126 MB L2; no explicit flush"
                              % (E * 2 * cap * BYTES_PER_AGENT_OBS / 1e9),
-                       "sharding": "envs [r*E,(r+1)*E) on rank r, no collective on the env path"},
-            "gpu_launches": 2 * K,
+                       "sharding": "envs [r*E,(r+1)*E) on rank r, no collective on the env path",
+                       "pipeline": "%d engine(s) x %d envs on %d stream(s)" % (P, Eh, P)},
+            "gpu_launches": 2 * K * P,
             "kernels_ms": {"k_obs": obs_ms, "k_step": step_ms},
             "roofline": {"bound": "hbm", "kernel": "k_obs", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
@@ -486,6 +519,8 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's)")
     ap.add_argument("--cpu-steps", type=int, default=60000, help="timed steps per CPU-baseline worker")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--pipeline", type=int, default=1,
+                    help="split the GPU's envs into this many engines on separate streams (k_step under k_obs)")
     ap.add_argument("--obs-tile", type=int, default=0, help="agents per k_obs CTA (tuning; 0 = engine default)")
     ap.add_argument("--step-threads", type=int, default=0, help="threads per k_step CTA (tuning; 0 = auto)")
     args = ap.parse_args()

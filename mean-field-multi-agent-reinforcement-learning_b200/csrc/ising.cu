@@ -70,8 +70,11 @@ __device__ __forceinline__ double action_threshold(double q0, double q1, double 
     return p0 / (p0 + p1);
 }
 __device__ __forceinline__ float action_threshold(float q0, float q1, float T) {
-    // same quantity, written so that exp cannot overflow in fp32 at small T: e0/(e0+e1) = 1/(1+exp((q1-q0)/T))
-    return 1.0f / (1.0f + expf((q1 - q0) / T));
+    // same quantity, written so that exp cannot overflow in fp32 at small T: e0/(e0+e1) = 1/(1+exp((q1-q0)/T)).
+    // ex2.approx + rcp.approx: |error| of the threshold < 4e-6 for |q| <= 2, T >= 0.25 (2 + 1.16|x| ulp of exp),
+    // i.e. an action can differ from the fp64 reference only for draws that close to the threshold -- the same
+    // order as the fp32 rounding of u itself (2^-24).  The fp64 kernel mode evaluates the reference's formula.
+    return __frcp_rn(1.0f + __expf(__fdividef(q1 - q0, T)));
 }
 
 __device__ __forceinline__ int bit_at(const uint32_t *rows, int wpr, int r, int x) {
