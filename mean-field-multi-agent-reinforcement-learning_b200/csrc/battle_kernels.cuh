@@ -573,7 +573,11 @@ k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO i
         __syncthreads();
         for (int c = tid; c < 2 * kViewCells; c += kObsThreads) {
             const int gg = c >= kViewCells;
-            s_mini[c] = __fdiv_rn((float)s_cnt[c], (float)(gg ? n1 : n0));   // GridWorld.cc:372-377
+            // GridWorld.cc:372-377.  An empty group is unreachable in the reference's loop (done ends the episode
+            // first, and :357 would dereference agents[0]); the batched driver keeps stepping finished envs, so the
+            // 0/0 is defined as 0 here instead of NaN.
+            const int tot = gg ? n1 : n0;
+            s_mini[c] = tot > 0 ? __fdiv_rn((float)s_cnt[c], (float)tot) : 0.0f;
         }
         // (the barrier at the top of the first chunk orders s_mini before its readers)
         const float *mini_own = s_mini + g * kViewCells, *mini_oth = s_mini + (1 - g) * kViewCells;

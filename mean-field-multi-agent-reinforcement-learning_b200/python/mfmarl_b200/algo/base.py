@@ -1,0 +1,154 @@
+"""ValueNet: the Q-network shared by MF-Q and IL (reference algo/base.py:7-281, TF1 graph) in PyTorch.
+
+Architecture (base.py:123-190): view -> conv3x3x32 -> conv3x3x32 -> dense 256; feature -> dense 32;
+[mean action -> dense 64 -> dense 32 when use_mf]; concat -> dense 128 -> dense 64 -> dense n_actions.
+Eval and target copies, soft target update tau = 0.005 (base.py:84-92), masked MSE on the taken action
+(base.py:94-116), Adam 1e-4, gamma = 0.95.  Inputs may be numpy arrays (single-env binding) or CUDA tensors
+(batched engine: observations and mean actions never leave the device).
+"""
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def as_tensor(x, device, dtype=torch.float32):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=dtype, non_blocking=True)
+    return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype).to(device, non_blocking=True)
+
+
+def checkpoint_path(dir_path, stem, step):
+    """<dir>/<stem>_<step>.pt -- the reference writes tf.train.Saver files "<stem>_<step>" per scope."""
+    return os.path.join(dir_path, "%s_%s.pt" % (stem, step))
+
+
+def _dense(n_in, n_out):
+    layer = nn.Linear(n_in, n_out)
+    nn.init.xavier_uniform_(layer.weight)      # tf.layers default: glorot_uniform, zero bias
+    nn.init.zeros_(layer.bias)
+    return layer
+
+
+class QNet(nn.Module):
+    def __init__(self, view_space, feature_space, num_actions, use_mf):
+        super().__init__()
+        h, w, c = view_space
+        self.use_mf = use_mf
+        self.conv1 = nn.Conv2d(c, 32, 3)
+        self.conv2 = nn.Conv2d(32, 32, 3)
+        for conv in (self.conv1, self.conv2):
+            nn.init.xavier_uniform_(conv.weight)
+            nn.init.zeros_(conv.bias)
+        self.dense_obs = _dense(32 * (h - 4) * (w - 4), 256)
+        self.dense_emb = _dense(feature_space[0], 32)
+        width = 256 + 32
+        if use_mf:
+            self.prob_emb = _dense(num_actions, 64)
+            self.dense_act_prob = _dense(64, 32)
+            width += 32
+        self.dense2 = _dense(width, 128)
+        self.dense_out = _dense(128, 64)
+        self.q_value = _dense(64, num_actions)
+
+    def forward(self, view, feature, prob=None):
+        x = view.permute(0, 3, 1, 2)                      # engine layout is NHWC: a channels_last view, no copy
+        x = F.relu(self.conv2(F.relu(self.conv1(x))))
+        x = x.permute(0, 2, 3, 1).flatten(1)              # flatten in (H, W, C) order like the TF graph (base.py:134-136)
+        parts = [F.relu(self.dense_obs(x)), F.relu(self.dense_emb(feature))]
+        if self.use_mf:
+            parts.append(F.relu(self.dense_act_prob(F.relu(self.prob_emb(prob)))))
+        x = F.relu(self.dense2(torch.cat(parts, dim=1)))
+        return self.q_value(F.relu(self.dense_out(x)))
+
+
+class ValueNet:
+    def __init__(self, env, handle, name, update_every=5, use_mf=False, learning_rate=1e-4, tau=0.005, gamma=0.95,
+                 device=None):
+        self.env, self.name, self.handle = env, name, handle
+        self.view_space = tuple(env.get_view_space(handle))
+        assert len(self.view_space) == 3
+        self.feature_space = tuple(env.get_feature_space(handle))
+        self.num_actions = env.get_action_space(handle)[0]
+        self.update_every, self.use_mf = update_every, use_mf
+        self.temperature = 0.1
+        self.lr, self.tau, self.gamma = learning_rate, tau, gamma
+        self.device = torch.device(device if device is not None else ("cuda" if torch.cuda.is_available() else "cpu"))
+        self.eval_net = QNet(self.view_space, self.feature_space, self.num_actions, use_mf).to(self.device)
+        self.target_net = QNet(self.view_space, self.feature_space, self.num_actions, use_mf).to(self.device)
+        self.optimizer = torch.optim.Adam(self.eval_net.parameters(), lr=learning_rate)
+
+    # -- the reference exposes the variable list for the self-play soft copy (base.py:185-190, tools.py:566-569)
+    @property
+    def vars(self):
+        return list(self.eval_net.parameters()) + list(self.target_net.parameters())
+
+    def _inputs(self, view, feature, prob):
+        v, f = as_tensor(view, self.device), as_tensor(feature, self.device)
+        p = None
+        if self.use_mf:
+            assert prob is not None
+            p = as_tensor(prob, self.device)
+            if p.shape[0] == 1 and v.shape[0] != 1:
+                p = p.expand(v.shape[0], -1)
+        return v, f, p
+
+    @torch.no_grad()
+    def calc_target_q(self, **kwargs):
+        """base.py:192-220: r + (1 - done) * gamma * Q_target(s', m')[argmax_a Q_eval(s', m')]."""
+        v, f, p = self._inputs(kwargs["obs"], kwargs["feature"], kwargs.get("prob"))
+        t_q, e_q = self.target_net(v, f, p), self.eval_net(v, f, p)
+        q = t_q.gather(1, e_q.argmax(dim=1, keepdim=True)).squeeze(1)
+        rewards = as_tensor(kwargs["rewards"], self.device)
+        dones = as_tensor(kwargs["dones"], self.device)
+        return rewards + (1.0 - dones) * q * self.gamma
+
+    @torch.no_grad()
+    def update(self):
+        """soft target update (base.py:84-92, 223-226)."""
+        for t, e in zip(self.target_net.parameters(), self.eval_net.parameters()):
+            t.mul_(1.0 - self.tau).add_(e, alpha=self.tau)
+
+    @torch.no_grad()
+    def act(self, **kwargs):
+        """argmax of softmax(Q / temperature).  As in the reference (base.py:39,82,240,253) the temperature is
+        baked at 0.1 and argmax is taken, so `eps` does not change the choice.  Returns int32 actions: numpy
+        for numpy inputs, a device tensor for device inputs."""
+        view, feature = kwargs["state"][0], kwargs["state"][1]
+        self.temperature = kwargs.get("eps", self.temperature)
+        v, f, p = self._inputs(view, feature, kwargs.get("prob"))
+        if self.use_mf and not isinstance(kwargs["prob"], torch.Tensor):
+            assert len(kwargs["prob"]) == len(view)
+        actions = self.eval_net(v, f, p).argmax(dim=1).to(torch.int32)
+        return actions if isinstance(view, torch.Tensor) else actions.cpu().numpy()
+
+    def train(self, **kwargs):
+        """base.py:256-281: masked squared error between target_q and Q_eval(s, m)[a]."""
+        v, f, p = self._inputs(kwargs["state"][0], kwargs["state"][1], kwargs.get("prob"))
+        target_q = as_tensor(kwargs["target_q"], self.device)
+        mask = as_tensor(kwargs["masks"], self.device)
+        acts = as_tensor(kwargs["acts"], self.device, torch.int64)
+        e_q = self.eval_net(v, f, p).gather(1, acts.unsqueeze(1)).squeeze(1)
+        loss = ((target_q - e_q) ** 2 * mask).sum() / mask.sum()
+        self.optimizer.zero_grad(set_to_none=True)
+        loss.backward()
+        self.optimizer.step()
+        return float(loss), {"Eval-Q": round(float(e_q.mean()), 6), "Target-Q": round(float(target_q.mean()), 6)}
+
+    # -- checkpoints (q_learning.py:53-71,146-171 use tf.train.Saver per scope)
+    def _save(self, dir_path, stem, step):
+        os.makedirs(dir_path, exist_ok=True)
+        path = checkpoint_path(dir_path, stem, step)
+        torch.save({"eval": self.eval_net.state_dict(), "target": self.target_net.state_dict(),
+                    "optimizer": self.optimizer.state_dict()}, path)
+        print("[*] Model saved at: {}".format(path))
+
+    def _load(self, dir_path, stem, step):
+        path = checkpoint_path(dir_path, stem, step)
+        blob = torch.load(path, map_location=self.device)
+        self.eval_net.load_state_dict(blob["eval"])
+        self.target_net.load_state_dict(blob["target"])
+        self.optimizer.load_state_dict(blob["optimizer"])
+        print("[*] Loaded model from {}".format(path))
