@@ -59,6 +59,12 @@ int mfb_query(mfb_engine *eng, const char *key, int *out);
  * not written.  group_mask: 1 = group 0 only, 2 = group 1 only, 3 = both.                           */
 int mfb_observe(mfb_engine *eng, float *d_view, float *d_feature, int group_mask, void *stream);
 
+/* K1 with one output block PER GROUP, each [E][cap][...] and contiguous -- the layout a per-group policy network
+ * consumes without a gather (senario_battle.py:100-111 feeds models[g] its own group's rows).  A NULL view pointer
+ * skips that group. */
+int mfb_observe_groups(mfb_engine *eng, float *d_view0, float *d_feature0, float *d_view1, float *d_feature1,
+                       void *stream);
+
 /* K2, fused set_action(g0), set_action(g1), step, get_reward, get_alive, mean action, clear_dead.
  *   d_actions      int32[E][2][cap]       in
  *   d_attack_perm  int32[E][2*cap]        in, only for MFB_RNG_INJECT (else NULL)
@@ -83,6 +89,12 @@ int mfb_mean_action(const int32_t *d_actions /* [rows][cap] */, const int32_t *d
 int mfb_get(mfb_engine *eng, const char *key, void *host_buf, void *stream);
 /* device pointer to the live int32[E][2] agent counts (for masking on the device) */
 int mfb_num_device_ptr(mfb_engine *eng, const int32_t **out);
+
+/* device pointers to live engine state, valid until mfb_destroy (read-only for the caller; they change with every
+ * launch on the engine's stream; a placement made by mfb_add_agents reaches the device with the next launch or
+ * mfb_get): "num" int32[E][2], "id" int32[E][2][cap], "pos" int32[E][2][cap] (x | y << 16),
+ * "hp" float[E][2][cap], "step_ct" int32[E] */
+int mfb_state_device_ptr(mfb_engine *eng, const char *key, const void **out);
 
 /* Host-buffer convenience used for the end-to-end measurement: pinned-host actions in, results out.
  * Copies h_actions -> device, runs mfb_step (clear_dead = 1), copies the results back, synchronises. */

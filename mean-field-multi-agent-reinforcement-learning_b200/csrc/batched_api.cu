@@ -125,6 +125,15 @@ int mfb_observe(mfb_engine *h, float *d_view, float *d_feature, int group_mask, 
     MFB_END("mfb_observe")
 }
 
+int mfb_observe_groups(mfb_engine *h, float *d_view0, float *d_feature0, float *d_view1, float *d_feature1,
+                       void *stream) {
+    MFB_BEGIN
+    float *v[kGroups] = {d_view0, d_view1}, *f[kGroups] = {d_feature0, d_feature1};
+    const int mask = (d_view0 ? 1 : 0) | (d_view1 ? 2 : 0);
+    E(h).observe_groups(v, f, E(h).params().cap, mask, (cudaStream_t)stream);
+    MFB_END("mfb_observe_groups")
+}
+
 int mfb_step(mfb_engine *h, const int32_t *d_actions, const int32_t *d_attack_perm, float *d_reward,
              uint8_t *d_alive, float *d_mean_action, int32_t *d_done, int clear_dead, void *stream) {
     MFB_BEGIN
@@ -196,6 +205,20 @@ int mfb_num_device_ptr(mfb_engine *h, const int32_t **out) {
     MFB_BEGIN
     *out = E(h).state().num;
     MFB_END("mfb_num_device_ptr")
+}
+
+int mfb_state_device_ptr(mfb_engine *h, const char *key, const void **out) {
+    MFB_BEGIN
+    Engine &e = E(h);
+    const BattleState &S = e.state();
+    const std::string k(key);
+    if (k == "num") *out = S.num;
+    else if (k == "id") *out = S.id;
+    else if (k == "pos") *out = S.pos;
+    else if (k == "hp") *out = S.hp;
+    else if (k == "step_ct") *out = S.step_ct;
+    else throw Fatal("mfb_state_device_ptr: unknown key " + k);
+    MFB_END("mfb_state_device_ptr")
 }
 
 int mfb_step_host(mfb_engine *h, const int32_t *h_actions, float *h_reward, uint8_t *h_alive,

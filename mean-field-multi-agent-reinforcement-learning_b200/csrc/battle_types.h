@@ -91,8 +91,9 @@ struct StepIO {
 };
 
 struct ObsIO {
-    float *view;     // [E][2][cap][13][13][7]
-    float *feature;  // [E][2][cap][feature_size]
+    float *view[kGroups];     // per group: rows of env e start at e * env_stride agent rows ([13][13][7] each)
+    float *feature[kGroups];  // per group, same indexing ([feature_size] each)
+    int env_stride;  // agent rows between consecutive envs: 2*cap for the [E][2][cap] block, cap for per-group blocks
     int group_mask;  // which groups to produce
     int tile_agents; // agents per CTA tile
     int tiles_per_group;

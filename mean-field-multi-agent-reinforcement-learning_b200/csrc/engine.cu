@@ -350,10 +350,23 @@ void Engine::download_num(cudaStream_t st) {
 // launches
 // ---------------------------------------------------------------------------------------------
 void Engine::observe(float *d_view, float *d_feature, int group_mask, cudaStream_t st) {
+    // one [E][2][cap] block: group g's rows of env e start at (e*2 + g) * cap
+    float *v[kGroups] = {d_view, d_view + (size_t)P_.cap * kViewRow};
+    float *f[kGroups] = {d_feature, d_feature + (size_t)P_.cap * P_.feature_size};
+    observe_groups(v, f, 2 * P_.cap, group_mask, st);
+}
+
+void Engine::observe_groups(float *const d_view[kGroups], float *const d_feature[kGroups], int env_stride,
+                            int group_mask, cudaStream_t st) {
     commit(st);
     if (group_mask < 1 || group_mask > 3) throw Fatal("observe: bad group mask");
     ObsIO io;
-    io.view = d_view; io.feature = d_feature; io.group_mask = group_mask;
+    for (int g = 0; g < kGroups; g++) {
+        io.view[g] = d_view[g]; io.feature[g] = d_feature[g];
+        if (((group_mask >> g) & 1) && (!d_view[g] || !d_feature[g])) throw Fatal("observe: null output buffer");
+        if (((group_mask >> g) & 1) && ((uintptr_t)d_view[g] & 15)) throw Fatal("observe: view buffer must be 16-byte aligned");
+    }
+    io.env_stride = env_stride; io.group_mask = group_mask;
     // tile: amortise the per-CTA grid rebuild over more agents when groups are large (measured: 256 at cap 512)
     const int want_tile = cfg_.obs_tile_agents > 0 ? cfg_.obs_tile_agents : std::min(256, std::max(64, P_.cap));
     io.tile_agents = std::min(kObsMaxTile, std::max(kObsChunk, round_up(want_tile, kObsChunk)));

@@ -64,6 +64,9 @@ public:
 
     // ---- kernels ----
     void observe(float *d_view, float *d_feature, int group_mask, cudaStream_t st);
+    // per-group output blocks [E][cap][...] (env_stride = cap) or any layout with `env_stride` rows between envs
+    void observe_groups(float *const d_view[kGroups], float *const d_feature[kGroups], int env_stride, int group_mask,
+                        cudaStream_t st);
     void step(const StepIO &io, cudaStream_t st);
     static void mean_action(const int32_t *d_actions, const int32_t *d_num, float *d_out, int rows,
                             int cap, int n_action, cudaStream_t st);

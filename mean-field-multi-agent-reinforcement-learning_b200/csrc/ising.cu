@@ -69,12 +69,22 @@ __device__ __forceinline__ double action_threshold(double q0, double q1, double 
     const double p0 = e0 / denom, p1 = e1 / denom;
     return p0 / (p0 + p1);
 }
-__device__ __forceinline__ float action_threshold(float q0, float q1, float T) {
-    // same quantity, written so that exp cannot overflow in fp32 at small T: e0/(e0+e1) = 1/(1+exp((q1-q0)/T)).
-    // ex2.approx + rcp.approx: |error| of the threshold < 4e-6 for |q| <= 2, T >= 0.25 (2 + 1.16|x| ulp of exp),
-    // i.e. an action can differ from the fp64 reference only for draws that close to the threshold -- the same
-    // order as the fp32 rounding of u itself (2^-24).  The fp64 kernel mode evaluates the reference's formula.
-    return __frcp_rn(1.0f + __expf(__fdividef(q1 - q0, T)));
+// fp32 production mode.  a = [u >= p0] with p0 = e0/(e0+e1) = 1/(1 + e), e = exp((q1-q0)/T), is evaluated as
+// u*(1 + e) >= 1, which needs neither the reciprocal nor the division: c = log2(e)/T is computed once per sweep,
+// e = ex2.approx((q1-q0)*c) (clamped so that e stays finite at tiny T), and u*e + u is one fma.  |error| of the
+// implied threshold < 4e-6 for |q| <= 2, T >= 0.25, i.e. an action can differ from the fp64 reference only for
+// draws that close to the threshold -- the same order as the fp32 rounding of u itself (2^-24).  Both fp32
+// kernels (streaming and resident) share this function, so they agree bit for bit.
+__device__ __forceinline__ float temperature_param(float T) { return __fdiv_rn(1.4426950408889634f, T); }
+__device__ __forceinline__ double temperature_param(double T) { return T; }
+__device__ __forceinline__ int draw_action(float u, float q0, float q1, float c) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf((q1 - q0) * c, 126.0f)));
+    return __fmaf_rn(u, e, u) >= 1.0f ? 1 : 0;
+}
+// fp64 mode replays the reference's operation sequence
+__device__ __forceinline__ int draw_action(double u, double q0, double q1, double T) {
+    return u >= action_threshold(q0, q1, T) ? 1 : 0;
 }
 
 __device__ __forceinline__ int bit_at(const uint32_t *rows, int wpr, int r, int x) {
@@ -107,6 +117,7 @@ __global__ void __launch_bounds__(sizeof(T) == 8 ? 512 : 1024) k_ising(const Isi
     }
     __syncthreads();
 
+    const T tparam = temperature_param(A.temperature);
     T keep_q[kIsingRB]; int keep_sa[kIsingRB];     // this band: selected Q value, s | a << 3
     T prev_q = (T)0; int prev_sa = 0;              // last row of the previous band
     T row0_q = (T)0; int row0_sa = 0;              // row 0, finalised last (needs row L-1)
@@ -166,7 +177,7 @@ __global__ void __launch_bounds__(sizeof(T) == 8 ? 512 : 1024) k_ising(const Isi
 #pragma unroll
         for (int j = 0; j < kIsingRB; j++) {
             int a = 0;
-            if (j < nrows && active) a = uu[j] >= action_threshold(q0[j], q1[j], A.temperature) ? 1 : 0;
+            if (j < nrows && active) a = draw_action(uu[j], q0[j], q1[j], tparam);
             const uint32_t word = __ballot_sync(0xFFFFFFFFu, a != 0);
             if (j < nrows && lane == 0) s_new[(r0 + j) * wpr + w] = word;
             keep_q[j] = a ? q1[j] : q0[j];
@@ -236,12 +247,22 @@ static void launch_ising(const IsingArgs<T> &A, cudaStream_t st) {
 // algorithmic, 45-60 B real in the disordered phase because the plane index s is data dependent and
 // 32-byte sectors are only partly used).  Here a lattice is cut into C horizontal strips, one CTA each,
 // the C CTAs forming one thread-block cluster; a CTA keeps its strip of Q ([5][rows*L][2], up to 160 KB) and
-// both bit-packed spin buffers in shared memory for all K sweeps and reads the neighbour strips' boundary
-// rows through distributed shared memory.  One cluster barrier per sweep suffices: a sweep reads the "old"
-// buffer (own + halo) and writes only its own "new" buffer, the buffers swap every sweep, and a CTA can
-// only be one barrier ahead of its neighbours.  HBM traffic drops to (80 B load + 80 B store) / K per
-// site-step.  Draws use the same Philox keys as the streaming kernel -- (seed, lattice) x (column, global
-// row band, step) -- so K resident sweeps equal K streaming launches bit for bit.
+// two bit-packed spin buffers (ping-pong, each with one halo row above and below) in shared memory for all
+// K sweeps.  HBM traffic drops to (80 B load + 80 B store) / K per site-step; the kernel is bound by issue
+// slots, so the sweep is written to need few instructions and ONE cluster barrier:
+//   * the up-neighbour count of the lattice after sweep k-1 is both the reward input of sweep k-1 and the
+//     Q-row index s of sweep k, so one fused phase per barrier does: count -> finish sweep k-1 (reward,
+//     Q update in shared memory, statistics) -> draw sweep k (Q pair, Boltzmann draw) -> publish the new bits;
+//   * a CTA PUSHES its two boundary rows into the neighbours' halo rows (st.shared::cluster is fire and
+//     forget), so every read is local -- no 200-cycle DSMEM load sits on the critical path;
+//   * the barrier is split (barrier.cluster.arrive.release ... wait.acquire) and the Philox draws of the next
+//     sweep plus the statistics flush are computed between the two halves;
+//   * left/right neighbours come from the row's ballot word (kept in a register) and the two adjacent words
+//     with one funnel shift each; up/down inside a thread's 4-row band come from its own registers.
+// A sweep reads buffer `cur` and writes buffer `cur^1`; a CTA can be at most one barrier ahead of its
+// neighbours and by then they have finished reading, so the ping-pong needs no second barrier.
+// Draws use the same Philox keys as the streaming kernel -- (seed, lattice) x (column, global row band, step) --
+// so K resident sweeps equal K streaming launches bit for bit.
 // C = 1 covers lattices whose whole Q fits one CTA (L <= 64 in fp32; the reference's 20 x 20 case);
 // 256 x 256 uses C = 16 (16 rows per CTA, 1024 threads = 256 columns x 4 bands).
 // ----------------------------------------------------------------------------------------------
@@ -262,7 +283,25 @@ struct IsingRunArgs {
     T *reward_sum;                  // [K][B] out or null, zeroed by the caller
 };
 
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
 template <typename T>
+__device__ __forceinline__ void ising_uniforms(T (&uu)[kIsingRB], uint32_t x, uint32_t gband, uint32_t step, uint2 key) {
+    if (sizeof(T) == 4) {
+        const uint4 rnd = philox4x32_10(make_uint4(x, gband, step, 0u), key);
+        uu[0] = uniform_from_bits<T>(rnd.x, 0); uu[1] = uniform_from_bits<T>(rnd.y, 0);
+        uu[2] = uniform_from_bits<T>(rnd.z, 0); uu[3] = uniform_from_bits<T>(rnd.w, 0);
+    } else {
+        const uint4 r1 = philox4x32_10(make_uint4(x, gband, step, 0u), key);
+        const uint4 r2 = philox4x32_10(make_uint4(x, gband, step, 1u), key);
+        uu[0] = uniform_from_bits<T>(r1.x, r1.y); uu[1] = uniform_from_bits<T>(r1.z, r1.w);
+        uu[2] = uniform_from_bits<T>(r2.x, r2.y); uu[3] = uniform_from_bits<T>(r2.z, r2.w);
+    }
+}
+
+// FAST: L % 32 == 0 and rows % 4 == 0 -- every thread owns 4 live sites and a row's x-wrap is a word wrap.
+template <typename T, bool FAST>
 __global__ void __launch_bounds__(1024, 1) k_ising_resident(const IsingRunArgs<T> A) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     cg::cluster_group cluster = cg::this_cluster();
@@ -270,129 +309,389 @@ __global__ void __launch_bounds__(1024, 1) k_ising_resident(const IsingRunArgs<T
     const int L = A.L, N = L * L, wpr = (L + 31) >> 5, LP = wpr * 32, rows = A.rows_per;
     const int b = blockIdx.x / C, row0 = rank * rows;
     const int strip = rows * L;                          // sites in this CTA's strip
+    const int HR = rows + 2;                             // bit rows per buffer: halo, rows, halo
 
     T *s_q = (T *)s_raw;                                 // [5][strip][2]
-    uint32_t *s_bits = (uint32_t *)(s_raw + (size_t)5 * strip * 2 * sizeof(T));   // [2][rows][wpr]
-    __shared__ int s_red_i;
-    __shared__ T s_red_r;
+    uint32_t *s_bits = (uint32_t *)(s_raw + (size_t)5 * strip * 2 * sizeof(T));   // [2][HR][wpr]
+    int *s_stat = (int *)(s_bits + 2 * HR * wpr);        // [2][2]: (up count, reward sum) of sweep parity
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int x = tid % LP, band = tid / LP, w = x >> 5;  // column, band (4 rows) inside the strip
-    const bool active = x < L;
+    const bool active = FAST || x < L;
     const int xl = x == 0 ? L - 1 : x - 1, xr = x == L - 1 ? 0 : x + 1;
+    const int wl = w == 0 ? wpr - 1 : w - 1, wr = w == wpr - 1 ? 0 : w + 1;
     const size_t lbase = (size_t)b * N;
+    const int rb = band * kIsingRB;                       // first local row of this thread
+    const int up_rank = (rank + C - 1) % C, dn_rank = (rank + 1) % C;
+    uint32_t *up_bits = cluster.map_shared_rank(s_bits, up_rank);   // == s_bits when C == 1
+    uint32_t *dn_bits = cluster.map_shared_rank(s_bits, dn_rank);
 
-    // ---- load: Q strip (5 contiguous plane slices) and spins -> bits ----
+    // publish one 32-column word of local row r into buffer `which`: own copy + the neighbour's halo row
+    auto publish = [&](int which, int r, uint32_t word) {
+        const int o = which * HR * wpr + w;
+        s_bits[o + (r + 1) * wpr] = word;
+        if (r == 0) up_bits[o + (rows + 1) * wpr] = word;            // I am the row below up_rank's last row
+        if (r == rows - 1) dn_bits[o] = word;                         // ... and the row above dn_rank's first
+    };
+
+    if (tid < 4) s_stat[tid] = 0;
+    // ---- load: Q strip (5 contiguous plane slices) and spins -> bits (buffer 0) ----
     for (int sp = 0; sp < 5; sp++) {
         const T *src = A.Q + (lbase * 5 + (size_t)sp * N + (size_t)row0 * L) * 2;
         T *dst = s_q + (size_t)sp * strip * 2;
-        for (int i = tid; i < strip * 2; i += blockDim.x) dst[i] = src[i];
+        if (sizeof(T) == 4 && (strip & 1) == 0) {
+            const float4 *s4 = (const float4 *)src; float4 *d4 = (float4 *)dst;
+            for (int i = tid; i < strip / 2; i += blockDim.x) d4[i] = s4[i];
+        } else {
+            for (int i = tid; i < strip * 2; i += blockDim.x) dst[i] = src[i];
+        }
     }
+    int a_cur[kIsingRB];            // this thread's spins in the current lattice
+    uint32_t w_cur[kIsingRB];       // the 32-column words those spins live in (ballot result)
+    cluster.sync();                 // everybody's shared memory exists before the first remote store
 #pragma unroll
     for (int j = 0; j < kIsingRB; j++) {
-        const int r = band * kIsingRB + j;
-        int v = 0;
-        if (r < rows && active) v = A.spins[lbase + (size_t)(row0 + r) * L + x];
-        const uint32_t word = __ballot_sync(0xFFFFFFFFu, v != 0);
-        if (r < rows && lane == 0) s_bits[r * wpr + w] = word;
+        const int r = rb + j;
+        const bool live = FAST || (r < rows && active);
+        a_cur[j] = live ? (int)A.spins[lbase + (size_t)(row0 + r) * L + x] : 0;
+        w_cur[j] = __ballot_sync(0xFFFFFFFFu, a_cur[j] != 0);
+        if ((FAST || r < rows) && lane == 0) publish(0, r, w_cur[j]);
     }
-    cluster.sync();
+    cluster_arrive();
 
-    const int up_rank = (rank + C - 1) % C, dn_rank = (rank + 1) % C;
-    int cur = 0;                                          // which bit buffer holds the current lattice
-    for (int k = 0; k < A.K; k++, cur ^= 1) {
-        const uint32_t *old_own = s_bits + cur * rows * wpr;
-        uint32_t *new_own = s_bits + (cur ^ 1) * rows * wpr;
-        const uint32_t *old_up = cluster.map_shared_rank(s_bits, up_rank) + cur * rows * wpr + (rows - 1) * wpr;
-        const uint32_t *old_dn = cluster.map_shared_rank(s_bits, dn_rank) + cur * rows * wpr;
-        const T temperature = A.temperatures[k];
-        if (tid == 0) { s_red_i = 0; s_red_r = (T)0; }
+    const uint2 key = make_uint2(A.seed, A.lattice_base + (uint32_t)b);
+    const uint32_t gband = (uint32_t)((row0 >> 2) + band);            // global band index: same counter as k_ising
+    T uu[kIsingRB];
+    if (A.u == nullptr) ising_uniforms<T>(uu, (uint32_t)x, gband, A.step0, key);
 
-        // ---- phase 1: neighbour counts on the old lattice, Boltzmann draw, publish new bits ----
-        T keep_q[kIsingRB]; int keep_sa[kIsingRB];
-        T uu[kIsingRB];
-        const int gband = (row0 >> 2) + band;             // global band index: same Philox counter as k_ising
+    T keep_q[kIsingRB]; int keep_s[kIsingRB];     // pending sweep: chosen Q value and its row index s (a is a_cur)
+#pragma unroll
+    for (int j = 0; j < kIsingRB; j++) { keep_q[j] = (T)0; keep_s[j] = 0; }
+
+    int cur = 0;
+    for (int k = 0; k <= A.K; k++, cur ^= 1) {
+        cluster_wait();                                   // lattice after sweep k-1 is complete in buffer `cur`
+        const uint32_t *ob = s_bits + cur * HR * wpr;
+        if (tid == 0 && k >= 2) {                         // statistics of sweep k-2: all warps added before this barrier
+            int *st = s_stat + (k & 1) * 2;
+            atomicAdd(&A.n_up[(size_t)(k - 2) * A.B + b], st[0]);
+            if (A.reward_sum) atomicAdd(&A.reward_sum[(size_t)(k - 2) * A.B + b], (T)st[1]);
+            st[0] = 0; st[1] = 0;
+        }
+        // ---- up-neighbour counts of the current lattice ----
+        int ups[kIsingRB];
+        {
+            const int v_top = (int)((ob[rb * wpr + w] >> lane) & 1u);                  // local row rb-1 (or halo)
+            const int v_bot = (int)((ob[(rb + kIsingRB + 1) * wpr + w] >> lane) & 1u);  // local row rb+4 (or halo)
+#pragma unroll
+            for (int j = 0; j < kIsingRB; j++) {
+                const int r = rb + j;
+                int up, dn, lf, rt;
+                if (FAST) {
+                    up = j == 0 ? v_top : a_cur[j - 1];
+                    dn = j == kIsingRB - 1 ? v_bot : a_cur[j + 1];
+                    const uint32_t Wl = ob[(r + 1) * wpr + wl], Wr = ob[(r + 1) * wpr + wr];
+                    lf = (int)((__funnelshift_l(Wl, w_cur[j], 1) >> lane) & 1u);
+                    rt = (int)((__funnelshift_r(w_cur[j], Wr, 1) >> lane) & 1u);
+                } else {
+                    const bool live = r < rows && active;
+                    up = live ? bit_at(ob, wpr, r, x) : 0;            // halo-indexed: local row r-1 is row r
+                    dn = live ? bit_at(ob, wpr, r + 2, x) : 0;
+                    lf = live ? bit_at(ob, wpr, r + 1, xl) : 0;
+                    rt = live ? bit_at(ob, wpr, r + 1, xr) : 0;
+                }
+                ups[j] = up + dn + lf + rt;
+            }
+        }
+        // ---- finish sweep k-1: reward on the new lattice, Q update in shared memory ----
+        if (k > 0) {
+            int nup = 0, rsum = 0;
+#pragma unroll
+            for (int j = 0; j < kIsingRB; j++) {
+                const int r = rb + j;
+                if (FAST || (r < rows && active)) {
+                    const int a = a_cur[j];
+                    const int ri = (2 * a - 1) * (ups[j] - 2);                       // Ising.py:101-111, in {-2..2}
+                    const T reward = (T)0.5 * (T)(2 * a - 1) * (T)(2 * ups[j] - 4);
+                    s_q[((size_t)keep_s[j] * strip + r * L + x) * 2 + a] = keep_q[j] + A.lr * (reward - keep_q[j]);
+                    nup += a; rsum += ri;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                nup += __shfl_xor_sync(0xFFFFFFFFu, nup, o);
+                rsum += __shfl_xor_sync(0xFFFFFFFFu, rsum, o);
+            }
+            if (lane == 0) { int *st = s_stat + ((k - 1) & 1) * 2; atomicAdd(&st[0], nup); atomicAdd(&st[1], rsum); }
+        }
+        if (k == A.K) break;
+        // ---- draw sweep k: s = the count just computed, Boltzmann action, publish into buffer cur^1 ----
+        const T tparam = temperature_param(A.temperatures[k]);
         if (A.u != nullptr) {
 #pragma unroll
             for (int j = 0; j < kIsingRB; j++) {
-                const int r = band * kIsingRB + j;
-                uu[j] = (r < rows && active) ? A.u[((size_t)k * A.B + b) * N + (size_t)(row0 + r) * L + x] : (T)0;
+                const int r = rb + j;
+                uu[j] = (FAST || (r < rows && active)) ? A.u[((size_t)k * A.B + b) * N + (size_t)(row0 + r) * L + x] : (T)0;
             }
-        } else if (sizeof(T) == 4) {
-            const uint4 rnd = philox4x32_10(make_uint4((uint32_t)x, (uint32_t)gband, A.step0 + (uint32_t)k, 0u),
-                                            make_uint2(A.seed, A.lattice_base + (uint32_t)b));
-            uu[0] = uniform_from_bits<T>(rnd.x, 0); uu[1] = uniform_from_bits<T>(rnd.y, 0);
-            uu[2] = uniform_from_bits<T>(rnd.z, 0); uu[3] = uniform_from_bits<T>(rnd.w, 0);
-        } else {
-            const uint2 key = make_uint2(A.seed, A.lattice_base + (uint32_t)b);
-            const uint4 r1 = philox4x32_10(make_uint4((uint32_t)x, (uint32_t)gband, A.step0 + (uint32_t)k, 0u), key);
-            const uint4 r2 = philox4x32_10(make_uint4((uint32_t)x, (uint32_t)gband, A.step0 + (uint32_t)k, 1u), key);
-            uu[0] = uniform_from_bits<T>(r1.x, r1.y); uu[1] = uniform_from_bits<T>(r1.z, r1.w);
-            uu[2] = uniform_from_bits<T>(r2.x, r2.y); uu[3] = uniform_from_bits<T>(r2.z, r2.w);
         }
 #pragma unroll
         for (int j = 0; j < kIsingRB; j++) {
-            const int r = band * kIsingRB + j;
-            int a = 0, sv = 0; T q0 = (T)0, q1 = (T)0;
-            if (r < rows && active) {
-                const int up = r == 0 ? (int)((old_up[x >> 5] >> (x & 31)) & 1u) : bit_at(old_own, wpr, r - 1, x);
-                const int dn = r == rows - 1 ? (int)((old_dn[x >> 5] >> (x & 31)) & 1u) : bit_at(old_own, wpr, r + 1, x);
-                sv = up + dn + bit_at(old_own, wpr, r, xl) + bit_at(old_own, wpr, r, xr);
-                const typename Pair<T>::type pr = *(const typename Pair<T>::type *)(s_q + ((size_t)sv * strip + r * L + x) * 2);
+            const int r = rb + j;
+            int a = 0; T q0 = (T)0, q1 = (T)0;
+            if (FAST || (r < rows && active)) {
+                const typename Pair<T>::type pr =
+                    *(const typename Pair<T>::type *)(s_q + ((size_t)ups[j] * strip + r * L + x) * 2);
                 q0 = pr.x; q1 = pr.y;
-                a = uu[j] >= action_threshold(q0, q1, temperature) ? 1 : 0;
+                a = draw_action(uu[j], q0, q1, tparam);
             }
             const uint32_t word = __ballot_sync(0xFFFFFFFFu, a != 0);
-            if (r < rows && lane == 0) new_own[r * wpr + w] = word;
-            keep_q[j] = a ? q1 : q0;
-            keep_sa[j] = sv | (a << 3);
+            if ((FAST || r < rows) && lane == 0) publish(cur ^ 1, r, word);
+            keep_q[j] = a ? q1 : q0; keep_s[j] = ups[j];
+            a_cur[j] = a; w_cur[j] = word;
         }
-        cluster.sync();   // every strip's new bits are published (and the reduction cells are reset)
-
-        // ---- phase 2: reward on the new lattice, Q update in shared memory ----
-        const uint32_t *new_up = cluster.map_shared_rank(s_bits, up_rank) + (cur ^ 1) * rows * wpr + (rows - 1) * wpr;
-        const uint32_t *new_dn = cluster.map_shared_rank(s_bits, dn_rank) + (cur ^ 1) * rows * wpr;
-        int nup = 0; T rsum = (T)0;
-#pragma unroll
-        for (int j = 0; j < kIsingRB; j++) {
-            const int r = band * kIsingRB + j;
-            if (r < rows && active) {
-                const int s = keep_sa[j] & 7, a = keep_sa[j] >> 3;
-                const int up = r == 0 ? (int)((new_up[x >> 5] >> (x & 31)) & 1u) : bit_at(new_own, wpr, r - 1, x);
-                const int dn = r == rows - 1 ? (int)((new_dn[x >> 5] >> (x & 31)) & 1u) : bit_at(new_own, wpr, r + 1, x);
-                const int ups = up + dn + bit_at(new_own, wpr, r, xl) + bit_at(new_own, wpr, r, xr);
-                const T reward = (T)0.5 * (T)(2 * a - 1) * (T)(2 * ups - 4);
-                s_q[((size_t)s * strip + r * L + x) * 2 + a] = keep_q[j] + A.lr * (reward - keep_q[j]);
-                nup += a; rsum += reward;
-            }
+        cluster_arrive();
+        // ---- under the barrier: the next sweep's Philox draws ----
+        if (A.u == nullptr && k + 1 < A.K) ising_uniforms<T>(uu, (uint32_t)x, gband, A.step0 + (uint32_t)(k + 1), key);
+    }
+    __syncthreads();
+    if (tid == 0) {                                       // sweeps K-1 (and K-2 when it was not flushed in the loop)
+        for (int kk = max(0, A.K - 1); kk < A.K; kk++) {
+            int *st = s_stat + (kk & 1) * 2;
+            atomicAdd(&A.n_up[(size_t)kk * A.B + b], st[0]);
+            if (A.reward_sum) atomicAdd(&A.reward_sum[(size_t)kk * A.B + b], (T)st[1]);
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            nup += __shfl_xor_sync(0xFFFFFFFFu, nup, o);
-            rsum += __shfl_xor_sync(0xFFFFFFFFu, rsum, o);
-        }
-        if (lane == 0) { atomicAdd(&s_red_i, nup); if (A.reward_sum) atomicAdd(&s_red_r, rsum); }
-        __syncthreads();
-        if (tid == 0) {
-            atomicAdd(&A.n_up[(size_t)k * A.B + b], s_red_i);
-            if (A.reward_sum) atomicAdd(&A.reward_sum[(size_t)k * A.B + b], s_red_r);
-        }
-        __syncthreads();   // s_red_* are rewritten at the top of the next sweep
     }
 
     // ---- store: Q strip and the final spins ----
     for (int sp = 0; sp < 5; sp++) {
         T *dst = A.Q + (lbase * 5 + (size_t)sp * N + (size_t)row0 * L) * 2;
         const T *src = s_q + (size_t)sp * strip * 2;
-        for (int i = tid; i < strip * 2; i += blockDim.x) dst[i] = src[i];
+        if (sizeof(T) == 4 && (strip & 1) == 0) {
+            float4 *d4 = (float4 *)dst; const float4 *s4 = (const float4 *)src;
+            for (int i = tid; i < strip / 2; i += blockDim.x) d4[i] = s4[i];
+        } else {
+            for (int i = tid; i < strip * 2; i += blockDim.x) dst[i] = src[i];
+        }
     }
-    const uint32_t *fin = s_bits + cur * rows * wpr;
 #pragma unroll
     for (int j = 0; j < kIsingRB; j++) {
-        const int r = band * kIsingRB + j;
-        if (r < rows && active) A.spins[lbase + (size_t)(row0 + r) * L + x] = (int8_t)bit_at(fin, wpr, r, x);
+        const int r = rb + j;
+        if (FAST || (r < rows && active)) A.spins[lbase + (size_t)(row0 + r) * L + x] = (int8_t)a_cur[j];
     }
-    cluster.sync();       // nobody leaves while a neighbour may still read its shared memory
+    cluster.sync();       // nobody leaves while a neighbour's last remote store may still be in flight
+}
+
+// ---- K6r specialised for fp32 and compile-time shapes (the bench shape 256 x 256 / 16 rows per CTA and the other
+// power-of-two sides): same algorithm, same bits as the generic kernel above, written for instruction count -- the
+// kernel is issue-bound (ncu: ALU pipe busiest, no DRAM traffic).  Shapes fold to constants, shared memory is
+// addressed with 32-bit shared-window addresses (ld.shared / st.shared / mapa + st.shared::cluster), the Q slot
+// to update is remembered as an address, the reward is (float)((2a-1)(ups-2)) (exact), and the two per-sweep
+// statistics travel through ONE packed shuffle tree and one shared atomic.  RPT = rows per thread (4 or 8).
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ float2 lds_f32x2(uint32_t a) {
+    float2 v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory"); return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t a, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank)); return r;
+}
+__device__ __forceinline__ void sts_cluster_u32(uint32_t a, uint32_t v) {
+    asm volatile("st.shared::cluster.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+// remote 4-byte store that also counts 4 bytes on the TARGET CTA's mbarrier: data and signal in one message, no fence
+__device__ __forceinline__ void st_async_u32(uint32_t remote_addr, uint32_t v, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];"
+                 :: "r"(remote_addr), "r"(v), "r"(remote_bar) : "memory");
+}
+
+template <int L, int ROWS, int RPT>
+__global__ void __launch_bounds__(L * (ROWS / RPT), 1) k_ising_resident_f32(const IsingRunArgs<float> A) {
+    static_assert(L % 32 == 0 && ROWS % RPT == 0 && RPT % kIsingRB == 0, "shape");
+    constexpr int N = L * L, WPR = L / 32, HR = ROWS + 2, STRIP = ROWS * L, NT = L * (ROWS / RPT);
+    constexpr int NPH = RPT / kIsingRB;                         // Philox calls per thread per sweep
+    constexpr uint32_t PLANE = (uint32_t)STRIP * 8u;            // bytes between the Q planes of consecutive s
+    constexpr uint32_t BUF = (uint32_t)HR * WPR * 4u;           // bytes per bit buffer
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int b = blockIdx.x / C, row0 = rank * ROWS;
+    float *s_q = (float *)s_raw;                                                    // [5][STRIP][2]
+    uint32_t *s_bits = (uint32_t *)(s_raw + (size_t)5 * STRIP * 8);                 // [2][HR][WPR]
+    unsigned long long *s_bar = (unsigned long long *)(s_bits + 2 * HR * WPR);      // [2] halo-arrival mbarrier per buffer
+    int *s_stat = (int *)(s_bar + 2);                                               // [2] packed statistics per sweep parity
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int x = tid % L, band = tid / L, w = x >> 5;
+    const int rb = band * RPT;
+    const int wl = w == 0 ? WPR - 1 : w - 1, wr = w == WPR - 1 ? 0 : w + 1;
+    const size_t lbase = (size_t)b * N;
+    const uint32_t up_rank = (uint32_t)((rank + C - 1) % C), dn_rank = (uint32_t)((rank + 1) % C);
+    const uint32_t bits0 = smem_addr(s_bits);
+    const uint32_t q_site0 = smem_addr(s_q) + (uint32_t)(rb * L + x) * 8u;          // Q pair of (s = 0, row rb, column x)
+    const uint32_t own_w = bits0 + (uint32_t)((rb + 1) * WPR + w) * 4u;             // this thread's word of local row rb, buffer 0
+    const uint32_t own_l = bits0 + (uint32_t)((rb + 1) * WPR + wl) * 4u, own_r = bits0 + (uint32_t)((rb + 1) * WPR + wr) * 4u;
+    // remote halo slots (buffer 0): up neighbour's bottom halo row, down neighbour's top halo row
+    const uint32_t halo_up = map_to_rank(bits0 + (uint32_t)((ROWS + 1) * WPR + w) * 4u, up_rank);
+    const uint32_t halo_dn = map_to_rank(bits0 + (uint32_t)w * 4u, dn_rank);
+    const uint32_t bar0 = smem_addr(s_bar);                                          // + 8 * buffer
+    const uint32_t bar_up = map_to_rank(bar0, up_rank), bar_dn = map_to_rank(bar0, dn_rank);
+    const bool first_band = rb == 0, last_band = rb + RPT == ROWS;
+    constexpr uint32_t HALO_BYTES = 2u * WPR * 4u;                                   // one row from above, one from below
+
+    if (tid < 2) s_stat[tid] = 0;
+    if (tid == 0) {
+        mbar_init(bar0, 1); mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bar0, HALO_BYTES);                                            // the initial lattice arrives in buffer 0
+    }
+    for (int sp = 0; sp < 5; sp++) {
+        const float4 *s4 = (const float4 *)(A.Q + (lbase * 5 + (size_t)sp * N + (size_t)row0 * L) * 2);
+        float4 *d4 = (float4 *)(s_q + (size_t)sp * STRIP * 2);
+#pragma unroll 4
+        for (int i = tid; i < STRIP / 2; i += NT) d4[i] = s4[i];
+    }
+    int a_cur[RPT]; uint32_t w_cur[RPT];
+    cluster.sync();                 // everybody's shared memory exists before the first remote store
+#pragma unroll
+    for (int j = 0; j < RPT; j++) {
+        a_cur[j] = (int)A.spins[lbase + (size_t)(row0 + rb + j) * L + x];
+        w_cur[j] = __ballot_sync(0xFFFFFFFFu, a_cur[j] != 0);
+        if (lane == 0) {
+            sts_u32(own_w + (uint32_t)j * WPR * 4u, w_cur[j]);
+            if (first_band && j == 0) st_async_u32(halo_up, w_cur[j], bar_up);
+            if (last_band && j == RPT - 1) st_async_u32(halo_dn, w_cur[j], bar_dn);
+        }
+    }
+
+    const uint2 key = make_uint2(A.seed, A.lattice_base + (uint32_t)b);
+    const uint32_t gband = (uint32_t)((row0 + rb) >> 2);
+    float uu[RPT];
+    auto draw_uniforms = [&](uint32_t step) {
+#pragma unroll
+        for (int h = 0; h < NPH; h++) {
+            const uint4 rnd = philox4x32_10(make_uint4((uint32_t)x, gband + (uint32_t)h, step, 0u), key);
+            uu[4 * h + 0] = uniform_from_bits<float>(rnd.x, 0); uu[4 * h + 1] = uniform_from_bits<float>(rnd.y, 0);
+            uu[4 * h + 2] = uniform_from_bits<float>(rnd.z, 0); uu[4 * h + 3] = uniform_from_bits<float>(rnd.w, 0);
+        }
+    };
+    if (A.u == nullptr) draw_uniforms(A.step0);
+    float tparam = temperature_param(A.temperatures[0]);
+
+    float keep_q[RPT]; uint32_t keep_addr[RPT];       // pending sweep: chosen Q value and the shared address it came from
+#pragma unroll
+    for (int j = 0; j < RPT; j++) { keep_q[j] = 0.0f; keep_addr[j] = q_site0; }
+
+    // Synchronisation per sweep: ONE __syncthreads (the CTA's own words) plus, for the two boundary bands only, a wait
+    // on the mbarrier that counts the halo bytes the neighbours pushed with st.async -- point to point, no cluster-wide
+    // barrier and no fence.  A neighbour cannot overwrite a halo row still being read: it only reaches the draw
+    // that writes buffer X again after receiving this CTA's next words, which are sent after these reads.
+    uint32_t cur = 0;                                 // byte offset of the buffer holding the current lattice (0 or BUF)
+    for (int k = 0; k <= A.K; k++, cur ^= BUF) {
+        __syncthreads();                              // own words of the lattice after sweep k-1 are in buffer `cur`
+        const uint32_t cur_bar = bar0 + (cur ? 8u : 0u);
+        if (tid == 0) mbar_expect_tx(bar0 + (cur ? 0u : 8u), HALO_BYTES);   // the other buffer fills during this iteration
+        if (first_band || last_band) mbar_wait(cur_bar, (uint32_t)(k >> 1) & 1u);
+        if (tid == 0 && k >= 2) {                     // statistics of sweep k-2: all warps added before this barrier
+            const int pk = s_stat[k & 1];
+            s_stat[k & 1] = 0;
+            atomicAdd(&A.n_up[(size_t)(k - 2) * A.B + b], pk & 0xFFFF);
+            if (A.reward_sum) atomicAdd(&A.reward_sum[(size_t)(k - 2) * A.B + b], (float)((pk >> 16) - 2 * RPT * NT));
+        }
+        // ---- up-neighbour counts of the current lattice ----
+        int ups[RPT];
+        {
+            const int v_top = (int)((lds_u32(own_w + cur - WPR * 4u) >> lane) & 1u);
+            const int v_bot = (int)((lds_u32(own_w + cur + (uint32_t)RPT * WPR * 4u) >> lane) & 1u);
+#pragma unroll
+            for (int j = 0; j < RPT; j++) {
+                const int up = j == 0 ? v_top : a_cur[j - 1];
+                const int dn = j == RPT - 1 ? v_bot : a_cur[j + 1];
+                const uint32_t Wl = lds_u32(own_l + cur + (uint32_t)j * WPR * 4u), Wr = lds_u32(own_r + cur + (uint32_t)j * WPR * 4u);
+                const uint32_t lf = __funnelshift_l(Wl, w_cur[j], 1), rt = __funnelshift_r(w_cur[j], Wr, 1);
+                ups[j] = up + dn + (int)((lf >> lane) & 1u) + (int)((rt >> lane) & 1u);
+            }
+        }
+        // ---- finish sweep k-1: reward on the new lattice, Q update in shared memory, statistics ----
+        if (k > 0) {
+            int packed = 0;
+#pragma unroll
+            for (int j = 0; j < RPT; j++) {
+                const int d = ups[j] - 2;
+                const int ri = a_cur[j] ? d : -d;                                  // (2a-1)(ups-2) = Ising.py:101-111
+                const float reward = (float)ri;                                    // == 0.5f * (2a-1) * (2 ups - 4), exactly
+                sts_f32(keep_addr[j], keep_q[j] + A.lr * (reward - keep_q[j]));
+                packed += a_cur[j] + ((ri + 2) << 16);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) packed += __shfl_xor_sync(0xFFFFFFFFu, packed, o);
+            if (lane == 0) atomicAdd(&s_stat[(k - 1) & 1], packed);
+        }
+        if (k == A.K) break;
+        // ---- draw sweep k: s = the count just computed, Boltzmann action, publish into the other buffer ----
+        if (A.u != nullptr) {
+#pragma unroll
+            for (int j = 0; j < RPT; j++) uu[j] = A.u[((size_t)k * A.B + b) * N + (size_t)(row0 + rb + j) * L + x];
+        }
+        const uint32_t nxt = cur ^ BUF;
+#pragma unroll
+        for (int j = 0; j < RPT; j++) {
+            const uint32_t addr = q_site0 + (uint32_t)ups[j] * PLANE + (uint32_t)j * (L * 8u);
+            const float2 pr = lds_f32x2(addr);
+            const int a = draw_action(uu[j], pr.x, pr.y, tparam);
+            const uint32_t word = __ballot_sync(0xFFFFFFFFu, a != 0);
+            if (lane == 0) {
+                sts_u32(own_w + nxt + (uint32_t)j * WPR * 4u, word);
+                if (first_band && j == 0) st_async_u32(halo_up + nxt, word, bar_up + (nxt ? 8u : 0u));
+                if (last_band && j == RPT - 1) st_async_u32(halo_dn + nxt, word, bar_dn + (nxt ? 8u : 0u));
+            }
+            keep_q[j] = a ? pr.y : pr.x; keep_addr[j] = addr + (uint32_t)a * 4u;
+            a_cur[j] = a; w_cur[j] = word;
+        }
+        // ---- the next sweep's Philox draws and temperature (independent of the lattice) ----
+        if (k + 1 < A.K) {
+            if (A.u == nullptr) draw_uniforms(A.step0 + (uint32_t)(k + 1));
+            tparam = temperature_param(A.temperatures[k + 1]);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int kk = A.K - 1, pk = s_stat[kk & 1];
+        atomicAdd(&A.n_up[(size_t)kk * A.B + b], pk & 0xFFFF);
+        if (A.reward_sum) atomicAdd(&A.reward_sum[(size_t)kk * A.B + b], (float)((pk >> 16) - 2 * RPT * NT));
+    }
+    for (int sp = 0; sp < 5; sp++) {
+        float4 *d4 = (float4 *)(A.Q + (lbase * 5 + (size_t)sp * N + (size_t)row0 * L) * 2);
+        const float4 *s4 = (const float4 *)(s_q + (size_t)sp * STRIP * 2);
+#pragma unroll 4
+        for (int i = tid; i < STRIP / 2; i += NT) d4[i] = s4[i];
+    }
+#pragma unroll
+    for (int j = 0; j < RPT; j++) A.spins[lbase + (size_t)(row0 + rb + j) * L + x] = (int8_t)a_cur[j];
+    cluster.sync();       // nobody leaves while a neighbour's last remote store may still be in flight
+}
+
+template <typename T>
+static size_t resident_smem_bytes(int L, int rows) {
+    const int wpr = (L + 31) >> 5;
+    return (size_t)5 * rows * L * 2 * sizeof(T) + (size_t)2 * (rows + 2) * wpr * 4 + 48;   // bit buffers, 2 mbarriers, statistics
 }
 
 // cluster size for a lattice side, 0 = the resident kernel does not apply
@@ -404,10 +703,25 @@ static int resident_cluster_size(int L) {
         const int rows = L / C;
         if (C > 1 && rows % kIsingRB) continue;
         const int bands = (rows + kIsingRB - 1) / kIsingRB;
-        const size_t smem = (size_t)5 * rows * L * 2 * sizeof(T) + (size_t)2 * rows * wpr * 4;
-        if (LP * bands <= 1024 && smem <= 200 * 1024) return C;
+        if (LP * bands <= 1024 && resident_smem_bytes<T>(L, rows) <= 200 * 1024) return C;
     }
     return 0;
+}
+
+// fp32 shapes with a compile-time specialisation (rows per thread from MFMARL_ISING_RPT, default 8: measured 11 % faster than 4)
+static void specialised_resident_kernel(const IsingRunArgs<double> &, void (*&)(const IsingRunArgs<double>), unsigned &) {}
+static void specialised_resident_kernel(const IsingRunArgs<float> &A, void (*&kern)(const IsingRunArgs<float>), unsigned &threads) {
+    const char *env = getenv("MFMARL_ISING_RPT");
+    const int rpt = env ? atoi(env) : 8;
+    if (env && atoi(env) == 0) return;                 // 0 = force the generic kernel (tests)
+#define MF_PICK(LL, RR) \
+    if (A.L == LL && A.rows_per == RR) { \
+        if (rpt == 8) { kern = k_ising_resident_f32<LL, RR, 8>; threads = LL * (RR / 8); } \
+        else { kern = k_ising_resident_f32<LL, RR, 4>; threads = LL * (RR / 4); } \
+        return; \
+    }
+    MF_PICK(256, 16) MF_PICK(128, 32) MF_PICK(64, 64)
+#undef MF_PICK
 }
 
 template <typename T>
@@ -418,17 +732,21 @@ static void launch_ising_resident(const IsingRunArgs<T> &A0, cudaStream_t st) {
     if (C == 0) throw Fatal("ising resident kernel: lattice side " + std::to_string(L) + " not supported (use mfi_step)");
     A.rows_per = L / C;
     const int bands = (A.rows_per + kIsingRB - 1) / kIsingRB;
-    const size_t smem = (size_t)5 * A.rows_per * L * 2 * sizeof(T) + (size_t)2 * A.rows_per * wpr * 4;
-    MF_CUDA(cudaFuncSetAttribute(k_ising_resident<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (C > 8) MF_CUDA(cudaFuncSetAttribute(k_ising_resident<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    const size_t smem = resident_smem_bytes<T>(L, A.rows_per);
+    const bool fast = (L % 32 == 0) && (A.rows_per % kIsingRB == 0);
+    void (*kern)(const IsingRunArgs<T>) = fast ? k_ising_resident<T, true> : k_ising_resident<T, false>;
+    unsigned threads = (unsigned)(LP * bands);
+    specialised_resident_kernel(A, kern, threads);
+    MF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (C > 8) MF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(A.B * C)); cfg.blockDim = dim3((unsigned)(LP * bands));
+    cfg.gridDim = dim3((unsigned)(A.B * C)); cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    MF_CUDA(cudaLaunchKernelEx(&cfg, k_ising_resident<T>, A));
+    MF_CUDA(cudaLaunchKernelEx(&cfg, kern, A));
 }
 
 }  // namespace mfmarl

@@ -15,6 +15,7 @@ import torch.nn.functional as F
 
 from . import tools
 from .base import _dense, as_tensor, checkpoint_path
+from .replay_device import DeviceEpisodesBuffer, segmented_discounted_returns
 
 
 class ACNet(nn.Module):
@@ -68,7 +69,7 @@ class _ActorCriticBase:
     stem = "ac"
 
     def __init__(self, name, handle, env, value_coef=0.1, ent_coef=0.08, gamma=0.95, batch_size=64, learning_rate=1e-4,
-                 device=None, seed=None):
+                 device=None, seed=None, stage_rows=1 << 18, sub_len=400):
         self.env, self.name = env, name
         self.view_space = tuple(env.get_view_space(handle))
         self.feature_space = tuple(env.get_feature_space(handle))
@@ -80,6 +81,8 @@ class _ActorCriticBase:
         self.net = ACNet(self.view_space, self.feature_space, self.num_actions, self.use_mf).to(self.device)
         self.optimizer = torch.optim.Adam(self.net.parameters(), lr=learning_rate)
         self.replay_buffer = tools.EpisodesBuffer(use_mean=self.use_mf)
+        self.device_replay = None
+        self._stage_cfg = (stage_rows, sub_len)
         self.generator = torch.Generator(device=self.device)
         if seed is not None:
             self.generator.manual_seed(seed)
@@ -90,6 +93,28 @@ class _ActorCriticBase:
 
     def flush_buffer(self, **kwargs):
         self.replay_buffer.push(**kwargs)
+
+    def flush_buffer_batched(self, **kwargs):
+        """One lockstep step of the batched engine (device tensors [E, cap, ...]) -> device episode store."""
+        if self.device_replay is None:
+            self.device_replay = DeviceEpisodesBuffer(self.view_space, self.feature_space, self.num_actions,
+                                                      self._stage_cfg[0], self._stage_cfg[1], use_mean=self.use_mf,
+                                                      device=self.device)
+        self.device_replay.push(**kwargs)
+
+    def _train_batched(self, verbose):
+        ep = self.device_replay.episodes()
+        if ep is None:
+            return None
+        with torch.no_grad():        # bootstrap = V(last state) per trajectory (ac.py:139-143)
+            last = ep["seg_last"]
+            boot = self.net(ep["view"][last], ep["feature"][last], ep["prob"][last] if self.use_mf else None)[1]
+        ret = segmented_discounted_returns(ep["reward"], ep["seg_last"], ep["seg_id"], boot, self.gamma)
+        out = self.update(ep["view"], ep["feature"], ep["action"], ret, ep["prob"])
+        if verbose:
+            print('[*] PG_LOSS:', np.round(out[0], 6), '/ VF_LOSS:', np.round(out[1], 6), '/ ENT_LOSS:',
+                  np.round(out[2], 6), '/ VALUE:', out[3])
+        return out
 
     @torch.no_grad()
     def act(self, **kwargs):
@@ -127,6 +152,8 @@ class _ActorCriticBase:
         return float(pg_loss), float(vf_loss), float(neg_entropy), float(value.mean())
 
     def train(self, verbose=True):
+        if self.device_replay is not None and self.device_replay.has_staged:
+            return self._train_batched(verbose)
         episodes = list(self.replay_buffer.episodes())
         self.replay_buffer = tools.EpisodesBuffer(use_mean=self.use_mf)
         n = sum(len(ep.rewards) for ep in episodes)

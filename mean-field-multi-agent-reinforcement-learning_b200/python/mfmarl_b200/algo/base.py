@@ -135,7 +135,8 @@ class ValueNet:
         self.optimizer.zero_grad(set_to_none=True)
         loss.backward()
         self.optimizer.step()
-        return float(loss), {"Eval-Q": round(float(e_q.mean()), 6), "Target-Q": round(float(target_q.mean()), 6)}
+        return float(loss.detach()), {"Eval-Q": round(float(e_q.detach().mean()), 6),
+                                      "Target-Q": round(float(target_q.mean()), 6)}
 
     # -- checkpoints (q_learning.py:53-71,146-171 use tf.train.Saver per scope)
     def _save(self, dir_path, stem, step):

@@ -115,6 +115,41 @@ class BatchedGridWorld:
             check(self.lib.mfb_observe(self._h, _ptr(view), _ptr(feat), group_mask, _stream()))
         return view, feat
 
+    def observe_groups(self, groups=(0, 1)):
+        """Per-group observation blocks, each contiguous: -> [(view_g float32[E, cap, 13, 13, 7], feature_g
+        float32[E, cap, 34]) for g in (0, 1)] (None for a group not asked for).  This is the layout a per-group
+        policy network consumes in place (`view_g.view(E * cap, 13, 13, 7)` is free)."""
+        s = self.sizes
+        E, cap, v = self.n_envs, s["capacity"], s["view_size"]
+        out, ptrs = [], []
+        for g in (0, 1):
+            if g in groups:
+                view = self._buf("view_g%d" % g, (E, cap, v, v, s["n_channel"]), torch.float32)
+                feat = self._buf("feat_g%d" % g, (E, cap, s["feature_size"]), torch.float32)
+                out.append((view, feat)); ptrs += [_ptr(view), _ptr(feat)]
+            else:
+                out.append(None); ptrs += [None, None]
+        with torch.cuda.device(self.device):
+            check(self.lib.mfb_observe_groups(self._h, *ptrs, _stream()))
+        return out
+
+    def device_state(self, key):
+        """Live engine state as a torch tensor ALIASING the engine's HBM arrays (read-only by convention; contents
+        change with every launch on the stream): "num" int32[E, 2], "id" int32[E, 2, cap], "pos" int32[E, 2, cap]
+        (x | y << 16), "hp" float32[E, 2, cap], "step_ct" int32[E]."""
+        E, cap = self.n_envs, self.capacity
+        spec = {"num": ((E, 2), "<i4", torch.int32), "id": ((E, 2, cap), "<i4", torch.int32),
+                "pos": ((E, 2, cap), "<i4", torch.int32), "hp": ((E, 2, cap), "<f4", torch.float32),
+                "step_ct": ((E,), "<i4", torch.int32)}[key]
+        self.get("num")                      # commits a pending placement and synchronises
+        ptr = ctypes.c_void_p()
+        check(self.lib.mfb_state_device_ptr(self._h, key.encode(), ctypes.byref(ptr)))
+
+        class _Alias:
+            __cuda_array_interface__ = {"shape": spec[0], "typestr": spec[1], "data": (ptr.value, False), "version": 2}
+        with torch.cuda.device(self.device):
+            return torch.as_tensor(_Alias(), device=self.device)
+
     def step(self, actions, attack_perm=None, clear_dead=True, want_mean_action=True):
         """actions int32[E, 2, cap] on the device -> (reward, alive, done, mean_action) device tensors."""
         s = self.sizes

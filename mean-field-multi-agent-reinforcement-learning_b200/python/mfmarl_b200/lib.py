@@ -44,6 +44,8 @@ def load_library(path=None):
         "mfb_set_seed": [vp, ctypes.c_ulong],
         "mfb_query": [vp, cp, ctypes.POINTER(ci)],
         "mfb_observe": [vp, vp, vp, ci, vp],
+        "mfb_observe_groups": [vp, vp, vp, vp, vp, vp],
+        "mfb_state_device_ptr": [vp, cp, ctypes.POINTER(vp)],
         "mfb_step": [vp, vp, vp, vp, vp, vp, vp, ci, vp],
         "mfb_clear_dead": [vp, vp],
         "mfb_mean_action": [vp, vp, vp, ci, ci, ci, vp],

@@ -50,3 +50,29 @@ def fight_actions(rng, pos, map_size):
 
 def uniform_actions(rng, n):
     return rng.randint(0, 21, size=n).astype(np.int32)
+
+
+class StandInPolicy:
+    """Duck type of the reference models (algo/base.py:228-254): act(state=[view, feature], prob=, eps=).
+    Deterministic given its inputs: attack the first enemy seen in the 8 neighbouring view cells (channel 4),
+    otherwise advance towards the other army, the exact move picked by a fixed random linear map of
+    (features, mean action) -- so the mean action feeds back into the trajectory as in MF-Q."""
+
+    ADVANCE = {+1: [7, 8, 3, 11], -1: [5, 4, 1, 9]}     # (dx, dy) moves with dx > 0 / dx < 0 (SURVEY.md section 8)
+
+    def __init__(self, seed, use_mf, direction):
+        rng = np.random.RandomState(seed)
+        self.w_feat = rng.randn(34, 4).astype(np.float32)
+        self.w_prob = rng.randn(21, 4).astype(np.float32) * (1.0 if use_mf else 0.0)
+        self.moves = np.array(self.ADVANCE[direction], np.int32)
+
+    def act(self, state, prob, eps):
+        view, feat = state
+        assert len(prob) == len(view)
+        near = view[:, 5:8, 5:8, 4].reshape(len(view), 9)            # [dy][dx] around the observer
+        near = np.delete(near, 4, axis=1)                            # the 8 attack targets, row-major
+        q = feat @ self.w_feat + prob.astype(np.float32) @ self.w_prob
+        acts = self.moves[np.argmax(q, axis=1)]
+        has = near.max(axis=1) > 0
+        acts[has] = 13 + np.argmax(near[has] > 0, axis=1)
+        return acts.astype(np.int32)

@@ -138,16 +138,22 @@ def test_full_size_256x256_properties():
         assert torch.allclose(m.reward_sum, bonds, rtol=1e-5, atol=1e-2)
 
 
-@pytest.mark.parametrize("L,B,K", [(20, 5, 30), (64, 3, 12), (128, 2, 8), (256, 3, 6)])
-def test_resident_kernel_equals_streaming_bit_for_bit(L, B, K):
-    """K sweeps in one launch with Q resident in shared memory (cluster of 1 / 1 / 4 / 16 CTAs per lattice,
-    DSMEM halos) give exactly the spins, Q and per-sweep statistics of K streaming launches (same Philox keys)."""
+@pytest.mark.parametrize("L,B,K,variant", [(20, 5, 30, ""), (48, 2, 9, ""), (64, 3, 12, "0"), (64, 3, 12, "4"),
+                                            (64, 2, 5, "8"), (128, 2, 8, "0"), (128, 2, 8, "4"), (128, 2, 7, "8"),
+                                            (256, 3, 6, "0"), (256, 3, 6, "4"), (256, 2, 9, "8"), (256, 2, 1, "4")])
+def test_resident_kernel_equals_streaming_bit_for_bit(L, B, K, variant, monkeypatch):
+    """K sweeps in one launch with Q resident in shared memory (cluster of 1 / 1 / 4 / 16 CTAs per lattice, halo
+    rows pushed through DSMEM) give exactly the spins, Q and per-sweep statistics of K streaming launches (same
+    Philox keys).  `variant` picks the kernel: "0" the generic one, "4"/"8" the shape-specialised fp32 kernel with
+    4 / 8 rows per thread (MFMARL_ISING_RPT); "" leaves the default."""
     from mfmarl_b200 import IsingMFQ
+    if variant:
+        monkeypatch.setenv("MFMARL_ISING_RPT", variant)
     rng = np.random.RandomState(L)
     spins = torch.from_numpy(rng.randint(0, 2, size=(B, L, L)).astype(np.int8))
     a = IsingMFQ(B, L, seed=21, spins=spins)
     b = IsingMFQ(B, L, seed=21, spins=spins)
-    assert a.resident_cluster == {20: 1, 64: 1, 128: 4, 256: 16}[L]
+    assert a.resident_cluster == {20: 1, 48: 1, 64: 1, 128: 4, 256: 16}[L]
     temps = [max(0.8, 0.3 * 0.99)] * K
     for rounds in range(2):            # two launches: state carries over (step counter, spins, Q)
         n_res, r_res = a.run(temps, resident=True)
