@@ -209,8 +209,9 @@ __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState
         // batch reads or writes: those lanes run in parallel.  The rest ("complex") run one lane at a time
         // in lane order, i.e. in the shuffled order; since the simple lanes commute with them the result is
         // bit-identical to the one-by-one loop.
-        auto one_attack = [&](int k, int v) {
+        auto one_attack = [&](int k, int v, int i) {
             if (st_dead(s_state[k])) return;                               // attacker died earlier this step
+            s_att[i] |= 0x80000000u;                                       // it acted: a render attack event (GridWorld.cc:533)
             if (v < 0 || st_dead(s_state[v])) {                            // blank / wall / team-mate / already dead
                 s_nr[k] = s_nr[k] + P.attack_penalty;
                 return;
@@ -245,19 +246,30 @@ __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState
                 const unsigned same_v = __match_any_sync(0xFFFFFFFFu, v >= 0 ? v : -1 - lane);
                 const bool complex = valid && (s_tag_v[k] == bid ||
                                                (v >= 0 && (__popc(same_v) > 1 || s_tag_a[v] == bid)));
-                if (valid && !complex) one_attack(k, v);
+                if (valid && !complex) one_attack(k, v, i);
                 __syncwarp();
                 unsigned todo = __ballot_sync(0xFFFFFFFFu, complex);
                 while (todo) {
                     const int l = __ffs(todo) - 1;
                     todo &= todo - 1;
-                    if (lane == l) one_attack(k, v);
+                    if (lane == l) one_attack(k, v, i);
                     __syncwarp();
                 }
             }
         }
         __syncthreads();
 
+        if (io.attack_events) {   // RenderAttackEvent{id, obj_x, obj_y} in processing order (GridWorld.cc:518-560)
+            int32_t *ev = io.attack_events + (size_t)e * (1 + 6 * cap);
+            if (tid == 0) ev[0] = nA;
+            for (int i = tid; i < nA; i += nt) {
+                const uint32_t ent = s_att[i];
+                const int k = ent & 0xFFFF, a = (ent >> 16) & 0x7FFF, p = s_pos[k];
+                ev[1 + 3 * i] = (ent >> 31) ? S.id[ebase + k] : -1;
+                ev[2 + 3 * i] = pos_x(p) + P.att_dx[a];
+                ev[3 + 3 * i] = pos_y(p) + P.att_dy[a];
+            }
+        }
         // ---- starve / recover (GridWorld.cc:574-595, Agent::starve GridWorld.h:199-206) ----
         for (int s = tid; s < 2 * cap; s += nt) {
             const int g = s >= cap, i = s - g * cap;

@@ -85,6 +85,8 @@ struct StepIO {
     uint8_t *alive;             // [E][2][cap]
     float *mean_action;         // [E][2][n_action]
     int32_t *done;              // [E]
+    int32_t *attack_events;     // optional [E][1 + 3*2*cap]: count, then per attack of the shuffled order (attacker id or
+                                // -1 when it was dead at its turn, target x, target y) -- the render trace's events
     int phases;
     int setact_mask;            // groups whose actions are applied by PH_SETACT
     int group_seq[kGroups];     // order in which groups called set_action (-1 = did not act)

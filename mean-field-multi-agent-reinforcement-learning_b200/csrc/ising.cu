@@ -55,7 +55,7 @@ template <> struct Pair<double> { typedef double2 type; };
 
 template <typename T> __device__ __forceinline__ T uniform_from_bits(uint32_t hi, uint32_t lo);
 template <> __device__ __forceinline__ float uniform_from_bits<float>(uint32_t hi, uint32_t) {
-    return (float)(hi >> 8) * (1.0f / 16777216.0f);                       // 24 bits, [0, 1)
+    return __uint2float_rz(hi) * (1.0f / 4294967296.0f);                  // round toward zero keeps it in [0, 1)
 }
 template <> __device__ __forceinline__ double uniform_from_bits<double>(uint32_t hi, uint32_t lo) {
     return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6)) * (1.0 / 9007199254740992.0);   // 53 bits
@@ -71,16 +71,22 @@ __device__ __forceinline__ double action_threshold(double q0, double q1, double 
 }
 // fp32 production mode.  a = [u >= p0] with p0 = e0/(e0+e1) = 1/(1 + e), e = exp((q1-q0)/T), is evaluated as
 // u*(1 + e) >= 1, which needs neither the reciprocal nor the division: c = log2(e)/T is computed once per sweep,
-// e = ex2.approx((q1-q0)*c) (clamped so that e stays finite at tiny T), and u*e + u is one fma.  |error| of the
+// e = ex2.approx((q1-q0)*c), and u*e + u is one fma.  |error| of the
 // implied threshold < 4e-6 for |q| <= 2, T >= 0.25, i.e. an action can differ from the fp64 reference only for
 // draws that close to the threshold -- the same order as the fp32 rounding of u itself (2^-24).  Both fp32
 // kernels (streaming and resident) share this function, so they agree bit for bit.
 __device__ __forceinline__ float temperature_param(float T) { return __fdiv_rn(1.4426950408889634f, T); }
 __device__ __forceinline__ double temperature_param(double T) { return T; }
 __device__ __forceinline__ int draw_action(float u, float q0, float q1, float c) {
-    float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf((q1 - q0) * c, 126.0f)));
+    float e;                                   // e = +inf at tiny T is fine: u * inf + u >= 1 for every u > 0
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((q1 - q0) * c));
     return __fmaf_rn(u, e, u) >= 1.0f ? 1 : 0;
+}
+// the same decision with the uniform still scaled by 2^32 (m = u * 2^32, exactly): saves the rescaling multiply
+__device__ __forceinline__ int draw_action_scaled(float m, float q0, float q1, float c) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((q1 - q0) * c));
+    return __fmaf_rn(m, e, m) >= 4294967296.0f ? 1 : 0;
 }
 // fp64 mode replays the reference's operation sequence
 __device__ __forceinline__ int draw_action(double u, double q0, double q1, double T) {
@@ -588,8 +594,8 @@ __global__ void __launch_bounds__(L * (ROWS / RPT), 1) k_ising_resident_f32(cons
 #pragma unroll
         for (int h = 0; h < NPH; h++) {
             const uint4 rnd = philox4x32_10(make_uint4((uint32_t)x, gband + (uint32_t)h, step, 0u), key);
-            uu[4 * h + 0] = uniform_from_bits<float>(rnd.x, 0); uu[4 * h + 1] = uniform_from_bits<float>(rnd.y, 0);
-            uu[4 * h + 2] = uniform_from_bits<float>(rnd.z, 0); uu[4 * h + 3] = uniform_from_bits<float>(rnd.w, 0);
+            uu[4 * h + 0] = __uint2float_rz(rnd.x); uu[4 * h + 1] = __uint2float_rz(rnd.y);   // u * 2^32
+            uu[4 * h + 2] = __uint2float_rz(rnd.z); uu[4 * h + 3] = __uint2float_rz(rnd.w);
         }
     };
     if (A.u == nullptr) draw_uniforms(A.step0);
@@ -648,14 +654,15 @@ __global__ void __launch_bounds__(L * (ROWS / RPT), 1) k_ising_resident_f32(cons
         // ---- draw sweep k: s = the count just computed, Boltzmann action, publish into the other buffer ----
         if (A.u != nullptr) {
 #pragma unroll
-            for (int j = 0; j < RPT; j++) uu[j] = A.u[((size_t)k * A.B + b) * N + (size_t)(row0 + rb + j) * L + x];
+            for (int j = 0; j < RPT; j++)
+                uu[j] = A.u[((size_t)k * A.B + b) * N + (size_t)(row0 + rb + j) * L + x] * 4294967296.0f;
         }
         const uint32_t nxt = cur ^ BUF;
 #pragma unroll
         for (int j = 0; j < RPT; j++) {
             const uint32_t addr = q_site0 + (uint32_t)ups[j] * PLANE + (uint32_t)j * (L * 8u);
             const float2 pr = lds_f32x2(addr);
-            const int a = draw_action(uu[j], pr.x, pr.y, tparam);
+            const int a = draw_action_scaled(uu[j], pr.x, pr.y, tparam);
             const uint32_t word = __ballot_sync(0xFFFFFFFFu, a != 0);
             if (lane == 0) {
                 sts_u32(own_w + nxt + (uint32_t)j * WPR * 4u, word);

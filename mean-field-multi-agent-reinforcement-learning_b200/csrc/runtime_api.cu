@@ -7,9 +7,12 @@
 // Scope: the battle path.  Configurations the kernels are not built for
 // (turn_mode, food_mode, bodies larger than 1x1, sector ranges, reward rules other than
 // `any(a) attack any(b) -> a`) fail loudly at reset instead of running something different.
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <fstream>
 #include <map>
+#include <sstream>
 #include <memory>
 #include <string>
 #include <vector>
@@ -55,8 +58,15 @@ struct Game {
     std::vector<int> seq;          // groups in set_action call order since the last step
     bool inject_next = false;
 
+    // render trace (RenderGenerator.cc): config.json once, then frames appended to video_<file_ct>.txt
+    std::string render_dir;
+    bool first_render = true;
+    int file_ct = 0, frame_ct = 0, frame_per_file = 10000;
+    int32_t *d_events = nullptr; int ev_cap = 0;
+    std::vector<int32_t> events;   // (id, x, y) of the last step's attacks, processing order
+
     ~Game() {
-        cudaFree(d_view); cudaFree(d_feat); cudaFree(d_actions); cudaFree(d_perm); cudaFree(d_done);
+        cudaFree(d_view); cudaFree(d_feat); cudaFree(d_actions); cudaFree(d_perm); cudaFree(d_done); cudaFree(d_events);
     }
 
     const TypeDef &type_of(int group) const {
@@ -187,7 +197,7 @@ int env_config_game(EnvHandle game, const char *name, void *p_value) {
     else if (streq(name, "minimap_mode")) g->minimap_mode = bvalue;
     else if (streq(name, "goal_mode")) g->goal_mode = bvalue;
     else if (streq(name, "embedding_size")) g->embedding_size = ivalue;
-    else if (streq(name, "render_dir")) { /* rendering is out of scope: accepted and ignored */ }
+    else if (streq(name, "render_dir")) g->render_dir = (const char *)p_value;      // GridWorld.cc:148-149
     else if (streq(name, "seed")) {                       // GridWorld.cc:150-151
         g->seed = (unsigned long)ivalue; g->seed_set = true;
         if (g->eng) g->eng->set_seed(g->seed);
@@ -203,6 +213,7 @@ int env_reset(EnvHandle game) {
     g->ensure_engine();
     g->eng->reset();
     g->seq.clear();
+    g->file_ct++; g->frame_ct = 0;                        // RenderGenerator::next_file (GridWorld.cc:102)
     API_END("env_reset")
 }
 
@@ -254,7 +265,22 @@ int env_step(EnvHandle game, int *done) {
     io.group_seq[0] = g->seq.size() > 0 ? g->seq[0] : -1;
     io.group_seq[1] = g->seq.size() > 1 ? g->seq[1] : -1;
     if (g->inject_next) E.set_rng_mode(RNG_INJECT);
+    const bool want_events = !g->first_render;            // GridWorld.cc:533,559: recorded once a frame was rendered
+    if (want_events) {
+        if (g->ev_cap < E.cap()) {
+            cudaFree(g->d_events);
+            MF_CUDA(cudaMalloc(&g->d_events, (size_t)(1 + 6 * E.cap()) * 4));
+            g->ev_cap = E.cap();
+        }
+        io.attack_events = g->d_events;
+    }
     E.step(io, g->st);
+    if (want_events) {
+        const std::vector<int32_t> raw = pull(g->d_events, (size_t)1 + 6 * E.cap(), g->st);
+        g->events.clear();
+        for (int i = 0; i < raw[0]; i++)
+            if (raw[1 + 3 * i] >= 0) g->events.insert(g->events.end(), raw.begin() + 1 + 3 * i, raw.begin() + 4 + 3 * i);
+    }
     if (g->inject_next) { E.set_rng_mode(RNG_MINSTD); g->inject_next = false; }
     int h_done = 0;
     MF_CUDA(cudaMemcpyAsync(&h_done, g->d_done, 4, cudaMemcpyDeviceToHost, g->st));
@@ -380,8 +406,86 @@ int env_get_info(EnvHandle game, GroupHandle group, const char *name, void *void
     API_END("env_get_info")
 }
 
-int env_render(EnvHandle) { return 0; }             // rendering (RenderGenerator.cc) is out of scope: no-op
-int env_render_next_file(EnvHandle) { return 0; }
+// The on-disk trace of RenderGenerator.cc:57-185, byte for byte: <dir>/config.json at the first call, then one frame
+// per call appended to <dir>/video_<n>.txt -- "W n" + wall cells before the first frame of a file, "F agents attacks 0",
+// one "id hp dir x y group" line per agent still in the lists (dead ones included until clear_dead, hp as an integer
+// percentage clamped to [0, 100], dir 0 = north), one "0 id x y" line per attack of the last step.
+int env_render(EnvHandle game) {
+    API_BEGIN
+    Game *g = G(game);
+    Engine &E = g->engine();
+    g->ensure_staging();
+    const TypeDef &t0 = g->type_of(0);
+    if (g->first_render) {
+        g->first_render = false;
+        if (!g->render_dir.empty()) {
+            std::ofstream f(g->render_dir + "/config.json");
+            const int colors[4][3] = {{192, 64, 64}, {64, 64, 192}, {64, 192, 64}, {64, 64, 64}};
+            auto rgba = [](int r, int gr, int b, float alpha) {
+                std::stringstream ss;
+                ss << "\"rgba(" << r << "," << gr << "," << b << "," << alpha << ")\"";
+                return ss.str();
+            };
+            auto kv = [&f](const char *key, const std::string &value, bool last = false) {
+                f << "\"" << key << "\": " << value << (last ? "" : ",") << std::endl;
+            };
+            auto num = [](float v) { std::stringstream ss; ss << v; return ss.str(); };
+            f << "{" << std::endl;
+            kv("width", std::to_string(g->width)); kv("height", std::to_string(g->height));
+            kv("static-file", "\"static.map\""); kv("obstacle-style", rgba(127, 127, 127, 1));
+            kv("dynamic-file-directory", "\".\""); kv("attack-style", rgba(63, 63, 63, 0.8f));
+            kv("minimap-width", "300"); kv("minimap-height", "250");
+            f << "\"group\" : [" << std::endl;
+            for (size_t i = 0; i < g->groups.size(); i++) {
+                const TypeDef &t = g->type_of((int)i);
+                const int *c = colors[i % 4];
+                f << "{" << std::endl;
+                kv("height", std::to_string(t.length)); kv("width", std::to_string(t.width));
+                kv("style", rgba(c[0], c[1], c[2], 1)); kv("anchor", "[0, 0]");
+                kv("max-speed", std::to_string((int)t.p.speed)); kv("speed-style", rgba(c[0], c[1], c[2], 0.01f));
+                kv("vision-radius", num(t.p.view_radius)); kv("vision-angle", num(t.view_angle));
+                kv("vision-style", rgba(c[0], c[1], c[2], 0.2f));
+                kv("attack-radius", num(t.p.attack_radius)); kv("attack-angle", num(t.attack_angle));
+                kv("attack-style", rgba(c[0], c[1], c[2], 0.1f)); kv("broadcast-radius", "1", true);
+                f << (i + 1 == g->groups.size() ? "}" : "},") << std::endl;
+            }
+            f << "]" << std::endl << "}" << std::endl;
+        }
+    }
+    if (g->render_dir.empty()) return 0;
+    std::ofstream out(g->render_dir + "/video_" + std::to_string(g->file_ct) + ".txt",
+                      g->frame_ct == 0 ? std::ios::out : std::ios::app);
+    if (g->frame_ct == 0) {
+        const std::vector<unsigned char> &w = E.host_walls();
+        out << "W " << std::count_if(w.begin(), w.end(), [](unsigned char c) { return c != 0; }) << std::endl;
+        for (int i = 0; i < g->width * g->height; i++)
+            if (w[i]) out << i % g->width << " " << i / g->width << std::endl;
+    }
+    const BattleState &S = E.state();
+    const int cap = E.cap();
+    const int n0 = E.host_num(0, 0), n1 = E.host_num(0, 1);
+    out << "F " << n0 + n1 << " " << g->events.size() / 3 << " " << 0 << std::endl;
+    for (int grp = 0; grp < 2; grp++) {
+        const int n = grp ? n1 : n0;
+        const std::vector<int32_t> pos = pull(S.pos + (size_t)grp * cap, n, g->st), id = pull(S.id + (size_t)grp * cap, n, g->st);
+        const std::vector<float> hp = pull(S.hp + (size_t)grp * cap, n, g->st);
+        for (int j = 0; j < n; j++) {
+            const int pct = std::min(100, std::max(0, (int)(100 * hp[j] / t0.p.hp)));
+            out << id[j] << " " << pct << " " << 0 << " " << (pos[j] & 0xFFFF) << " " << (pos[j] >> 16) << " " << grp << std::endl;
+        }
+    }
+    for (size_t i = 0; i + 2 < g->events.size(); i += 3)
+        out << 0 << " " << g->events[i] << " " << g->events[i + 1] << " " << g->events[i + 2] << std::endl;
+    if (g->frame_ct++ > g->frame_per_file) { g->frame_ct = 0; g->file_ct++; }
+    API_END("env_render")
+}
+
+int env_render_next_file(EnvHandle game) {
+    API_BEGIN
+    Game *g = G(game);
+    g->file_ct++; g->frame_ct = 0;
+    API_END("env_render_next_file")
+}
 
 int gridworld_register_agent_type(EnvHandle game, const char *name, int n, const char **keys, float *values) {
     API_BEGIN

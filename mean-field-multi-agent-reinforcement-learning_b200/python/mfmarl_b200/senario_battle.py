@@ -123,9 +123,9 @@ def play_batched(env, n_round, max_steps, models, eps=1.0, train=False, print_ev
     env.add_agents(left_group, positions[0])
     env.add_agents(1 - left_group, positions[1])
     n_action = env.sizes["n_action"]
-    num = torch.as_tensor(env.get_num(), device=dev)                    # [E, 2] int32
-    max_nums = num.clone()
-    ids = torch.as_tensor(env.get("id"), device=dev)                    # [E, 2, cap], compacted like the engine does
+    live_num, live_id = env.device_state("num"), env.device_state("id")    # aliases of the engine's HBM state
+    num = live_num.clone()                                                 # [E, 2] agents at observation time
+    max_nums, final_nums = num.clone(), num.clone()
     former = torch.zeros((E, 2, n_action), dtype=torch.float32, device=dev)
     active = torch.ones((E,), dtype=torch.bool, device=dev)
     slot = torch.arange(cap, device=dev, dtype=torch.int32)
@@ -135,38 +135,35 @@ def play_batched(env, n_round, max_steps, models, eps=1.0, train=False, print_ev
     actions = torch.zeros((E, 2, cap), dtype=torch.int32, device=dev)
     step_ct = 0
     while step_ct < max_steps and bool(active.any()):
-        view, feat = env.observe()
+        obs = env.observe_groups()                         # per group: view [E, cap, 13, 13, 7], feature [E, cap, 34]
+        num.copy_(live_num)
+        ids = live_id.clone()                              # rows of this step, before clear_dead compacts them
         valid = (slot[None, None, :] < num[:, :, None]) & active[:, None, None]          # [E, 2, cap]
         for g in range(2):
+            view, feat = obs[g]
             prob = former[:, g, None, :].expand(E, cap, n_action).reshape(E * cap, n_action)
-            a = models[g].act(state=[view[:, g].reshape((E * cap,) + tuple(view.shape[3:])),
-                                     feat[:, g].reshape(E * cap, -1)], prob=prob, eps=eps)
+            a = models[g].act(state=[view.view((E * cap,) + tuple(view.shape[2:])), feat.view(E * cap, -1)],
+                              prob=prob, eps=eps)
             actions[:, g] = a.reshape(E, cap)
         actions.masked_fill_(~valid, 0)
-        if train:
-            view0, feat0 = view[:, 0], feat[:, 0]
         reward, alive, done, mean = env.step(actions)
-        if train:   # rows of this step, before clear_dead compacts the ids
-            models[0].flush_buffer_batched(state=(view0, feat0), acts=actions[:, 0], rewards=reward[:, 0],
-                                           alives=alive[:, 0], ids=ids[:, 0], prob=former[:, 0], num=num[:, 0],
-                                           active=active)
+        if train:
+            models[0].flush_buffer_batched(state=obs[0], acts=actions[:, 0], rewards=reward[:, 0], alives=alive[:, 0],
+                                           ids=ids[:, 0], prob=former[:, 0], num=num[:, 0], active=active)
         # statistics (senario_battle.py:146-152): nums still include the agents that died this step
         r = torch.where(valid, reward, torch.zeros_like(reward)).to(torch.float64).sum(dim=2)   # [E, 2]
         act_f = active[:, None].to(torch.float64)
         sum_total += r * act_f
         sum_mean += r / num.clamp(min=1).to(torch.float64) * act_f
         steps_run += active.to(torch.int64)
-        # the engine compacted the survivors (clear_dead inside the launch): do the same to the id table
-        keep = valid & alive.bool()
-        order = torch.sort((~keep).to(torch.int8), dim=2, stable=True).indices
-        ids = torch.gather(ids, 2, order)
-        new_num = keep.sum(dim=2).to(torch.int32)
-        num = torch.where(active[:, None], new_num, num)
+        final_nums = torch.where(active[:, None], live_num, final_nums)    # after clear_dead, like the last get_num
         former = torch.where(active[:, None, None], mean, former)
         active = active & (done == 0)
         step_ct += 1
         if print_every and step_ct % print_every == 0:
-            print("> step #{}, active envs: {}, agents: {}".format(step_ct, int(active.sum()), num.sum(dim=0).tolist()))
+            print("> step #{}, active envs: {}, agents: {}".format(step_ct, int(active.sum()),
+                                                                   final_nums.sum(dim=0).tolist()))
+    num = final_nums
     if train:
         models[0].train()
     steps = steps_run.clamp(min=1).to(torch.float64)[:, None]

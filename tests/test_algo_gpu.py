@@ -1,0 +1,133 @@
+"""Batched, device-resident rollout (`senario_battle.play_batched`) against the reference-shaped host loop (`play`
+through the `magent` binding), both over the CUDA engine, plus one training round of every learner on the GPU."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from engines import CUDA_SO
+
+pytestmark = pytest.mark.gpu
+
+ADVANCE = {+1: [7, 8, 3, 11], -1: [5, 4, 1, 9]}
+
+
+class ExactPolicy:
+    """A policy whose decision uses only exactly representable inputs (0/1 view cells, id bits, one mean-action entry
+    compared with a threshold no count/n can hit), so the numpy and the torch evaluation agree bit for bit:
+    attack the first adjacent enemy, else advance with a move picked from the id bits and the mean action."""
+
+    def __init__(self, direction):
+        self.moves_np = np.array(ADVANCE[direction], np.int32)
+        self.rows = []
+
+    def act(self, state, prob, eps):
+        view, feat = state
+        if isinstance(view, torch.Tensor):
+            near = view[:, 5:8, 5:8, 4].reshape(view.shape[0], 9)
+            near = torch.cat([near[:, :4], near[:, 5:]], dim=1) > 0
+            pick = (feat[:, 0] + 2 * feat[:, 1]).to(torch.int64) + (prob[:, 7] > 0.3137).to(torch.int64)
+            acts = torch.as_tensor(self.moves_np, device=view.device)[pick % 4]
+            first = torch.argmax(near.to(torch.int8), dim=1).to(torch.int32)
+            return torch.where(near.any(dim=1), 13 + first, acts).to(torch.int32)
+        near = view[:, 5:8, 5:8, 4].reshape(len(view), 9)
+        near = np.delete(near, 4, axis=1) > 0
+        pick = (feat[:, 0] + 2 * feat[:, 1]).astype(np.int64) + (prob[:, 7] > 0.3137).astype(np.int64)
+        acts = self.moves_np[pick % 4]
+        return np.where(near.any(axis=1), 13 + np.argmax(near, axis=1), acts).astype(np.int32)
+
+    # recording "learner"
+    def flush_buffer(self, **kw):
+        self.rows.append({k: np.array(kw[k]) for k in ("ids", "acts", "rewards", "alives")} | {"prob": np.array(kw["prob"][0])})
+
+    def flush_buffer_batched(self, **kw):
+        self.rows.append({k: kw[k].cpu().numpy().copy() for k in ("ids", "acts", "rewards", "alives", "prob", "num", "active")})
+
+    def train(self):
+        pass
+
+
+def test_play_batched_equals_host_play_per_environment():
+    import magent
+    from magent import c_lib
+    from mfmarl_b200 import BatchedGridWorld
+    from mfmarl_b200.senario_battle import play, play_batched
+    steps, E = 70, 3
+    # host loop, one environment through the reference binding (group 0 on the left)
+    env = magent.GridWorld("battle", lib=c_lib.load(CUDA_SO), map_size=40)
+    handles = env.get_handles()
+    random.seed(1)
+    state = random.getstate(); left = random.randint(0, 1); random.setstate(state)
+    host_models = [ExactPolicy(+1 if left == 0 else -1), ExactPolicy(-1 if left == 0 else +1)]
+    h_max, h_nums, h_mean, h_total = play(env=env, n_round=0, map_size=40, max_steps=steps, handles=handles,
+                                          models=host_models, print_every=1000, eps=1.0, train=True)
+    assert sum(h_nums) < 128, "the stand-in policies should produce kills"
+    # batched loop, E identical environments on the device
+    benv = BatchedGridWorld(E, map_size=40, capacity=64, rng="minstd", seed=0)
+    dev_models = [ExactPolicy(+1 if left == 0 else -1), ExactPolicy(-1 if left == 0 else +1)]
+    b_max, b_nums, b_mean, b_total = play_batched(benv, 0, steps, dev_models, eps=1.0, train=True, left_group=left)
+    for e in range(E):
+        assert list(b_max[e]) == list(h_max) and list(b_nums[e]) == list(h_nums)
+        np.testing.assert_allclose(b_total[e], np.array(h_total, np.float64), rtol=1e-5, atol=1e-4)
+        np.testing.assert_allclose(b_mean[e], np.array(h_mean, np.float64), rtol=1e-5, atol=1e-6)
+    assert len(dev_models[0].rows) == len(host_models[0].rows)
+    for t, (d, h) in enumerate(zip(dev_models[0].rows, host_models[0].rows)):
+        n = len(h["ids"])
+        for e in range(E):
+            assert d["num"][e] == n and d["active"][e]
+            assert np.array_equal(d["ids"][e, :n], h["ids"]), t
+            assert np.array_equal(d["acts"][e, :n], h["acts"]), t
+            assert np.array_equal(d["rewards"][e, :n].view(np.uint32), h["rewards"].view(np.uint32)), t
+            assert np.array_equal(d["alives"][e, :n].astype(bool), h["alives"]), t
+            np.testing.assert_allclose(d["prob"][e], h["prob"], rtol=1e-6, atol=1e-7)       # mean action: 1e-6
+
+
+def test_observe_groups_and_device_state_alias():
+    from mfmarl_b200 import BatchedGridWorld
+    from scenarios import generate_map_positions, uniform_actions
+    E = 5
+    env = BatchedGridWorld(E, map_size=40, capacity=64, rng="minstd")
+    left, right = generate_map_positions(40)
+    env.reset(); env.add_agents(0, left); env.add_agents(1, right)
+    rng = np.random.RandomState(0)
+    for _ in range(3):
+        view, feat = env.observe()
+        view, feat = view.clone(), feat.clone()
+        (v0, f0), (v1, f1) = env.observe_groups()
+        num = env.get_num()
+        for e in range(E):
+            for g, (vg, fg) in enumerate(((v0, f0), (v1, f1))):
+                n = num[e, g]
+                assert torch.equal(vg[e, :n], view[e, g, :n]) and torch.equal(fg[e, :n], feat[e, g, :n])
+        only1 = env.observe_groups(groups=(1,))
+        assert only1[0] is None and torch.equal(only1[1][0], v1)
+        assert np.array_equal(env.device_state("num").cpu().numpy(), num)
+        assert np.array_equal(env.device_state("id").cpu().numpy(), env.get("id"))
+        acts = np.stack([np.stack([uniform_actions(rng, 64) for _ in range(2)]) for _ in range(E)])
+        env.step(torch.from_numpy(acts).cuda())
+
+
+@pytest.mark.parametrize("algo", ["mfq", "il", "mfac", "ac"])
+def test_every_learner_trains_a_batched_round_on_the_gpu(algo):
+    from mfmarl_b200 import BatchedGridWorld
+    from mfmarl_b200.algo import spawn_ai
+    from mfmarl_b200.senario_battle import play_batched
+    torch.manual_seed(0)
+
+    class Spaces:
+        def get_view_space(self, h): return (13, 13, 7)
+        def get_feature_space(self, h): return (34,)
+        def get_action_space(self, h): return (21,)
+
+    E, steps = 6, 10
+    env = BatchedGridWorld(E, map_size=40, capacity=64, rng="philox", seed=3)
+    models = [spawn_ai(algo, Spaces(), 0, algo + "-me", steps, device="cuda"),
+              spawn_ai(algo, Spaces(), 1, algo + "-opponent", steps, device="cuda")]
+    before = [p.detach().clone() for p in models[0].vars]
+    max_nums, nums, mean_r, total_r = play_batched(env, 0, steps, models, eps=1.0, train=True, left_group=0)
+    assert max_nums.shape == (E, 2) and (max_nums == 64).all() and (nums <= 64).all()
+    assert np.isfinite(mean_r).all() and np.isfinite(total_r).all()
+    assert any(not torch.equal(a, b) for a, b in zip(before, models[0].vars))
+    for p in models[0].vars:
+        assert torch.isfinite(p).all()
