@@ -131,3 +131,30 @@ def test_every_learner_trains_a_batched_round_on_the_gpu(algo):
     assert any(not torch.equal(a, b) for a, b in zip(before, models[0].vars))
     for p in models[0].vars:
         assert torch.isfinite(p).all()
+
+
+def test_train_battle_and_battle_scripts_end_to_end(tmp_path):
+    """train_battle.py (two rounds, single environment through magent, then two rounds with 8 lock-stepped
+    environments) and battle.py on the checkpoints it saved -- the reference's two entry points, same flags."""
+    import importlib.util
+    import os
+    from conftest import PKG
+
+    def load(name):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(PKG, "python", name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+
+    train, battle = load("train_battle"), load("battle")
+    assert train.linear_decay(0, [0, 8, 10], [1, 0.2, 0.1]) == 1 and abs(train.linear_decay(9, [0, 8, 10], [1, 0.2, 0.1]) - 0.15) < 1e-12
+    data = str(tmp_path / "data")
+    for algo in ("mfq", "mfac"):
+        common = ["--algo", algo, "--n_round", "2", "--max_steps", "8", "--data_dir", data]
+        runner = train.main(common)
+        for tag in ("0", "1"):            # make sure checkpoints exist even if the self-play condition never fired
+            runner.models[int(tag)].save(os.path.join(data, "models/%s-%s" % (algo, tag)), 0)
+        train.main(common + ["--envs", "8"])
+    win = battle.main(["--algo", "mfq", "--oppo", "mfac", "--n_round", "2", "--max_steps", "8", "--idx", "0", "0",
+                       "--data_dir", data])
+    assert win["main"] + win["opponent"] >= 2
