@@ -470,7 +470,10 @@ def run_ising(args):
             "gpu_launches": K // S,
             "sweeps_per_launch": S,
             "roofline": {"bound": "hbm", "kernel": "k_ising_resident" if resident else "k_ising", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": ncu_traffic("c5"), "peak_source": peak_src,
+                         "frac": achieved / peak,
+                         "traffic": (lambda t: None if t is None else t * B * L * L)(ncu_traffic(
+                             "c5_resident_bytes_per_site_per_launch" if resident else "c5_stream_bytes_per_site_per_launch")),
+                         "peak_source": peak_src,
                          "bytes_per_site": BYTES_PER_SITE, "sites_per_launch": B * L * L * S,
                          "note": ("algorithmic bytes are the STREAMING formulation's 14 B per site-step; the resident "
                                   "kernel keeps Q in shared memory for %d sweeps and really moves (80 + 2) / %d B per "

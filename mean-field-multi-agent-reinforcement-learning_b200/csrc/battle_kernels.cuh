@@ -595,8 +595,9 @@ k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO i
         const float *mini_own = s_mini + g * kViewCells, *mini_oth = s_mini + (1 - g) * kViewCells;
 
         // ---- stream the tile: compose, bulk-store ----
-        float *vout = io.view[g] + (size_t)e * io.env_stride * kViewRow;
-        float *fout = io.feature[g] + (size_t)e * io.env_stride * FS;
+        // (selects, not io.view[g]: a dynamic index into a kernel parameter would spill the struct to local memory)
+        float *vout = (g ? io.view[1] : io.view[0]) + (size_t)e * io.env_stride * kViewRow;
+        float *fout = (g ? io.feature[1] : io.feature[0]) + (size_t)e * io.env_stride * FS;
         int self_prev1 = -1, self_prev2 = -1;   // self-marker cell of the row in the other / this buffer
         int stale = 2;                          // staging buffers whose minimap channels belong to another item
         for (int c0 = a_begin; c0 < a_end; c0 += kObsChunk, buf ^= 1) {

@@ -81,8 +81,8 @@ def main(argv=None):
         import magent
         from mfmarl_b200.senario_battle import play
         env = magent.GridWorld('battle', map_size=args.map_size)
-        env.set_render_dir(os.path.join(args.data_dir, 'render'))
         os.makedirs(os.path.join(args.data_dir, 'render'), exist_ok=True)
+        env.set_render_dir(os.path.join(args.data_dir, 'render'))
         handles = env.get_handles()
     models = [spawn_ai(args.algo, env, handles[0], args.algo + '-me', args.max_steps, device=args.device),
               spawn_ai(args.algo, env, handles[1], args.algo + '-opponent', args.max_steps, device=args.device)]
