@@ -35,6 +35,8 @@ WORKLOADS = {
     "c4": dict(name="battle_80x80_512v512_128envs_per_gpu_uniform_actions (BASELINE configs[3] shard)",
                map_size=80, cap=512, envs=128, max_steps=400),
 }
+WORKLOADS["play"] = dict(name="battle_40x40_64v64_rollout_with_policy_networks (senario_battle.play, batched)",
+                         map_size=40, cap=64, envs=1024, max_steps=400)
 WORKLOADS["c5"] = dict(name="ising_256x256_x16384_lattices_mfq_T0.8 (BASELINE configs[4])", side=256,
                        lattices=16384, temperature=0.8, lr=0.1)
 REF_SO = os.path.join(REPO, "oracle", "_ref", "libmagent_ref.so")
@@ -53,7 +55,7 @@ def cpu_worker(argv):
     """One single-threaded environment: `warm` untimed + `steps` timed lockstep steps of the hot loop
     (get_observation x2, set_action x2, step, get_reward/get_alive x2, mean action, clear_dead)."""
     kind, map_size, warm, steps, seed = argv[0], int(argv[1]), int(argv[2]), int(argv[3]), int(argv[4])
-    os.environ["OMP_NUM_THREADS"] = "1"
+    os.environ["OMP_NUM_THREADS"] = argv[5] if len(argv) > 5 else "1"
     import numpy as np
     from engines import OracleEngine, RefEngine
     from scenarios import c4_positions, generate_map_positions
@@ -100,6 +102,16 @@ def run_cpu(kind, map_size, warm, steps, procs):
     total = sum(o["agent_steps"] for o in outs)
     seconds = max(o["seconds"] for o in outs)
     return total / seconds, total, seconds
+
+
+def run_cpu_openmp(kind, map_size, warm, steps, threads):
+    """SURVEY.md 8d mode (ii): ONE environment with the reference's intra-env OpenMP on `threads` threads (its
+    default is cpu_count // 2, c_lib.py:53-54).  Nondeterministic under OpenMP (SURVEY F2) -- timing only."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--_cpu_worker", kind, str(map_size), str(warm), str(steps),
+           "999", str(threads)]
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads), CUDA_VISIBLE_DEVICES="")
+    out = json.loads(subprocess.run(cmd, stdout=subprocess.PIPE, env=env).stdout.decode().strip().splitlines()[-1])
+    return out["agent_steps"] / out["seconds"], out["seconds"]
 
 
 def cpu_kind():
@@ -309,6 +321,29 @@ def run_ours(args):
     h2d = P * h_act[0][0].numel() * 4
     d2h = P * sum(t.numel() * t.element_size() for t in results[0][0])
 
+    # ---- the same loop with the observations ALSO copied to pinned host memory every step, i.e. what a policy that
+    #      lives on the host (the reference's own TF feed) would cost: PCIe-bound, reported for completeness ----
+    obs_host = None
+    if args.obs_to_host_steps > 0:
+        view0, feat0 = envs[0].observe()
+        h_view = torch.empty(view0.shape, dtype=torch.float32).pin_memory()
+        h_feat = torch.empty(feat0.shape, dtype=torch.float32).pin_memory()
+        barrier()
+        as2 = agent_steps_total()
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        o0.record()
+        for k in range(args.obs_to_host_steps):
+            for h, env in enumerate(envs):
+                v, f = env.observe()
+                h_view.copy_(v, non_blocking=True); h_feat.copy_(f, non_blocking=True)
+                env.host_wait(env.step_host_async(h_act[h][k % POOL], *results[h][k & 1]))
+        o1.record()
+        barrier()
+        obs_host = {"value": (agent_steps_total() - as2) / (o0.elapsed_time(o1) * 1e-3), "unit": "agent-steps/s",
+                    "steps": args.obs_to_host_steps,
+                    "d2h_bytes_per_step": d2h + P * (h_view.numel() + h_feat.numel()) * 4,
+                    "note": "observations copied to pinned host memory as well (rank 0's figure): PCIe-bound"}
+
     if world > 1:
         t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -346,7 +381,8 @@ def run_ours(args):
                     "d2h_bytes_per_step": d2h,
                     "note": "mfb_step_host_async: actions from pinned host memory, rewards/alive/done/mean action "
                             "copied back to pinned host memory and waited for every step (copies pipelined under "
-                            "k_obs); observations stay in HBM for the policy network"},
+                            "k_obs); observations stay in HBM for the policy network",
+                    "with_observations_to_host": obs_host},
             "clocks": clocks.summary(),
         }
         if world == 1 and not args.no_cpu:
@@ -356,6 +392,11 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": v, "unit": "agent-steps/s", "cores": procs, "kind": kind,
                                     "sample": "%d independent single-thread envs (OMP_NUM_THREADS=1) x %d lockstep steps "
                                               "of the same hot loop, %.1f s" % (procs, args.cpu_steps, secs)}
+            if kind == "reference":
+                v2, secs2 = run_cpu_openmp(kind, wl["map_size"], 20, max(2000, args.cpu_steps // 10), procs)
+                line["cpu_baseline"]["one_env_openmp"] = {
+                    "value": v2, "threads": procs,
+                    "note": "one env, the reference's intra-env OpenMP on all cores (%.1f s); racy by construction" % secs2}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -499,6 +540,49 @@ def run_ising(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# rollout with the policy networks in the loop: an additional line, not the headline
+# ------------------------------------------------------------------------------------------------
+def run_play(args):
+    import torch
+    from mfmarl_b200 import BatchedGridWorld
+    from mfmarl_b200.algo import spawn_ai
+    from mfmarl_b200.senario_battle import play_batched
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    wl = WORKLOADS["play"]
+    E, K = args.envs or wl["envs"], args.steps
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    env = BatchedGridWorld(E, map_size=wl["map_size"], capacity=wl["cap"], device=dev, rng="philox", seed=0)
+
+    class Spaces:
+        def get_view_space(self, h): return (13, 13, 7)
+        def get_feature_space(self, h): return (34,)
+        def get_action_space(self, h): return (21,)
+
+    models = [spawn_ai(args.algo, Spaces(), g, "%s-%d" % (args.algo, g), K, device=dev) for g in range(2)]
+    play_batched(env, 0, max(3, args.warmup), models, eps=1.0, train=False, left_group=0)
+    torch.cuda.synchronize()
+    a0 = int(env.get("agent_steps").sum())
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(dev.index or 0) as clocks:
+        t0.record()
+        play_batched(env, 1, K, models, eps=1.0, train=False, left_group=0)
+        t1.record()
+        torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1)
+    agent_steps = int(env.get("agent_steps").sum()) - a0
+    print(json.dumps({
+        "metric": "battle rollout agent-steps/sec incl. policy networks", "value": agent_steps / (ms * 1e-3),
+        "unit": "agent-steps/s", "n_gpus": 1, "steps": K, "warmup": max(3, args.warmup), "ms_per_step": ms / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "envs_per_gpu": E, "algo": args.algo,
+                   "note": "play_batched: k_obs (per-group blocks) -> two PyTorch policy forwards on the observation "
+                           "block in place -> k_step; nothing leaves the device except one `any(active)` flag per step"},
+        "clocks": clocks.summary()}), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU engine on the host cores, same metric / config
 # ------------------------------------------------------------------------------------------------
 def run_reference(args):
@@ -551,6 +635,9 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's)")
     ap.add_argument("--cpu-steps", type=int, default=60000, help="timed steps per CPU-baseline worker")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--algo", default="mfq", choices=["mfq", "il", "mfac", "ac"], help="--workload play: the learner")
+    ap.add_argument("--obs-to-host-steps", type=int, default=5,
+                    help="extra e2e variant: steps timed with the observations copied to the host too (0 = skip)")
     ap.add_argument("--pipeline", type=int, default=1,
                     help="split the GPU's envs into this many engines on separate streams (k_step under k_obs)")
     ap.add_argument("--sweeps-per-launch", type=int, default=0,
@@ -571,6 +658,8 @@ def main():
         raise SystemExit(subprocess.call(cmd))
     if args.workload == "c5":
         return run_ising(args)
+    if args.workload == "play":
+        return run_play(args)
     run_ours(args)
 
 

@@ -409,7 +409,7 @@ int env_get_info(EnvHandle game, GroupHandle group, const char *name, void *void
 // The on-disk trace of RenderGenerator.cc:57-185, byte for byte: <dir>/config.json at the first call, then one frame
 // per call appended to <dir>/video_<n>.txt -- "W n" + wall cells before the first frame of a file, "F agents attacks 0",
 // one "id hp dir x y group" line per agent still in the lists (dead ones included until clear_dead, hp as an integer
-// percentage clamped to [0, 100], dir 0 = north), one "0 id x y" line per attack of the last step.
+// percentage clamped to [0, 100], dir = dir2angle[NORTH] = 270), one "0 id x y" line per attack of the last step.
 int env_render(EnvHandle game) {
     API_BEGIN
     Game *g = G(game);
@@ -471,7 +471,7 @@ int env_render(EnvHandle game) {
         const std::vector<float> hp = pull(S.hp + (size_t)grp * cap, n, g->st);
         for (int j = 0; j < n; j++) {
             const int pct = std::min(100, std::max(0, (int)(100 * hp[j] / t0.p.hp)));
-            out << id[j] << " " << pct << " " << 0 << " " << (pos[j] & 0xFFFF) << " " << (pos[j] >> 16) << " " << grp << std::endl;
+            out << id[j] << " " << pct << " " << 270 /* NORTH: turn_mode is off, GridWorld.cc:264 */ << " " << (pos[j] & 0xFFFF) << " " << (pos[j] >> 16) << " " << grp << std::endl;
         }
     }
     for (size_t i = 0; i + 2 < g->events.size(); i += 3)
