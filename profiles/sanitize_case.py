@@ -23,6 +23,16 @@ for (ms, cap, pos) in [(40, 64, (left, right)), (80, 512, c4_positions())]:
         for e in range(3):
             for g in range(2): a[e, g, :n[e, g]] = fight_actions(rng, p[e, g, :n[e, g]], ms)
         env.step(torch.from_numpy(a).cuda())
-for L in (20, 64, 256):
-    m = IsingMFQ(2, L); m.run([0.8] * 3, resident=False); m.run([0.8] * 3, resident=True)
+for L in (20, 64, 128, 256):
+    for rpt in ("0", "4", "8"):          # generic cluster-barrier kernel, specialised st.async/mbarrier kernel (4 / 8 rows per thread)
+        os.environ["MFMARL_ISING_RPT"] = rpt
+        m = IsingMFQ(2, L); m.run([0.8] * 3, resident=False); m.run([0.8] * 5, resident=True)
+env = BatchedGridWorld(3, map_size=40, capacity=64, rng="minstd")
+env.reset(); env.add_agents(0, left); env.add_agents(1, right)
+env.observe_groups(); env.observe_groups(groups=(1,)); env.device_state("id")
+tmp = "/tmp/_trace"; os.makedirs(tmp, exist_ok=True)
+cu.env.set_render_dir(tmp)
+for s in range(4):
+    for g in range(2): cu.set_action(g, fight_actions(rng, cu.get_pos(g), 40))
+    cu.step(); cu.env.render(); cu.clear_dead()
 torch.cuda.synchronize(); print("sanitize case done")

@@ -268,3 +268,34 @@ def test_host_buffer_paths_match_the_device_path():
     async_env.host_wait(ticket)
     same(async_out[79 & 1], prev[0], prev[1])
     assert deaths > 10
+
+
+def test_annihilated_group_keeps_stepping_without_nan():
+    """A finished environment (one group wiped out) is unreachable in the reference's loop -- `done` ends it, and
+    get_observation would dereference agents[0] (GridWorld.cc:357).  The lock-step engine keeps stepping it next to
+    the live ones, so the behaviour is defined: done stays set, the empty group has no rows, its minimap and mean
+    action are 0 (not 0/0), and the survivors' observations stay finite."""
+    from mfmarl_b200 import BatchedGridWorld
+    E = 3
+    env = BatchedGridWorld(E, map_size=40, capacity=64, rng="minstd")
+    env.reset()
+    env.add_agents(0, [[10, 10, 0], [12, 10, 0], [10, 12, 0], [12, 12, 0]])      # four attackers around ...
+    env.add_agents(1, [[11, 11, 0]])                                              # ... one victim
+    # attack deltas (SURVEY.md section 8): 13 (-1,-1) 15 (1,-1) 18 (-1,1) 20 (1,1); the victim idles
+    acts = torch.zeros((E, 2, 64), dtype=torch.int32, device="cuda")
+    acts[:, 0, :4] = torch.tensor([20, 18, 15, 13], dtype=torch.int32)
+    acts[:, 1, 0] = 6
+    done_at = None
+    for s in range(6):
+        env.observe()
+        reward, alive, done, mean = env.step(acts)
+        if int(done[0]) and done_at is None:
+            done_at = s
+    assert done_at is not None and done_at <= 2        # 4 hits of 2 per step against hp 10 (+0.1 recovery): dead in 2 steps
+    assert env.get_num().tolist() == [[4, 0]] * E
+    view, feat = env.observe()
+    assert torch.isfinite(view[:, 0, :4]).all() and torch.isfinite(feat[:, 0, :4]).all()
+    assert float(view[:, 0, :4, :, :, 6].abs().max()) <= 1.0           # other-group minimap: only the +1 self marker
+    reward, alive, done, mean = env.step(acts)
+    assert done.tolist() == [1] * E and torch.isfinite(reward[:, 0, :4]).all()
+    assert float(mean[:, 1].abs().sum()) == 0.0 and abs(float(mean[0, 0].sum()) - 1.0) < 1e-6
