@@ -528,16 +528,18 @@ k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO i
 
     // ---- per-lane view geometry: cell c = pass * 32 + lane -> offset in the padded grid relative to the
     //      window's top-left corner; cells outside the view disc keep offset 0 with the disc bit cleared ----
-    int off[kObsPasses];
-    uint32_t disc = 0;
+    constexpr int kDiscPasses = kObsDiscSlots / 32;
+    int off[kDiscPasses], cell7[kDiscPasses];     // grid offset and staging-row offset (cell * 7) of this lane's cells; -1 = idle
 #pragma unroll
-    for (int it = 0; it < kObsPasses; it++) {
-        const int c = it * 32 + lane;
+    for (int it = 0; it < kDiscPasses; it++) {
+        const int c = P.obs_cell[it * 32 + lane];
         const int vy = c / kView, vx = c - vy * kView;
-        const bool in = c < kViewCells && ((P.disc[it] >> lane) & 1u);
-        off[it] = in ? vy * PW + vx : 0;
-        if (in) disc |= 1u << it;
+        off[it] = c < kViewCells ? vy * PW + vx : 0;
+        cell7[it] = c < kViewCells ? c * kChan : -1;
     }
+    // cells outside the view disc never carry occupancy: their five occupancy channels are zeroed once here and
+    // never written again (the minimap channels of all 169 cells are refreshed per item below)
+    for (int i = tid; i < 2 * kObsStageBytes / 16; i += kObsThreads) ((uint4 *)s_stage0)[i] = make_uint4(0u, 0u, 0u, 0u);
 
     // Persistent CTAs: each loops over work items (env, group, tile).  The bulk stores are asynchronous, so
     // the grid rebuild of the next item overlaps the drain of this item's last chunks, and the staging-buffer
@@ -616,19 +618,24 @@ k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO i
                 // window top-left corner (ax - 6, ay - 6) in padded coordinates is simply (ax, ay)
                 const uint16_t *win = s_code + ay * PW + ax;
 #pragma unroll
-                for (int it = 0; it < kObsPasses; it++) {
-                    const int c = it * 32 + lane;
-                    if (c < kViewCells) {               // compile-time true for passes 0..4
-                        const uint32_t code = ((disc >> it) & 1u) ? (uint32_t)win[off[it]] : 0u;
+                for (int it = 0; it < kDiscPasses; it++) {
+                    if (cell7[it] >= 0) {               // only the last pass has idle lanes
+                        const uint32_t code = (uint32_t)win[off[it]];
                         const uint32_t k = code >> 14;
                         const float hp = s_hp10[code & 0x3FFFu];
-                        float *o = row + c * kChan;
+                        float *o = row + cell7[it];
                         o[0] = k == KIND_WALL ? 1.0f : 0.0f;
                         o[1] = k == KIND_OWN ? 1.0f : 0.0f;
                         o[2] = k == KIND_OWN ? hp : 0.0f;
                         o[4] = k == KIND_OTHER ? 1.0f : 0.0f;
                         o[5] = k == KIND_OTHER ? hp : 0.0f;
-                        if (stale > 0) { o[3] = mini_own[c]; o[6] = mini_oth[c]; }   // new item: refresh the shared part
+                    }
+                }
+                if (stale > 0) {                        // new item: refresh the part all its agents share
+#pragma unroll
+                    for (int it = 0; it < kObsPasses; it++) {
+                        const int c = it * 32 + lane;
+                        if (c < kViewCells) { row[c * kChan + 3] = mini_own[c]; row[c * kChan + 6] = mini_oth[c]; }
                     }
                 }
                 // self marker in BOTH minimap channels (GridWorld.cc:396-408): move it
@@ -658,7 +665,12 @@ k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO i
             stale--;
             fence_proxy_async_smem();   // make the generic-proxy smem writes visible to the async proxy
             __syncthreads();
-            if (tid == 0) {
+            if (io.debug & 2) {   // experiment: plain 16-byte stores by all threads instead of the TMA bulk store
+                const uint32_t n16 = ((uint32_t)cn * kViewRow * 4 + 15u) >> 4;
+                const uint4 *src = (const uint4 *)(buf ? s_stage1 : s_stage0);
+                uint4 *dst = (uint4 *)(vout + (size_t)c0 * kViewRow);
+                for (uint32_t i = tid; i < n16; i += kObsThreads) __stcs(dst + i, src[i]);
+            } else if (tid == 0) {
                 // rows are 4732 B (= 12 mod 16): a ragged tail is rounded up to 16 B; the <= 12 spill bytes land
                 // in the next, unused row of the same [cap] block (cap is a multiple of 4, see engine.cu)
                 const uint32_t bytes = ((uint32_t)cn * kViewRow * 4 + 15u) & ~15u;

@@ -27,6 +27,7 @@ constexpr int kGroups = 2;
 constexpr int kMaxMoves = 32;    // |move range| (13 for speed 2)
 constexpr int kMaxAttacks = 32;  // |attack range| (8 for radius 1.5)
 constexpr int kMaxActions = 64;
+constexpr int kObsDiscSlots = 128;   // 4 passes x 32 lanes cover the <= 113 in-disc cells of the 13x13 window
 // battle observation geometry (view disc radius 6 -> 13x13 window, 1 wall + 2 x (has, hp, minimap) channels)
 constexpr int kView = 13, kViewCells = 169, kChan = 7, kViewRow = kViewCells * kChan;   // 1183 floats
 
@@ -65,6 +66,8 @@ struct BattleParams {
     int8_t move_dx[kMaxMoves], move_dy[kMaxMoves];
     int8_t att_dx[kMaxAttacks], att_dy[kMaxAttacks];
     uint32_t disc[8];       // view disc mask, bit c of word c/32 for view cell c = vy*view + vx
+    uint8_t obs_cell[kObsDiscSlots];   // k_obs lane schedule: slot p*32 + lane -> in-disc view cell (255 = idle), chosen
+                                       // so that the cells of one pass fall into distinct shared-memory banks when possible
 };
 
 struct BattleState {   // device pointers

@@ -98,6 +98,26 @@ Engine::Engine(const EngineConfig &cfg) : cfg_(cfg) {
     memset(P_.disc, 0, sizeof(P_.disc));
     for (int c = 0; c < kViewCells; c++)
         if (view_.in[c]) P_.disc[c >> 5] |= 1u << (c & 31);
+    {   // lane schedule of k_obs: only in-disc cells are ever rewritten (the others stay 0 in the staging rows).  A cell's
+        // channel-j store goes to bank (7 c + j) mod 32, so two cells of one pass collide iff they agree mod 32:
+        // give every cell the first pass in which its residue is still free (falling back to any free slot).
+        memset(P_.obs_cell, 255, sizeof(P_.obs_cell));
+        const int passes = kObsDiscSlots / 32;
+        std::vector<int> left;
+        for (int c = 0; c < kViewCells; c++) {
+            if (!view_.in[c]) continue;
+            bool placed = false;
+            for (int p = 0; p < passes && !placed; p++)
+                if (P_.obs_cell[p * 32 + (c & 31)] == 255) { P_.obs_cell[p * 32 + (c & 31)] = (uint8_t)c; placed = true; }
+            if (!placed) left.push_back(c);
+        }
+        for (int c : left) {
+            int slot = -1;
+            for (int s = 0; s < kObsDiscSlots && slot < 0; s++) if (P_.obs_cell[s] == 255) slot = s;
+            if (slot < 0) throw Fatal("view disc has more than 128 cells: k_obs lane schedule too small");
+            P_.obs_cell[slot] = (uint8_t)c;
+        }
+    }
 
     // cap-independent per-env arrays
     const size_t E = (size_t)P_.E;

@@ -14,7 +14,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import tools
-from .base import _dense, as_tensor, checkpoint_path
+from .base import _dense, as_tensor, checkpoint_path, sync_gradients
 from .replay_device import DeviceEpisodesBuffer, segmented_discounted_returns
 
 
@@ -82,6 +82,7 @@ class _ActorCriticBase:
         self.optimizer = torch.optim.Adam(self.net.parameters(), lr=learning_rate)
         self.replay_buffer = tools.EpisodesBuffer(use_mean=self.use_mf)
         self.device_replay = None
+        self.grad_sync = False        # True: average gradients over the torch.distributed ranks before every step
         self._stage_cfg = (stage_rows, sub_len)
         self.generator = torch.Generator(device=self.device)
         if seed is not None:
@@ -148,6 +149,8 @@ class _ActorCriticBase:
         pg_loss, vf_loss, neg_entropy, value = self.losses(view, feature, action, ret, prob)
         self.optimizer.zero_grad(set_to_none=True)
         (pg_loss + vf_loss + neg_entropy).backward()
+        if self.grad_sync:
+            sync_gradients(self.net.parameters())
         self.optimizer.step()
         return float(pg_loss), float(vf_loss), float(neg_entropy), float(value.mean())
 

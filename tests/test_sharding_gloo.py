@@ -68,3 +68,54 @@ def test_reference_arm_only_rank0_reports(tmp_path):
     r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "3",
                         "--warmup", "3"], env=env, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def _grad_worker(rank, world, port, out):
+    """two ranks train the same MF-Q net on different halves of a batch with grad_sync: identical parameters after
+    the step, and equal to one process stepping on the whole batch (masked-mean loss, equal mask counts)."""
+    import numpy as np
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mfmarl_b200.algo import MFQ
+    from mfmarl_b200.algo.base import ValueNet
+
+    class Spaces:
+        def get_view_space(self, h): return (13, 13, 7)
+        def get_feature_space(self, h): return (34,)
+        def get_action_space(self, h): return (21,)
+
+    torch.manual_seed(0)
+    m = MFQ("m", 0, Spaces(), 10, device="cpu")
+    m.grad_sync = True
+    rng = np.random.RandomState(0)
+    n = 16
+    view, feat = rng.rand(n, 13, 13, 7).astype(np.float32), rng.rand(n, 34).astype(np.float32)
+    prob = rng.dirichlet(np.ones(21), size=n).astype(np.float32)
+    acts, tq = rng.randint(0, 21, n).astype(np.int32), rng.randn(n).astype(np.float32)
+    masks = np.ones(n, bool)
+    sl = slice(rank * n // world, (rank + 1) * n // world)
+    ValueNet.train(m, state=[view[sl], feat[sl]], target_q=tq[sl], prob=prob[sl], acts=acts[sl], masks=masks[sl])
+    flat = torch.cat([p.detach().reshape(-1) for p in m.eval_net.parameters()])
+    gathered = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    if rank == 0:
+        torch.manual_seed(0)
+        solo = MFQ("s", 0, Spaces(), 10, device="cpu")
+        ValueNet.train(solo, state=[view, feat], target_q=tq, prob=prob, acts=acts, masks=masks)
+        ref = torch.cat([p.detach().reshape(-1) for p in solo.eval_net.parameters()])
+        out.put((bool(torch.equal(gathered[0], gathered[1])), float((gathered[0] - ref).abs().max())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_optional_gradient_allreduce_matches_single_process_training():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_grad_worker, args=(r, world, port, out)) for r in range(world)]
+    [p.start() for p in procs]
+    same, err = out.get(timeout=180)
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert same                      # both ranks hold the same parameters after the synchronised step
+    assert err < 2e-6                # ... and they are the single-process result on the whole batch (Adam step 1e-4)
