@@ -467,8 +467,12 @@ __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState
 // The map is never re-read from HBM: occupancy/hp grid and both minimaps are rebuilt per CTA from the
 // SoA agent arrays.
 // ----------------------------------------------------------------------------------------------
-constexpr int kObsThreads = 256, kObsWarps = kObsThreads / 32;
-constexpr int kObsChunk = 8;                                   // agents per bulk store (multiple of 4)
+#ifndef MF_OBS_CHUNK
+#define MF_OBS_CHUNK 8
+#endif
+constexpr int kObsChunk = MF_OBS_CHUNK;                        // agents per bulk store (multiple of 4) = warps per CTA
+constexpr int kObsThreads = 32 * kObsChunk, kObsWarps = kObsThreads / 32;
+constexpr int kObsCtasPerSm = 16 / kObsChunk;                  // resident CTAs per SM the kernel is tuned for
 constexpr int kObsStageBytes = kObsChunk * kViewRow * 4;       // 37 856, a multiple of 16
 constexpr int kObsPasses = (kViewCells + 31) / 32;             // 6
 static_assert(kObsChunk == kObsWarps, "one warp composes one row of a chunk");
@@ -509,7 +513,7 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 // cell kinds in the CTA-local grid, relative to the observing group
 enum : uint32_t { KIND_EMPTY = 0, KIND_WALL = 1, KIND_OWN = 2, KIND_OTHER = 3 };
 
-__global__ void __launch_bounds__(kObsThreads, 2)
+__global__ void __launch_bounds__(kObsThreads, kObsCtasPerSm)
 k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO io) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const ObsSmem L = obs_smem_layout(P.W, P.H, P.cap);
@@ -547,7 +551,21 @@ k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO i
     int buf = 0;
     const int groups_per_env = io.group_mask == 3 ? 2 : 1;
     const int n_items = P.E * groups_per_env * io.tiles_per_group;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    // Work distribution is DYNAMIC: a CTA takes its next item from a global ticket counter.  With a static split the
+    // kernel ends when the slowest SM ends, and SMs do not drain stores at the same rate (GPCs of 16-20 SMs share
+    // their path to L2): measured with the bare store loop (profiles/tma_store_probe.cu), 2.55 GB of 37 856-byte
+    // bulk stores take 0.402 ms split statically over the CTAs and 0.346 ms handed out 8 chunks per ticket.
+    // The ticket of the NEXT item is requested at the start of the current one, so its latency is never waited for;
+    // the last CTA to finish rewinds the counters for the next launch.
+    __shared__ int s_next;
+    if (tid == 0) s_next = atomicAdd(&S.obs_ticket[0], 1);
+    for (;;) {
+        __syncthreads();                                  // s_next is set; every warp is done with the previous item
+        const int item = s_next;
+        __syncthreads();                                  // ... and has read it before thread 0 replaces it
+        if (item >= n_items) break;
+        int next_ticket = 0;
+        if (tid == 0) next_ticket = atomicAdd(&S.obs_ticket[0], 1);
         int t = item;
         const int tile = t % io.tiles_per_group; t /= io.tiles_per_group;
         int g, e;
@@ -555,13 +573,15 @@ k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO i
         const int n0 = S.num[e * 2], n1 = S.num[e * 2 + 1];
         const int ng = g ? n1 : n0;
         const int a_begin = tile * io.tile_agents;
-        if (a_begin >= ng) continue;                      // uniform across the CTA
+        if (a_begin >= ng) {                              // nothing to do (uniform across the CTA)
+            if (tid == 0) s_next = next_ticket;
+            continue;
+        }
         const int a_end = min(ng, a_begin + io.tile_agents);
         const size_t ebase = (size_t)e * 2 * cap;
         const size_t gbase = ebase + (size_t)g * cap;
 
         // ---- padded occupancy grid (kind << 14 | slot per cell), hp/10 per slot, minimap counts ----
-        __syncthreads();                                  // every warp is done reading the previous item's grid
         {
             const uint4 *tmpl = (const uint4 *)S.grid_template;   // padded grid with the walls, built at commit
             for (int c = tid; c < (pcells * 2 + 15) / 16; c += kObsThreads) ((uint4 *)s_code)[c] = tmpl[c];
@@ -665,12 +685,7 @@ k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO i
             stale--;
             fence_proxy_async_smem();   // make the generic-proxy smem writes visible to the async proxy
             __syncthreads();
-            if (io.debug & 2) {   // experiment: plain 16-byte stores by all threads instead of the TMA bulk store
-                const uint32_t n16 = ((uint32_t)cn * kViewRow * 4 + 15u) >> 4;
-                const uint4 *src = (const uint4 *)(buf ? s_stage1 : s_stage0);
-                uint4 *dst = (uint4 *)(vout + (size_t)c0 * kViewRow);
-                for (uint32_t i = tid; i < n16; i += kObsThreads) __stcs(dst + i, src[i]);
-            } else if (tid == 0) {
+            if (tid == 0) {
                 // rows are 4732 B (= 12 mod 16): a ragged tail is rounded up to 16 B; the <= 12 spill bytes land
                 // in the next, unused row of the same [cap] block (cap is a multiple of 4, see engine.cu)
                 const uint32_t bytes = ((uint32_t)cn * kViewRow * 4 + 15u) & ~15u;
@@ -678,8 +693,12 @@ k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO i
                 bulk_commit();
             }
         }
+        if (tid == 0) s_next = next_ticket;
     }
-    if (tid == 0) bulk_wait<0>();
+    if (tid == 0) {
+        bulk_wait<0>();
+        if (atomicAdd(&S.obs_ticket[1], 1) == (int)gridDim.x - 1) { S.obs_ticket[0] = 0; S.obs_ticket[1] = 0; }
+    }
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -77,6 +77,7 @@ struct BattleState {   // device pointers
     uint16_t *grid_template;           // [(H+12)*(W+12)] padded occupancy grid holding only the walls (kind << 14)
     uint8_t *mini_lut;                 // [W] x / scale_w, then [H] (y / scale_h) * view: minimap cell of a position
     unsigned long long *agent_steps;   // [E] running count of agents taken through a step (statistic)
+    int32_t *obs_ticket;               // [2] k_obs work distribution: next item, CTAs finished (rewound by the last CTA)
     // episode template for auto-reset
     int32_t *init_pos; int32_t *init_num;   // [2][cap], [2]
 };

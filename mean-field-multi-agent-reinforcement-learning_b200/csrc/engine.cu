@@ -139,6 +139,8 @@ Engine::Engine(const EngineConfig &cfg) : cfg_(cfg) {
     }
     MF_CUDA(cudaMalloc(&S_.agent_steps, E * sizeof(unsigned long long)));
     MF_CUDA(cudaMemset(S_.agent_steps, 0, E * sizeof(unsigned long long)));
+    MF_CUDA(cudaMalloc(&S_.obs_ticket, 2 * sizeof(int32_t)));
+    MF_CUDA(cudaMemset(S_.obs_ticket, 0, 2 * sizeof(int32_t)));
     MF_CUDA(cudaMemset(S_.num, 0, E * 2 * sizeof(int32_t)));
     MF_CUDA(cudaMemset(S_.dead_ct, 0, E * 2 * sizeof(int32_t)));
     MF_CUDA(cudaMemset(S_.step_ct, 0, E * sizeof(int32_t)));
@@ -152,7 +154,7 @@ Engine::Engine(const EngineConfig &cfg) : cfg_(cfg) {
 Engine::~Engine() {
     free_state();
     cudaFree(S_.num); cudaFree(S_.dead_ct); cudaFree(S_.rng); cudaFree(S_.step_ct);
-    cudaFree(S_.id_counter); cudaFree(S_.walls); cudaFree(S_.init_num); cudaFree(S_.agent_steps); cudaFree(S_.mini_lut); cudaFree(S_.grid_template);
+    cudaFree(S_.id_counter); cudaFree(S_.walls); cudaFree(S_.init_num); cudaFree(S_.agent_steps); cudaFree(S_.obs_ticket); cudaFree(S_.mini_lut); cudaFree(S_.grid_template);
 }
 
 size_t Engine::grid_template_bytes() const {
@@ -399,7 +401,9 @@ void Engine::observe_groups(float *const d_view[kGroups], float *const d_feature
     }
     // persistent CTAs: two per SM (shared-memory bound), each loops over (env, group, tile) work items
     const size_t items = (size_t)P_.E * (group_mask == 3 ? 2 : 1) * io.tiles_per_group;
-    const unsigned grid = (unsigned)std::min<size_t>(items, (size_t)2 * n_sm_);
+    int ctas_per_sm = 0;
+    MF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_obs, kObsThreads, L.total));
+    const unsigned grid = (unsigned)std::min<size_t>(items, (size_t)std::max(1, ctas_per_sm) * n_sm_);
     k_obs<<<grid, kObsThreads, L.total, st>>>(P_, S_, io);
     MF_CUDA(cudaGetLastError());
 }
