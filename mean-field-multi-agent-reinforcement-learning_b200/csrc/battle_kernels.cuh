@@ -479,8 +479,11 @@ static_assert(kObsChunk == kObsWarps, "one warp composes one row of a chunk");
 
 constexpr int kPad = kView / 2;   // the smem grid carries a 6-cell empty margin: view windows never need a bounds test
 
-struct ObsSmem { int stage0, stage1, rec, hp10, mini, cnt, code, total; };
-constexpr int kObsMaxTile = 256;   // agents per CTA tile, upper bound (record staging)
+struct ObsSmem { int stage0, stage1, rec, hp10, mini, cnt, code, fxy, tmpl, total; };
+constexpr int kObsMaxTile = kObsThreads;   // agents per CTA tile, upper bound (one record per thread)
+// The pristine wall template is kept in shared memory when two CTAs per SM still fit with it (40x40: +5.4 KB);
+// larger maps copy it from global memory (L2) per item instead.
+__host__ __device__ inline bool obs_template_in_smem(int W, int H) { return (W + 2 * kPad) * (H + 2 * kPad) * 2 <= 8 * 1024; }
 __host__ __device__ inline ObsSmem obs_smem_layout(int W, int H, int cap) {
     ObsSmem L; int o = 0;
     L.stage0 = o; o += kObsStageBytes;
@@ -490,6 +493,9 @@ __host__ __device__ inline ObsSmem obs_smem_layout(int W, int H, int cap) {
     L.mini = o;   o += 4 * 2 * kViewCells;
     L.cnt = o;    o += 4 * 2 * kViewCells;
     L.code = o;   o += (2 * (W + 2 * kPad) * (H + 2 * kPad) + 3) & ~3;  // u16 per padded cell: kind << 14 | slot
+    L.fxy = o;    o += 4 * (W + H);                                    // x / W and y / H as tables (features 32, 33)
+    o = (o + 15) & ~15;
+    L.tmpl = o;   if (obs_template_in_smem(W, H)) o += (2 * (W + 2 * kPad) * (H + 2 * kPad) + 15) & ~15;
     L.total = (o + 127) & ~127;
     return L;
 }
@@ -523,6 +529,9 @@ k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO i
     float *s_mini = (float *)(smem_raw + L.mini);
     int *s_cnt = (int *)(smem_raw + L.cnt);
     uint16_t *s_code = (uint16_t *)(smem_raw + L.code);
+    float *s_fxy = (float *)(smem_raw + L.fxy);
+    const bool tmpl_smem = obs_template_in_smem(P.W, P.H);
+    const uint4 *s_tmpl = tmpl_smem ? (const uint4 *)(smem_raw + L.tmpl) : (const uint4 *)S.grid_template;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = P.W, H = P.H, cap = P.cap;
@@ -544,6 +553,11 @@ k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO i
     // cells outside the view disc never carry occupancy: their five occupancy channels are zeroed once here and
     // never written again (the minimap channels of all 169 cells are refreshed per item below)
     for (int i = tid; i < 2 * kObsStageBytes / 16; i += kObsThreads) ((uint4 *)s_stage0)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (tmpl_smem)
+        for (int c = tid; c < (pcells * 2 + 15) / 16; c += kObsThreads)   // padded grid with the walls, built at commit
+            ((uint4 *)(smem_raw + L.tmpl))[c] = ((const uint4 *)S.grid_template)[c];
+    for (int i = tid; i < W + H; i += kObsThreads)       // GridWorld.cc:419-420, the same IEEE divisions done once
+        s_fxy[i] = i < W ? __fdiv_rn((float)i, (float)W) : __fdiv_rn((float)(i - W), (float)H);
 
     // Persistent CTAs: each loops over work items (env, group, tile).  The bulk stores are asynchronous, so
     // the grid rebuild of the next item overlaps the drain of this item's last chunks, and the staging-buffer
@@ -570,37 +584,42 @@ k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO i
         const int tile = t % io.tiles_per_group; t /= io.tiles_per_group;
         int g, e;
         if (io.group_mask == 3) { g = t & 1; e = t >> 1; } else { g = io.group_mask >> 1; e = t; }
-        const int n0 = S.num[e * 2], n1 = S.num[e * 2 + 1];
-        const int ng = g ? n1 : n0;
+        // Every global read of the item is issued here, up front and independent of the others (none waits for
+        // `num`): slot state for the occupancy grid and the minimaps, and the tile's agent records.  One memory
+        // round trip per item instead of four dependent ones.
+        const size_t ebase = (size_t)e * 2 * cap;
+        const size_t gbase = ebase + (size_t)g * cap;
         const int a_begin = tile * io.tile_agents;
+        const int n0 = S.num[e * 2], n1 = S.num[e * 2 + 1];
+        int slot_pos = 0; uint32_t slot_state = 1u; float slot_hp = 0.0f;          // slot `tid` of the env (both groups)
+        if (tid < 2 * cap) { slot_pos = S.pos[ebase + tid]; slot_state = S.state[ebase + tid]; slot_hp = S.hp[ebase + tid]; }
+        int4 my_rec = make_int4(0, 0, 0, 0);                                       // agent a_begin + tid of the tile
+        if (tid < io.tile_agents && a_begin + tid < cap) {
+            const size_t s = gbase + a_begin + tid;
+            my_rec = make_int4(S.pos[s], S.id[s], (int)S.state[s], __float_as_int(S.last_rew[s]));
+        }
+        const int ng = g ? n1 : n0;
         if (a_begin >= ng) {                              // nothing to do (uniform across the CTA)
             if (tid == 0) s_next = next_ticket;
             continue;
         }
         const int a_end = min(ng, a_begin + io.tile_agents);
-        const size_t ebase = (size_t)e * 2 * cap;
-        const size_t gbase = ebase + (size_t)g * cap;
 
         // ---- padded occupancy grid (kind << 14 | slot per cell), hp/10 per slot, minimap counts ----
-        {
-            const uint4 *tmpl = (const uint4 *)S.grid_template;   // padded grid with the walls, built at commit
-            for (int c = tid; c < (pcells * 2 + 15) / 16; c += kObsThreads) ((uint4 *)s_code)[c] = tmpl[c];
-        }
+        for (int c = tid; c < (pcells * 2 + 15) / 16; c += kObsThreads) ((uint4 *)s_code)[c] = s_tmpl[c];
         for (int c = tid; c < 2 * kViewCells; c += kObsThreads) s_cnt[c] = 0;
-        for (int a = tid; a < a_end - a_begin; a += kObsThreads) {   // the tile's agent records
-            const size_t s = gbase + a_begin + a;
-            s_rec[a] = make_int4(S.pos[s], S.id[s], (int)S.state[s], __float_as_int(S.last_rew[s]));
-        }
+        if (tid < a_end - a_begin) s_rec[tid] = my_rec;
         __syncthreads();
         for (int s = tid; s < 2 * cap; s += kObsThreads) {
             const int gg = s >= cap, i = s - gg * cap;
             if (i < (gg ? n1 : n0)) {
-                const int p = S.pos[ebase + s], x = pos_x(p), y = pos_y(p);
+                const bool first = s == tid;              // the first 256 slots come from the registers loaded above
+                const int p = first ? slot_pos : S.pos[ebase + s], x = pos_x(p), y = pos_y(p);
                 // minimap counts every agent still in the list, dead or not (GridWorld.cc:359-370)
                 atomicAdd(&s_cnt[gg * kViewCells + lut[W + y] + lut[x]], 1);
-                if (!st_dead(S.state[ebase + s])) {
+                if (!st_dead(first ? slot_state : S.state[ebase + s])) {
                     s_code[(y + kPad) * PW + x + kPad] = (uint16_t)(((gg == g ? KIND_OWN : KIND_OTHER) << 14) | s);
-                    s_hp10[s] = __fdiv_rn(S.hp[ebase + s], P.hp);       // Map.cc:208
+                    s_hp10[s] = __fdiv_rn(first ? slot_hp : S.hp[ebase + s], P.hp);       // Map.cc:208
                 }
             }
         }
@@ -670,7 +689,7 @@ k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO i
                     row[self_new * kChan + 6] = mini_oth[self_new] + 1.0f;
                 }
                 // features (GridWorld.cc:411-421): id bits LSB first, one-hot last action, last reward, x/W, y/H
-                const float fx = __fdiv_rn((float)ax, (float)W), fy = __fdiv_rn((float)ay, (float)H);
+                const float fx = s_fxy[ax], fy = s_fxy[W + ay];
                 const int act = (int)st_act(st);
                 float *f = fout + (size_t)(c0 + warp) * FS;
                 for (int k = lane; k < FS; k += 32) {
