@@ -8,7 +8,9 @@ the dominant kernel and the reference CPU engine timed beside it.
 Workload (BASELINE.json configs[2], "C3"): 40x40 battle, 64 v 64 agents, 4096 lock-stepped environments per
 GPU, synthetic uniform-random actions, episodes auto-reset at done / 400 steps.  One "step" = one lockstep
 pass of the hot path over all environments of the GPU: k_obs (both groups' views + features) then k_step
-(set_action x2, step, reward, alive, mean action, clear_dead).  Unit of work: agent-step.
+(set_action x2, step, reward, alive, mean action, clear_dead).  By default the GPU's environments are split into
+two engines on two streams (--pipeline 2), so that one half's latency-bound k_step runs under the other half's
+bandwidth-bound k_obs -- what a double-buffered actor loop does.  Unit of work: agent-step.
 Inputs (actions) are resident in HBM for `value`; `e2e` feeds them from pinned host memory every step and
 reads rewards / alive / done / mean actions back to the host inside the timed region.
 """
@@ -276,6 +278,24 @@ def run_ours(args):
     obs_ms = sum(e[0].elapsed_time(e[1]) for evh in ev for e in evh) / (K * P)     # per k_obs launch
     step_ms = sum(e[1].elapsed_time(e[2]) for evh in ev for e in evh) / (K * P)    # per k_step launch
 
+    # ---- attribution: with P > 1 the two kernels of different engines overlap, so the event pairs above contain
+    #      the time a kernel shared the GPU with the other one.  A short extra run with the launches back to back on
+    #      ONE stream gives each kernel's duration alone (what the ncu launch list also shows). ----
+    alone = None
+    if P > 1:
+        n_alone = min(K, 20)
+        as_a = agent_steps_total()
+        eva = [[[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_alone)] for _ in range(P)]
+        barrier()
+        for k in range(n_alone):
+            for h, env in enumerate(envs):
+                eva[h][k][0].record(); env.observe(); eva[h][k][1].record()
+                env.step(pool[h][k % POOL]); eva[h][k][2].record()
+        barrier()
+        alone = {"k_obs": sum(e[0].elapsed_time(e[1]) for evh in eva for e in evh) / (n_alone * P),
+                 "k_step": sum(e[1].elapsed_time(e[2]) for evh in eva for e in evh) / (n_alone * P),
+                 "agents_per_launch": (agent_steps_total() - as_a) / (n_alone * P), "launches": n_alone * P}
+
     # ---- e2e: actions from pinned host memory each step, results read back to pinned host memory each step.
     #      Pipelined like an actor loop: the upload of step t and the download of step t-1 ride on copy
     #      streams under k_obs; a step's results are consumed (waited for) before its buffers are reused ----
@@ -372,11 +392,22 @@ def run_ours(args):
                        "sharding": "envs [r*E,(r+1)*E) on rank r, no collective on the env path",
                        "pipeline": "%d engine(s) x %d envs on %d stream(s)" % (P, Eh, P)},
             "gpu_launches": 2 * K * P,
-            "kernels_ms": {"k_obs": obs_ms, "k_step": step_ms},
+            "kernels_ms": {"k_obs": obs_ms, "k_step": step_ms,
+                           "note": "event pairs on the launching streams inside the timed region" +
+                                   ("; with %d streams they include time shared with the other engine's kernel" % P
+                                    if P > 1 else "")},
+            "kernels_alone_ms": alone,
             "roofline": {"bound": "hbm", "kernel": "k_obs", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
+                         "frac": achieved / peak,
+                         # per launch, like `achieved`: the ncu capture is one launch over the workload's full env count
+                         "traffic": (lambda t: None if t is None else t * Eh / wl["envs"])(ncu_traffic(args.workload)),
+                         "peak_source": peak_src,
                          "bytes_per_agent": BYTES_PER_AGENT_OBS, "agents_per_launch": agents_per_launch,
-                         "whole_step_frac": (agent_steps / K) * BYTES_PER_AGENT_STEP / (ms / K * 1e-3) / 1e9 / peak},
+                         "whole_step_frac": (agent_steps / K) * BYTES_PER_AGENT_STEP / (ms / K * 1e-3) / 1e9 / peak,
+                         "alone": None if alone is None else {
+                             "achieved": alone["agents_per_launch"] * BYTES_PER_AGENT_OBS / (alone["k_obs"] * 1e-3) / 1e9,
+                             "frac": alone["agents_per_launch"] * BYTES_PER_AGENT_OBS / (alone["k_obs"] * 1e-3) / 1e9 / peak,
+                             "note": "k_obs launched with nothing else on the GPU (short run after the timed region)"}},
             "e2e": {"value": e2e_all / (e2e_ms * 1e-3), "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h,
                     "note": "mfb_step_host_async: actions from pinned host memory, rewards/alive/done/mean action "
@@ -638,8 +669,9 @@ def main():
     ap.add_argument("--algo", default="mfq", choices=["mfq", "il", "mfac", "ac"], help="--workload play: the learner")
     ap.add_argument("--obs-to-host-steps", type=int, default=5,
                     help="extra e2e variant: steps timed with the observations copied to the host too (0 = skip)")
-    ap.add_argument("--pipeline", type=int, default=1,
-                    help="split the GPU's envs into this many engines on separate streams (k_step under k_obs)")
+    ap.add_argument("--pipeline", type=int, default=2,
+                    help="split the GPU's envs into this many engines on separate streams, so that the latency-bound "
+                         "k_step of one half runs under the bandwidth-bound k_obs of the other (1 = one engine, one stream)")
     ap.add_argument("--sweeps-per-launch", type=int, default=0,
                     help="c5: Ising sweeps per launch (1 = streaming kernel, >1 = shared-memory-resident kernel, 0 = auto)")
     ap.add_argument("--obs-tile", type=int, default=0, help="agents per k_obs CTA (tuning; 0 = engine default)")

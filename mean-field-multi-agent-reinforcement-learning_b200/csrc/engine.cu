@@ -389,21 +389,28 @@ void Engine::observe_groups(float *const d_view[kGroups], float *const d_feature
         if (((group_mask >> g) & 1) && ((uintptr_t)d_view[g] & 15)) throw Fatal("observe: view buffer must be 16-byte aligned");
     }
     io.env_stride = env_stride; io.group_mask = group_mask;
-    // tile: amortise the per-CTA grid rebuild over more agents when groups are large (measured: 256 at cap 512)
-    const int want_tile = cfg_.obs_tile_agents > 0 ? cfg_.obs_tile_agents : std::min(256, std::max(64, P_.cap));
-    io.tile_agents = std::min(kObsMaxTile, std::max(kObsChunk, round_up(want_tile, kObsChunk)));
-    io.tiles_per_group = (P_.cap + io.tile_agents - 1) / io.tile_agents;
     { const char *dbg = getenv("MFMARL_OBS_DEBUG"); io.debug = dbg ? atoi(dbg) : 0; }
     const ObsSmem L = obs_smem_layout(P_.W, P_.H, P_.cap);
     if (obs_attr_ != L.total) {
         MF_CUDA(cudaFuncSetAttribute(k_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        MF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&obs_ctas_per_sm_, k_obs, kObsThreads, L.total));
         obs_attr_ = L.total;
     }
-    // persistent CTAs: two per SM (shared-memory bound), each loops over (env, group, tile) work items
+    // persistent CTAs (two per SM, shared-memory bound) take (env, group, tile) work items from a ticket counter
+    const size_t ctas = (size_t)std::max(1, obs_ctas_per_sm_) * n_sm_;
+    // tile: a larger tile amortises the per-item grid rebuild over more agents (it matters when groups are large),
+    // but the items must stay numerous enough to balance over the CTAs: measured at cap 512 x 128 envs, 128-agent
+    // tiles (1024 items) beat 256 (512 items for 296 CTAs) and 64
+    int want_tile = cfg_.obs_tile_agents;
+    if (want_tile <= 0) {
+        want_tile = std::min(256, std::max(64, P_.cap));
+        const size_t groups = (size_t)P_.E * (group_mask == 3 ? 2 : 1);
+        while (want_tile > 128 && groups * ((P_.cap + want_tile - 1) / want_tile) < 3 * ctas) want_tile /= 2;
+    }
+    io.tile_agents = std::min(kObsMaxTile, std::max(kObsChunk, round_up(want_tile, kObsChunk)));
+    io.tiles_per_group = (P_.cap + io.tile_agents - 1) / io.tile_agents;
     const size_t items = (size_t)P_.E * (group_mask == 3 ? 2 : 1) * io.tiles_per_group;
-    int ctas_per_sm = 0;
-    MF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_obs, kObsThreads, L.total));
-    const unsigned grid = (unsigned)std::min<size_t>(items, (size_t)std::max(1, ctas_per_sm) * n_sm_);
+    const unsigned grid = (unsigned)std::min<size_t>(items, ctas);
     k_obs<<<grid, kObsThreads, L.total, st>>>(P_, S_, io);
     MF_CUDA(cudaGetLastError());
 }

@@ -1,10 +1,11 @@
 set -x
-timeout 900 python -m pytest tests/test_cuda_battle_abi.py tests/test_cuda_battle_batched.py tests/test_golden.py tests/test_play_loop.py -m gpu -x -q 2>&1 | tail -3
-for W in c3 c3 c4 c4; do
-python bench.py --no-cpu --obs-to-host-steps 0 --workload $W > gpurun_out/ab.json 2>/dev/null
-python -c "
-import json; d=json.loads(open('gpurun_out/ab.json').read().strip().splitlines()[-1]); print('$W', d['kernels_ms'], d['value'], d['roofline']['frac'], d['e2e']['value'])"
-done
-python bench.py --no-cpu --obs-to-host-steps 0 --workload c4 --obs-tile 128 > gpurun_out/ab.json 2>/dev/null
-python -c "
-import json; d=json.loads(open('gpurun_out/ab.json').read().strip().splitlines()[-1]); print('c4 tile 128', d['kernels_ms'], d['value'])"
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py > gpurun_out/bench_c3_v5.json 2> gpurun_out/bench_c3_v5.err; echo rc=$?
+python bench.py --pipeline 1 --no-cpu > gpurun_out/bench_c3_v5_p1.json 2> gpurun_out/bench_c3_v5_p1.err; echo rc=$?
+python bench.py --workload c4 --no-cpu --obs-to-host-steps 0 > gpurun_out/bench_c4_v5.json 2>gpurun_out/bench_c4_v5.err; echo rc=$?
+python bench.py --workload c4 --no-cpu --obs-to-host-steps 0 --pipeline 1 > gpurun_out/bench_c4_v5_p1.json 2>gpurun_out/bench_c4_v5_p1.err; echo rc=$?
+python - <<'PY'
+import json
+for f in ['bench_c3_v5','bench_c3_v5_p1','bench_c4_v5','bench_c4_v5_p1']:
+    d=json.loads(open('gpurun_out/%s.json'%f).read().strip().splitlines()[-1]); print(f, '%.4e'%d['value'], d['kernels_ms'], d.get('kernels_alone_ms'), d['roofline']['frac'], d['roofline'].get('alone'), '%.4e'%d['e2e']['value'])
+PY
