@@ -591,8 +591,14 @@ k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO i
         const size_t gbase = ebase + (size_t)g * cap;
         const int a_begin = tile * io.tile_agents;
         const int n0 = S.num[e * 2], n1 = S.num[e * 2 + 1];
-        int slot_pos = 0; uint32_t slot_state = 1u; float slot_hp = 0.0f;          // slot `tid` of the env (both groups)
-        if (tid < 2 * cap) { slot_pos = S.pos[ebase + tid]; slot_state = S.state[ebase + tid]; slot_hp = S.hp[ebase + tid]; }
+        constexpr int kPre = 4;                       // slots tid + j*256, j < 4, in registers (covers cap <= 512)
+        int slot_pos[kPre]; uint32_t slot_state[kPre]; float slot_hp[kPre];
+#pragma unroll
+        for (int j = 0; j < kPre; j++) {
+            const int s = tid + j * kObsThreads;
+            slot_pos[j] = 0; slot_state[j] = 1u; slot_hp[j] = 0.0f;
+            if (s < 2 * cap) { slot_pos[j] = S.pos[ebase + s]; slot_state[j] = S.state[ebase + s]; slot_hp[j] = S.hp[ebase + s]; }
+        }
         int4 my_rec = make_int4(0, 0, 0, 0);                                       // agent a_begin + tid of the tile
         if (tid < io.tile_agents && a_begin + tid < cap) {
             const size_t s = gbase + a_begin + tid;
@@ -610,19 +616,25 @@ k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO i
         for (int c = tid; c < 2 * kViewCells; c += kObsThreads) s_cnt[c] = 0;
         if (tid < a_end - a_begin) s_rec[tid] = my_rec;
         __syncthreads();
-        for (int s = tid; s < 2 * cap; s += kObsThreads) {
+        auto place = [&](int s, int p, uint32_t st, float hp) {
             const int gg = s >= cap, i = s - gg * cap;
             if (i < (gg ? n1 : n0)) {
-                const bool first = s == tid;              // the first 256 slots come from the registers loaded above
-                const int p = first ? slot_pos : S.pos[ebase + s], x = pos_x(p), y = pos_y(p);
+                const int x = pos_x(p), y = pos_y(p);
                 // minimap counts every agent still in the list, dead or not (GridWorld.cc:359-370)
                 atomicAdd(&s_cnt[gg * kViewCells + lut[W + y] + lut[x]], 1);
-                if (!st_dead(first ? slot_state : S.state[ebase + s])) {
+                if (!st_dead(st)) {
                     s_code[(y + kPad) * PW + x + kPad] = (uint16_t)(((gg == g ? KIND_OWN : KIND_OTHER) << 14) | s);
-                    s_hp10[s] = __fdiv_rn(first ? slot_hp : S.hp[ebase + s], P.hp);       // Map.cc:208
+                    s_hp10[s] = __fdiv_rn(hp, P.hp);       // Map.cc:208
                 }
             }
+        };
+#pragma unroll
+        for (int j = 0; j < kPre; j++) {
+            const int s = tid + j * kObsThreads;
+            if (s < 2 * cap) place(s, slot_pos[j], slot_state[j], slot_hp[j]);
         }
+        for (int s = tid + kPre * kObsThreads; s < 2 * cap; s += kObsThreads)      // cap > 512: the rest from global
+            place(s, S.pos[ebase + s], S.state[ebase + s], S.hp[ebase + s]);
         __syncthreads();
         for (int c = tid; c < 2 * kViewCells; c += kObsThreads) {
             const int gg = c >= kViewCells;
