@@ -491,7 +491,7 @@ def run_ising(args):
     # mfi_run; same bits as S streaming launches); S = 1 is the streaming kernel K6 (mfi_step), one launch per sweep.
     S = args.sweeps_per_launch
     if S == 0:
-        S = 25 if model.resident_cluster > 0 else 1
+        S = 100 if model.resident_cluster > 0 else 1
     S = max(1, min(S, K))
     while K % S:
         S -= 1                      # exactly K sweeps are timed

@@ -108,3 +108,31 @@ def test_injected_attack_order():
 
     st = run_lockstep(ora, cu, steps=150, seed=21, stream="fight", check_obs_every=10, on_step=inject)
     assert st["deaths"] > 10
+
+
+def test_global_minimap_and_getters_match_the_reference_engine():
+    """get_info keys the scripts can reach (GridWorld.cc:777-978): global_minimap, pos, id, alive, num -- CUDA engine
+    against the unmodified reference engine mid-fight (dead agents still in the lists)."""
+    from engines import RefEngine, have_ref
+    from scenarios import fight_actions
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    ref, cu = RefEngine(40), CudaEngine(40)
+    left, right = generate_map_positions(40)
+    for eng in (ref, cu):
+        eng.reset(); eng.add_agents(0, left); eng.add_agents(1, right)
+    rng = np.random.RandomState(3)
+    for s in range(40):
+        for g in range(2):
+            a = fight_actions(rng, ref.get_pos(g), 40)
+            ref.set_action(g, a); cu.set_action(g, a)
+        assert ref.step() == cu.step()
+        if s % 8 == 7:                      # between step and clear_dead: the dead are still listed
+            for hw in ((10, 10), (13, 13), (7, 5)):
+                a, b = ref.env.get_global_minimap(*hw), cu.env.get_global_minimap(*hw)
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (s, hw)
+            for g in range(2):
+                assert np.array_equal(ref.get_pos(g), cu.get_pos(g)) and np.array_equal(ref.get_agent_id(g), cu.get_agent_id(g))
+                assert np.array_equal(ref.get_alive(g), cu.get_alive(g)) and ref.get_num(g) == cu.get_num(g)
+        ref.clear_dead(); cu.clear_dead()
+    assert ref.get_num(0) + ref.get_num(1) < 128
