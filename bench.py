@@ -37,6 +37,8 @@ WORKLOADS = {
     "c4": dict(name="battle_80x80_512v512_128envs_per_gpu_uniform_actions (BASELINE configs[3] shard)",
                map_size=80, cap=512, envs=128, max_steps=400),
 }
+WORKLOADS["c2"] = dict(name="battle_40x40_64v64_single_env_through_the_reference_C_ABI (BASELINE configs[1])",
+                       map_size=40, cap=64, envs=1, max_steps=400)
 WORKLOADS["play"] = dict(name="battle_40x40_64v64_rollout_with_policy_networks (senario_battle.play, batched)",
                          map_size=40, cap=64, envs=1024, max_steps=400)
 WORKLOADS["c5"] = dict(name="ising_256x256_x16384_lattices_mfq_T0.8 (BASELINE configs[4])", side=256,
@@ -61,7 +63,11 @@ def cpu_worker(argv):
     import numpy as np
     from engines import OracleEngine, RefEngine
     from scenarios import c4_positions, generate_map_positions
-    eng = RefEngine(map_size) if kind == "reference" else OracleEngine(map_size)
+    if kind == "cuda":            # --workload c2: the product through the reference-facing single-env C ABI
+        from engines import CudaEngine
+        eng = CudaEngine(map_size)
+    else:
+        eng = RefEngine(map_size) if kind == "reference" else OracleEngine(map_size)
     left, right = generate_map_positions(40) if map_size == 40 else c4_positions()
     rng = np.random.RandomState(seed)
     eye = np.eye(21)
@@ -580,6 +586,32 @@ def run_ising(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# BASELINE configs[1]: ONE environment through the reference's own C ABI (host numpy buffers, every call synchronous)
+# ------------------------------------------------------------------------------------------------
+def run_single_env(args):
+    wl = WORKLOADS["c2"]
+    steps = max(200, args.steps * 10)
+    cmd = [sys.executable, os.path.abspath(__file__), "--_cpu_worker", "cuda", str(wl["map_size"]), "50", str(steps), "7"]
+    out = json.loads(subprocess.run(cmd, stdout=subprocess.PIPE, env=dict(os.environ, OMP_NUM_THREADS="1"))
+                     .stdout.decode().strip().splitlines()[-1])
+    v = out["agent_steps"] / out["seconds"]
+    line = {"metric": "battle agent-steps/sec incl. obs+mean-action, single env via the reference C ABI", "value": v,
+            "unit": "agent-steps/s", "n_gpus": 1, "steps": steps, "warmup": 50, "ms_per_step": out["seconds"] * 1e3 / steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"],
+                       "note": "magent.GridWorld over build/libmagent.so: get_observation x2 (device->host copies of the "
+                               "views), set_action x2, step, get_reward/get_alive x2, clear_dead; wall clock, every call "
+                               "synchronises.  A latency figure: one 64 v 64 env cannot fill a GPU."},
+            "e2e": {"value": v, "unit": "agent-steps/s", "h2d_bytes_per_step": 2 * wl["cap"] * 4,
+                    "d2h_bytes_per_step": 2 * wl["cap"] * (BYTES_PER_AGENT_OBS + 5)}}
+    if not args.no_cpu and os.path.exists(REF_SO):
+        rv, _total, secs = run_cpu("reference", wl["map_size"], 50, steps, 1)
+        line["cpu_baseline"] = {"value": rv, "unit": "agent-steps/s", "cores": 1, "kind": "reference",
+                                "sample": "the same loop on the reference engine, one process, %.1f s" % secs}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
 # rollout with the policy networks in the loop: an additional line, not the headline
 # ------------------------------------------------------------------------------------------------
 def run_play(args):
@@ -601,6 +633,12 @@ def run_play(args):
         def get_action_space(self, h): return (21,)
 
     models = [spawn_ai(args.algo, Spaces(), g, "%s-%d" % (args.algo, g), K, device=dev) for g in range(2)]
+    if args.policy_precision == "tf32":
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cudnn.allow_tf32 = True
+    elif args.policy_precision == "bf16":
+        for m in models:
+            m.act_autocast = torch.bfloat16
     play_batched(env, 0, max(3, args.warmup), models, eps=1.0, train=False, left_group=0)
     torch.cuda.synchronize()
     a0 = int(env.get("agent_steps").sum())
@@ -616,7 +654,7 @@ def run_play(args):
         "metric": "battle rollout agent-steps/sec incl. policy networks", "value": agent_steps / (ms * 1e-3),
         "unit": "agent-steps/s", "n_gpus": 1, "steps": K, "warmup": max(3, args.warmup), "ms_per_step": ms / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "envs_per_gpu": E, "algo": args.algo,
+        "config": {"workload": wl["name"], "envs_per_gpu": E, "algo": args.algo, "policy_precision": args.policy_precision,
                    "note": "play_batched: k_obs (per-group blocks) -> two PyTorch policy forwards on the observation "
                            "block in place -> k_step; nothing leaves the device except one `any(active)` flag per step"},
         "clocks": clocks.summary()}), flush=True)
@@ -676,6 +714,8 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=60000, help="timed steps per CPU-baseline worker")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--algo", default="mfq", choices=["mfq", "il", "mfac", "ac"], help="--workload play: the learner")
+    ap.add_argument("--policy-precision", default="fp32", choices=["fp32", "tf32", "bf16"],
+                    help="--workload play: precision of the rollout forward pass (training is always fp32)")
     ap.add_argument("--obs-to-host-steps", type=int, default=5,
                     help="extra e2e variant: steps timed with the observations copied to the host too (0 = skip)")
     ap.add_argument("--pipeline", type=int, default=2,
@@ -701,6 +741,8 @@ def main():
         return run_ising(args)
     if args.workload == "play":
         return run_play(args)
+    if args.workload == "c2":
+        return run_single_env(args)
     run_ours(args)
 
 

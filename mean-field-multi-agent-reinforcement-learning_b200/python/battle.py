@@ -1,6 +1,5 @@
 """Evaluation battles between two trained models -- the reference's battle.py with the same flags, over the CUDA
 engine and the PyTorch learners (checkpoints written by train_battle.py)."""
-import argparse
 import os
 import sys
 
@@ -10,25 +9,15 @@ BASE_DIR = os.path.dirname(os.path.abspath(__file__))
 
 
 def main(argv=None):
-    parser = argparse.ArgumentParser()
-    parser.add_argument('--algo', type=str, choices={'ac', 'mfac', 'mfq', 'il'}, required=True,
-                        help='choose an algorithm from the preset')
-    parser.add_argument('--oppo', type=str, choices={'ac', 'mfac', 'mfq', 'il'}, help='indicate the opponent model')
-    parser.add_argument('--n_round', type=int, default=50, help='set the trainning round')
-    parser.add_argument('--render', action='store_true', help='render or not (if true, will render every save)')
-    parser.add_argument('--map_size', type=int, default=40, help='set the size of map')
-    parser.add_argument('--max_steps', type=int, default=400, help='set the max steps')
-    parser.add_argument('--idx', nargs='*', required=True)
-    parser.add_argument('--device', type=str, default=None)
-    parser.add_argument('--data_dir', type=str, default=os.path.join(BASE_DIR, 'data'))
-    args = parser.parse_args(argv)
+    from mfmarl_b200.cli import battle_parser, data_dirs
+    args = battle_parser("evaluation battles between two trained models", training=False).parse_args(argv)
+    args.data_dir, render_dir = data_dirs(args, BASE_DIR)
 
     import magent
     from mfmarl_b200.algo import spawn_ai, tools
     from mfmarl_b200.senario_battle import battle
     env = magent.GridWorld('battle', map_size=args.map_size)
-    os.makedirs(os.path.join(args.data_dir, 'render'), exist_ok=True)
-    env.set_render_dir(os.path.join(args.data_dir, 'render'))
+    env.set_render_dir(render_dir)
     handles = env.get_handles()
     main_model_dir = os.path.join(args.data_dir, 'models/{}-0'.format(args.algo))
     oppo_model_dir = os.path.join(args.data_dir, 'models/{}-1'.format(args.oppo))

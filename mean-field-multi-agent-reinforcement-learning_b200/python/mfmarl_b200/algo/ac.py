@@ -83,6 +83,7 @@ class _ActorCriticBase:
         self.replay_buffer = tools.EpisodesBuffer(use_mean=self.use_mf)
         self.device_replay = None
         self.grad_sync = False        # True: average gradients over the torch.distributed ranks before every step
+        self.act_autocast = None      # e.g. torch.bfloat16: run the ROLLOUT forward (act) under autocast; training stays fp32
         self._stage_cfg = (stage_rows, sub_len)
         self.generator = torch.Generator(device=self.device)
         if seed is not None:
@@ -121,7 +122,12 @@ class _ActorCriticBase:
     def act(self, **kwargs):
         """multinomial(log policy) (ac.py:43-48, 70): numpy int32 for numpy inputs, a device tensor otherwise."""
         view, feature = kwargs['state'][0], kwargs['state'][1]
-        policy = self.net.policy(as_tensor(view, self.device), as_tensor(feature, self.device))
+        v, f = as_tensor(view, self.device), as_tensor(feature, self.device)
+        if self.act_autocast is not None and v.is_cuda:
+            with torch.autocast("cuda", dtype=self.act_autocast):
+                policy = self.net.policy(v, f).float()
+        else:
+            policy = self.net.policy(v, f)
         action = torch.multinomial(policy, 1, generator=self.generator).reshape(-1).to(torch.int32)
         return action if isinstance(view, torch.Tensor) else action.cpu().numpy()
 

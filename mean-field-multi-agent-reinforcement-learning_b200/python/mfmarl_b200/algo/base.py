@@ -96,6 +96,7 @@ class ValueNet:
         self.update_every, self.use_mf = update_every, use_mf
         self.temperature = 0.1
         self.grad_sync = False        # True: average gradients over the torch.distributed ranks before every step
+        self.act_autocast = None      # e.g. torch.bfloat16: run the ROLLOUT forward (act) under autocast; training stays fp32
         self.lr, self.tau, self.gamma = learning_rate, tau, gamma
         self.device = torch.device(device if device is not None else ("cuda" if torch.cuda.is_available() else "cpu"))
         self.eval_net = QNet(self.view_space, self.feature_space, self.num_actions, use_mf).to(self.device)
@@ -143,7 +144,12 @@ class ValueNet:
         v, f, p = self._inputs(view, feature, kwargs.get("prob"))
         if self.use_mf and not isinstance(kwargs["prob"], torch.Tensor):
             assert len(kwargs["prob"]) == len(view)
-        actions = self.eval_net(v, f, p).argmax(dim=1).to(torch.int32)
+        if self.act_autocast is not None and v.is_cuda:
+            with torch.autocast("cuda", dtype=self.act_autocast):
+                q = self.eval_net(v, f, p)
+        else:
+            q = self.eval_net(v, f, p)
+        actions = q.argmax(dim=1).to(torch.int32)
         return actions if isinstance(view, torch.Tensor) else actions.cpu().numpy()
 
     def train(self, **kwargs):

@@ -5,7 +5,6 @@ engine and the PyTorch learners.
     python train_battle.py --algo mfq --envs 1024       1024 lock-stepped environments on the GPU per round:
                                                          observations, mean actions and replay stay in HBM
 """
-import argparse
 import os
 import sys
 
@@ -54,19 +53,9 @@ class BatchedEnvAdapter:
 
 
 def main(argv=None):
-    parser = argparse.ArgumentParser()
-    parser.add_argument('--algo', type=str, choices={'ac', 'mfac', 'mfq', 'il'}, required=True,
-                        help='choose an algorithm from the preset')
-    parser.add_argument('--save_every', type=int, default=10, help='decide the self-play update interval')
-    parser.add_argument('--update_every', type=int, default=5, help='decide the udpate interval for q-learning, optional')
-    parser.add_argument('--n_round', type=int, default=2000, help='set the trainning round')
-    parser.add_argument('--render', action='store_true', help='render or not (if true, will render every save)')
-    parser.add_argument('--map_size', type=int, default=40, help='set the size of map')
-    parser.add_argument('--max_steps', type=int, default=400, help='set the max steps')
-    parser.add_argument('--envs', type=int, default=0, help='lock-stepped environments on the GPU (0 = one, via magent)')
-    parser.add_argument('--device', type=str, default=None)
-    parser.add_argument('--data_dir', type=str, default=os.path.join(BASE_DIR, 'data'))
-    args = parser.parse_args(argv)
+    from mfmarl_b200.cli import battle_parser, data_dirs
+    args = battle_parser("self-play training on the battle scenario", training=True).parse_args(argv)
+    args.data_dir, render_dir = data_dirs(args, BASE_DIR)
 
     from mfmarl_b200.algo import spawn_ai, tools
     log_dir = os.path.join(args.data_dir, 'tmp')
@@ -81,8 +70,7 @@ def main(argv=None):
         import magent
         from mfmarl_b200.senario_battle import play
         env = magent.GridWorld('battle', map_size=args.map_size)
-        os.makedirs(os.path.join(args.data_dir, 'render'), exist_ok=True)
-        env.set_render_dir(os.path.join(args.data_dir, 'render'))
+        env.set_render_dir(render_dir)
         handles = env.get_handles()
     models = [spawn_ai(args.algo, env, handles[0], args.algo + '-me', args.max_steps, device=args.device),
               spawn_ai(args.algo, env, handles[1], args.algo + '-opponent', args.max_steps, device=args.device)]

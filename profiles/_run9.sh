@@ -1,10 +1,7 @@
 set -x
-timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --workload c4 --no-cpu --obs-to-host-steps 0 > gpurun_out/bench_c4_v5.json 2>gpurun_out/bench_c4_v5.err; echo rc=$?
-python bench.py --workload c4 --no-cpu --obs-to-host-steps 0 --pipeline 1 > gpurun_out/bench_c4_v5_p1.json 2>gpurun_out/bench_c4_v5_p1.err; echo rc=$?
-python bench.py --no-cpu --obs-to-host-steps 0 --pipeline 1 > gpurun_out/bench_c3_v5_p1.json 2> gpurun_out/bench_c3_v5_p1.err; echo rc=$?
-python - <<'PY'
-import json
-for f in ['bench_c3_v5_p1','bench_c4_v5','bench_c4_v5_p1']:
-    d=json.loads(open('gpurun_out/%s.json'%f).read().strip().splitlines()[-1]); print(f, '%.4e'%d['value'], d['kernels_ms']['k_obs'], d['kernels_ms']['k_step'], d.get('kernels_alone_ms'), d['roofline']['frac'], '%.4e'%d['e2e']['value'])
-PY
+timeout 900 python -m pytest tests/test_algo_gpu.py tests/test_cuda_battle_abi.py -m gpu -x -q 2>&1 | tail -3
+python bench.py --workload c2 > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err; echo rc=$?; cut -c1-250 gpurun_out/bench_c2.json; tail -2 gpurun_out/bench_c2.err
+for PP in fp32 tf32 bf16; do
+python bench.py --workload play --algo mfq --steps 50 --envs 1024 --policy-precision $PP > gpurun_out/bench_play_mfq_$PP.json 2> gpurun_out/bench_play_mfq_$PP.err; echo rc=$?; cut -c1-160 gpurun_out/bench_play_mfq_$PP.json; tail -2 gpurun_out/bench_play_mfq_$PP.err
+done
+python bench.py --workload c5 > gpurun_out/bench_c5_default.json 2> gpurun_out/bench_c5_default.err; echo rc=$?; cut -c1-200 gpurun_out/bench_c5_default.json
