@@ -406,6 +406,8 @@ void Engine::observe_groups(float *const d_view[kGroups], float *const d_feature
         want_tile = std::min(256, std::max(64, P_.cap));
         const size_t groups = (size_t)P_.E * (group_mask == 3 ? 2 : 1);
         while (want_tile > 128 && groups * ((P_.cap + want_tile - 1) / want_tile) < 3 * ctas) want_tile /= 2;
+        // a handful of environments (the single-env ABI): latency, not throughput -- one chunk per CTA
+        while (want_tile > kObsChunk && groups * ((P_.cap + want_tile - 1) / want_tile) < ctas / 8) want_tile /= 2;
     }
     io.tile_agents = std::min(kObsMaxTile, std::max(kObsChunk, round_up(want_tile, kObsChunk)));
     io.tiles_per_group = (P_.cap + io.tile_agents - 1) / io.tile_agents;
@@ -423,6 +425,8 @@ void Engine::step(const StepIO &io, cudaStream_t st) {
         step_attr_ = L.total;
     }
     int threads = cfg_.step_threads > 0 ? cfg_.step_threads : std::min(1024, std::max(64, P_.cap));
+    // a few environments cannot fill the GPU anyway: wider CTAs shorten the parallel phases (grid load, lists, scans)
+    if (cfg_.step_threads <= 0 && P_.E <= n_sm_ / 2) threads = std::max(threads, 256);
     threads = round_up(threads, 32);
     k_step<<<P_.E, threads, L.total, st>>>(P_, S_, io);
     MF_CUDA(cudaGetLastError());

@@ -86,6 +86,8 @@ public:
     int n_envs() const { return P_.E; }
     int n_action() const { return P_.n_move + P_.n_attack; }
     int host_num(int env, int group) const { return h_num_[env * 2 + group]; }
+    // the caller already knows the counts after clear_dead (it holds the alive flags): no device round trip
+    void set_host_num(int env, int group, int n) { h_num_[env * 2 + group] = n; }
     bool placement_pending() const { return placement_dirty_; }
     size_t slots() const { return (size_t)P_.E * 2 * P_.cap; }
     const CircleRange &view_range() const { return view_; }

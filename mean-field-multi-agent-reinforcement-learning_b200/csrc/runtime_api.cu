@@ -58,6 +58,19 @@ struct Game {
     std::vector<int> seq;          // groups in set_action call order since the last step
     bool inject_next = false;
 
+    // Host mirror (pinned).  Every env_* call of the reference ABI is synchronous, so the cost of one environment
+    // is the number of stream synchronisations per step, not kernel time.  The mirror brings it from ~12 to 3:
+    //   * set_action only stages the actions on the host; env_step uploads both groups and runs set_action x2 + step
+    //     in ONE launch (if an observation or a getter is asked for in between, the staged actions are applied first);
+    //   * after step / clear_dead the agents' pos, id, state, hp and reward come back in one batch, and get_reward,
+    //     get_alive, get_pos, get_agent_id, mean_info, global_minimap and render answer from it;
+    //   * the first get_observation after a state change computes and downloads BOTH groups' rows.
+    char *pin = nullptr; int pin_cap = 0;
+    int32_t *m_pos = nullptr, *m_id = nullptr, *m_actions = nullptr; uint32_t *m_state = nullptr;
+    float *m_hp = nullptr, *m_rew = nullptr, *m_view = nullptr, *m_feat = nullptr;
+    bool state_fresh = false, obs_fresh = false;
+    unsigned pending_mask = 0;     // groups whose staged actions have not reached the device yet
+
     // render trace (RenderGenerator.cc): config.json once, then frames appended to video_<file_ct>.txt
     std::string render_dir;
     bool first_render = true;
@@ -67,6 +80,60 @@ struct Game {
 
     ~Game() {
         cudaFree(d_view); cudaFree(d_feat); cudaFree(d_actions); cudaFree(d_perm); cudaFree(d_done); cudaFree(d_events);
+        cudaFreeHost(pin);
+    }
+
+    void invalidate() { state_fresh = false; obs_fresh = false; }
+
+    void ensure_mirror() {
+        const int cap = engine().cap(), FS = engine().params().feature_size;
+        if (pin_cap >= cap) return;
+        std::vector<int32_t> keep(m_actions ? m_actions : nullptr, m_actions ? m_actions + 2 * pin_cap : nullptr);
+        const int old_cap = pin_cap;
+        cudaFreeHost(pin);
+        const size_t n = (size_t)2 * cap;
+        MF_CUDA(cudaMallocHost(&pin, n * 4 * 6 + n * (kViewRow + FS) * 4));
+        char *p = pin;
+        m_pos = (int32_t *)p; p += n * 4; m_id = (int32_t *)p; p += n * 4; m_state = (uint32_t *)p; p += n * 4;
+        m_hp = (float *)p; p += n * 4; m_rew = (float *)p; p += n * 4; m_actions = (int32_t *)p; p += n * 4;
+        m_view = (float *)p; p += n * kViewRow * 4; m_feat = (float *)p;
+        memset(m_actions, 0, n * 4);
+        for (int grp = 0; grp < 2 && old_cap > 0; grp++)      // staged actions survive a capacity growth
+            memcpy(m_actions + (size_t)grp * cap, keep.data() + (size_t)grp * old_cap, (size_t)old_cap * 4);
+        pin_cap = cap;
+        invalidate();
+    }
+
+    // staged set_action calls -> device (one SETACT launch); only needed when something looks at the state before step
+    void flush_actions() {
+        if (!pending_mask) return;
+        Engine &E = engine();
+        MF_CUDA(cudaMemcpyAsync(d_actions, m_actions, (size_t)2 * E.cap() * 4, cudaMemcpyHostToDevice, st));
+        StepIO io{};
+        io.actions = d_actions; io.phases = PH_SETACT; io.setact_mask = (int)pending_mask;
+        io.group_seq[0] = io.group_seq[1] = -1;
+        E.step(io, st);
+        pending_mask = 0;
+        invalidate();
+    }
+
+    void enqueue_state_download() {
+        Engine &E = engine();
+        const BattleState &S = E.state();
+        const size_t bytes = (size_t)2 * E.cap() * 4;
+        MF_CUDA(cudaMemcpyAsync(m_pos, S.pos, bytes, cudaMemcpyDeviceToHost, st));
+        MF_CUDA(cudaMemcpyAsync(m_id, S.id, bytes, cudaMemcpyDeviceToHost, st));
+        MF_CUDA(cudaMemcpyAsync(m_state, S.state, bytes, cudaMemcpyDeviceToHost, st));
+        MF_CUDA(cudaMemcpyAsync(m_hp, S.hp, bytes, cudaMemcpyDeviceToHost, st));
+        MF_CUDA(cudaMemcpyAsync(m_rew, S.next_rew, bytes, cudaMemcpyDeviceToHost, st));
+    }
+
+    void fetch_state() {
+        flush_actions();
+        if (state_fresh) return;
+        enqueue_state_download();
+        MF_CUDA(cudaStreamSynchronize(st));
+        state_fresh = true;
     }
 
     const TypeDef &type_of(int group) const {
@@ -125,6 +192,7 @@ struct Game {
 
     void ensure_staging() {
         Engine &E = engine();
+        if (E.placement_pending()) invalidate();
         E.commit(st);
         const int cap = E.cap();
         if (obs_cap < cap) {
@@ -141,6 +209,7 @@ struct Game {
             act_cap = cap;
         }
         if (!d_done) MF_CUDA(cudaMalloc(&d_done, 4));
+        ensure_mirror();
     }
 };
 
@@ -213,6 +282,7 @@ int env_reset(EnvHandle game) {
     g->ensure_engine();
     g->eng->reset();
     g->seq.clear();
+    g->pending_mask = 0; g->invalidate();
     g->file_ct++; g->frame_ct = 0;                        // RenderGenerator::next_file (GridWorld.cc:102)
     API_END("env_reset")
 }
@@ -223,14 +293,25 @@ int env_get_observation(EnvHandle game, GroupHandle group, float **buffer) {
     Engine &E = g->engine();
     g->type_of(group);
     g->ensure_staging();
+    g->flush_actions();                       // features carry the last action (GridWorld.cc:411-417)
     const int n = E.host_num(0, group), cap = E.cap(), FS = E.params().feature_size;
     if (n == 0) return 0;
-    E.observe(g->d_view, g->d_feat, 1 << group, g->st);
-    MF_CUDA(cudaMemcpyAsync(buffer[0], g->d_view + (size_t)group * cap * kViewRow, (size_t)n * kViewRow * 4,
-                            cudaMemcpyDeviceToHost, g->st));
-    MF_CUDA(cudaMemcpyAsync(buffer[1], g->d_feat + (size_t)group * cap * FS, (size_t)n * FS * 4,
-                            cudaMemcpyDeviceToHost, g->st));
-    MF_CUDA(cudaStreamSynchronize(g->st));
+    if (!g->obs_fresh) {                      // both groups in one launch, one batch of copies, one synchronisation
+        const int n0 = E.host_num(0, 0), n1 = E.host_num(0, 1);
+        E.observe(g->d_view, g->d_feat, (n0 > 0 ? 1 : 0) | (n1 > 0 ? 2 : 0), g->st);
+        for (int grp = 0; grp < 2; grp++) {
+            const int ng = grp ? n1 : n0;
+            if (ng == 0) continue;
+            MF_CUDA(cudaMemcpyAsync(g->m_view + (size_t)grp * cap * kViewRow, g->d_view + (size_t)grp * cap * kViewRow,
+                                    (size_t)ng * kViewRow * 4, cudaMemcpyDeviceToHost, g->st));
+            MF_CUDA(cudaMemcpyAsync(g->m_feat + (size_t)grp * cap * FS, g->d_feat + (size_t)grp * cap * FS,
+                                    (size_t)ng * FS * 4, cudaMemcpyDeviceToHost, g->st));
+        }
+        MF_CUDA(cudaStreamSynchronize(g->st));
+        g->obs_fresh = true;
+    }
+    memcpy(buffer[0], g->m_view + (size_t)group * cap * kViewRow, (size_t)n * kViewRow * 4);
+    memcpy(buffer[1], g->m_feat + (size_t)group * cap * FS, (size_t)n * FS * 4);
     API_END("env_get_observation")
 }
 
@@ -243,15 +324,10 @@ int env_set_action(EnvHandle game, GroupHandle group, const int *actions) {
     for (int s : g->seq)
         if (s == group) throw Fatal("set_action called twice for one group before step");
     const int n = E.host_num(0, group);
-    if (n > 0)
-        MF_CUDA(cudaMemcpyAsync(g->d_actions + (size_t)group * E.cap(), actions, (size_t)n * 4,
-                                cudaMemcpyHostToDevice, g->st));
-    StepIO io{};
-    io.actions = g->d_actions; io.phases = PH_SETACT; io.setact_mask = 1 << group;
-    io.group_seq[0] = io.group_seq[1] = -1;
-    E.step(io, g->st);
-    MF_CUDA(cudaStreamSynchronize(g->st));   // `actions` may be freed by the caller on return
+    if (n > 0) memcpy(g->m_actions + (size_t)group * E.cap(), actions, (size_t)n * 4);   // staged; applied by env_step
+    g->pending_mask |= 1u << group;
     g->seq.push_back(group);
+    g->invalidate();                          // last_action changes (features, mean_info)
     API_END("env_set_action")
 }
 
@@ -264,6 +340,11 @@ int env_step(EnvHandle game, int *done) {
     io.phases = PH_STEP; io.done = g->d_done; io.attack_perm = g->d_perm;
     io.group_seq[0] = g->seq.size() > 0 ? g->seq[0] : -1;
     io.group_seq[1] = g->seq.size() > 1 ? g->seq[1] : -1;
+    if (g->pending_mask) {                    // set_action(g0), set_action(g1) and step in one launch
+        MF_CUDA(cudaMemcpyAsync(g->d_actions, g->m_actions, (size_t)2 * E.cap() * 4, cudaMemcpyHostToDevice, g->st));
+        io.actions = g->d_actions; io.phases |= PH_SETACT; io.setact_mask = (int)g->pending_mask;
+        g->pending_mask = 0;
+    }
     if (g->inject_next) E.set_rng_mode(RNG_INJECT);
     const bool want_events = !g->first_render;            // GridWorld.cc:533,559: recorded once a frame was rendered
     if (want_events) {
@@ -284,7 +365,9 @@ int env_step(EnvHandle game, int *done) {
     if (g->inject_next) { E.set_rng_mode(RNG_MINSTD); g->inject_next = false; }
     int h_done = 0;
     MF_CUDA(cudaMemcpyAsync(&h_done, g->d_done, 4, cudaMemcpyDeviceToHost, g->st));
+    g->enqueue_state_download();              // rewards, alive flags, positions: what the caller asks for next
     MF_CUDA(cudaStreamSynchronize(g->st));
+    g->state_fresh = true; g->obs_fresh = false;
     *done = h_done;
     g->seq.clear();
     API_END("env_step")
@@ -297,12 +380,9 @@ int env_get_reward(EnvHandle game, GroupHandle group, float *buffer) {
     g->type_of(group);
     g->ensure_staging();
     const int n = E.host_num(0, group);
-    if (n > 0) {
-        MF_CUDA(cudaMemcpyAsync(buffer, E.state().next_rew + (size_t)group * E.cap(), (size_t)n * 4,
-                                cudaMemcpyDeviceToHost, g->st));
-        MF_CUDA(cudaStreamSynchronize(g->st));
-    }
-    for (int i = 0; i < n; i++) buffer[i] = buffer[i] + 0.0f;   // + Group::get_reward(), always 0 (GridWorld.cc:764-768)
+    g->fetch_state();
+    const float *rew = g->m_rew + (size_t)group * E.cap();
+    for (int i = 0; i < n; i++) buffer[i] = rew[i] + 0.0f;   // + Group::get_reward(), always 0 (GridWorld.cc:764-768)
     API_END("env_get_reward")
 }
 
@@ -366,7 +446,8 @@ int env_get_info(EnvHandle game, GroupHandle group, const char *name, void *void
         for (int i = 0; i < ng; i++) {
             const int channel = ((i - group + ng) % ng + ng) % ng;
             const int n = E.host_num(0, i);
-            const std::vector<int32_t> pos = pull(S.pos + (size_t)i * cap, n, g->st);
+            g->fetch_state();
+            const int32_t *pos = g->m_pos + (size_t)i * cap;
             for (int j = 0; j < n; j++)
                 fbuf[(((pos[j] >> 16) & 0xFFFF) / scale_h * vw + (pos[j] & 0xFFFF) / scale_w) * ng + channel] += 1.0f;
             for (int k = 0; k < vh * vw; k++) fbuf[k * ng + channel] /= (size_t)n;
@@ -379,17 +460,20 @@ int env_get_info(EnvHandle game, GroupHandle group, const char *name, void *void
     if (streq(name, "num")) {
         ibuf[0] = n;
     } else if (streq(name, "id")) {
-        if (n) { MF_CUDA(cudaMemcpyAsync(ibuf, S.id + (size_t)group * cap, (size_t)n * 4, cudaMemcpyDeviceToHost, g->st));
-                 MF_CUDA(cudaStreamSynchronize(g->st)); }
+        g->fetch_state();
+        memcpy(ibuf, g->m_id + (size_t)group * cap, (size_t)n * 4);
     } else if (streq(name, "pos")) {
-        const std::vector<int32_t> pos = pull(S.pos + (size_t)group * cap, n, g->st);
+        g->fetch_state();
+        const int32_t *pos = g->m_pos + (size_t)group * cap;
         for (int i = 0; i < n; i++) { ibuf[2 * i] = pos[i] & 0xFFFF; ibuf[2 * i + 1] = (pos[i] >> 16) & 0xFFFF; }
     } else if (streq(name, "alive")) {
-        const std::vector<uint32_t> st = pull(S.state + (size_t)group * cap, n, g->st);
+        g->fetch_state();
+        const uint32_t *st = g->m_state + (size_t)group * cap;
         for (int i = 0; i < n; i++) bbuf[i] = !(st[i] & 1u);
     } else if (streq(name, "mean_info")) {                 // GridWorld.cc:849-870
-        const std::vector<int32_t> pos = pull(S.pos + (size_t)group * cap, n, g->st);
-        const std::vector<uint32_t> st = pull(S.state + (size_t)group * cap, n, g->st);
+        g->fetch_state();
+        const int32_t *pos = g->m_pos + (size_t)group * cap;
+        const uint32_t *st = g->m_state + (size_t)group * cap;
         const int n_action = E.n_action();
         std::vector<int> counter(n_action + 1, 0);
         float sum_x = 0, sum_y = 0;
@@ -467,8 +551,9 @@ int env_render(EnvHandle game) {
     out << "F " << n0 + n1 << " " << g->events.size() / 3 << " " << 0 << std::endl;
     for (int grp = 0; grp < 2; grp++) {
         const int n = grp ? n1 : n0;
-        const std::vector<int32_t> pos = pull(S.pos + (size_t)grp * cap, n, g->st), id = pull(S.id + (size_t)grp * cap, n, g->st);
-        const std::vector<float> hp = pull(S.hp + (size_t)grp * cap, n, g->st);
+        g->fetch_state();
+        const int32_t *pos = g->m_pos + (size_t)grp * cap, *id = g->m_id + (size_t)grp * cap;
+        const float *hp = g->m_hp + (size_t)grp * cap;
         for (int j = 0; j < n; j++) {
             const int pct = std::min(100, std::max(0, (int)(100 * hp[j] / t0.p.hp)));
             out << id[j] << " " << pct << " " << 270 /* NORTH: turn_mode is off, GridWorld.cc:264 */ << " " << (pos[j] & 0xFFFF) << " " << (pos[j] >> 16) << " " << grp << std::endl;
@@ -576,9 +661,19 @@ int gridworld_clear_dead(EnvHandle game) {
     Engine &E = g->engine();
     g->ensure_staging();
     StepIO io{};
+    g->fetch_state();                         // (already on the host after env_step: no synchronisation)
+    // the survivors' count follows from the alive flags the host already holds, so the compaction kernel is only
+    // enqueued -- it runs back to back with whatever comes next (normally the observation kernel)
+    for (int grp = 0; grp < 2; grp++) {
+        const int n = E.host_num(0, grp);
+        const uint32_t *st = g->m_state + (size_t)grp * E.cap();
+        int alive = 0;
+        for (int i = 0; i < n; i++) alive += !(st[i] & 1u);
+        E.set_host_num(0, grp, alive);
+    }
     io.phases = PH_CLEAR; io.group_seq[0] = io.group_seq[1] = -1;
     E.step(io, g->st);
-    E.download_num(g->st);
+    g->invalidate();
     API_END("gridworld_clear_dead")
 }
 

@@ -5,6 +5,6 @@ buffers (device memory, streams); the engine never runs on the CPU.
 """
 from .lib import load_library, LIB_PATH
 from .battle import BatchedGridWorld, mean_action
-from .ising import IsingMFQ, ising_smoke
+from .ising import IsingMFQ
 
-__all__ = ["load_library", "LIB_PATH", "BatchedGridWorld", "mean_action", "IsingMFQ", "ising_smoke"]
+__all__ = ["load_library", "LIB_PATH", "BatchedGridWorld", "mean_action", "IsingMFQ"]

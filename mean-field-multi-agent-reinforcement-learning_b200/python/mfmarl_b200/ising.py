@@ -167,26 +167,5 @@ def run(argv=None):
     return results
 
 
-def ising_smoke():
-    """One small sweep on cuda:0 checked against the numpy oracle (used by __graft_entry__.smoke)."""
-    import os
-    import sys
-    here = os.path.dirname(os.path.abspath(__file__))
-    sys.path.insert(0, os.path.normpath(os.path.join(here, "..", "..", "..", "oracle")))
-    import ising_oracle
-    rng = np.random.RandomState(0)
-    B, L = 3, 20
-    spins = rng.randint(0, 2, size=(B, L, L)).astype(np.int8)
-    m = IsingMFQ(B, L, dtype=torch.float64, device="cuda:0", spins=torch.from_numpy(spins))
-    Q = np.zeros((B, 5, L * L, 2))
-    for t in range(10):
-        u = rng.random_sample((B, L * L))
-        m.step(0.8, uniforms=torch.from_numpy(u).cuda())
-        spins, Q, info = ising_oracle.step(spins, Q, 0.8, 0.1, u)
-        assert np.array_equal(m.spins.cpu().numpy(), spins), "ising spins mismatch at step %d" % t
-        assert np.allclose(m.Q.cpu().numpy(), Q, rtol=1e-12, atol=1e-15), "ising Q mismatch"
-    print("[smoke] ising: 10 sweeps x %d lattices (%dx%d, fp64) match the oracle" % (B, L, L))
-
-
 if __name__ == "__main__":
     run()
