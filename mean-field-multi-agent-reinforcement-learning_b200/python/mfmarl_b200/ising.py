@@ -117,8 +117,27 @@ class IsingMFQ:
         return self.Q.permute(0, 2, 1, 3).contiguous()
 
 
+def temperature_schedule(t0, n, decay_rate, decay_gap, floor, start=0.3):
+    """main_MFQ_Ising.py:103-112: T starts at 0.3, is multiplied by decay_rate every decay_gap steps (first at step 0)
+    and never drops below the -t flag.  -> (temperatures of steps t0 .. t0+n-1, as Python floats)."""
+    temps, cur = [], start
+    for t in range(t0 + n):
+        if t % decay_gap == 0:
+            cur *= decay_rate
+        if cur < floor:
+            cur = floor
+        if t >= t0:
+            temps.append(cur)
+    return temps
+
+
 def run(argv=None):
-    """`python -m mfmarl_b200.ising -n 400 -t 0.8`: the experiment of main_MFQ_Ising.py on the GPU."""
+    """`python -m mfmarl_b200.ising -n 400 -t 0.8`: the experiment of main_MFQ_Ising.py on the GPU.
+
+    Verbose (default): one fused step per launch, the per-step line of the reference printed for lattice 0.
+    --quiet: `--chunk` sweeps per launch through the shared-memory-resident kernel when the shape allows (same bits as
+    stepping one by one); the stagnation stop of main_MFQ_Ising.py:149-156 is evaluated on the per-sweep up counts of
+    every chunk, so MaxO and its step are those of the step-by-step loop."""
     ap = argparse.ArgumentParser(description="Ising tabular MFQ (B200)")
     ap.add_argument("-n", "--num_agents", default=100, type=int)
     ap.add_argument("-t", "--temperature", default=1, type=float)
@@ -130,6 +149,7 @@ def run(argv=None):
     ap.add_argument("-ac", "--act_rate", default=1.0, type=float)
     ap.add_argument("--lattices", default=1, type=int, help="independent lattices stepped together")
     ap.add_argument("--quiet", action="store_true")
+    ap.add_argument("--chunk", default=100, type=int, help="sweeps per launch in --quiet mode")
     args = ap.parse_args(argv)
     side = int(np.ceil(np.sqrt(args.num_agents)))
     assert side * side == args.num_agents, "num_agents must be a perfect square"
@@ -138,31 +158,38 @@ def run(argv=None):
         model = IsingMFQ(args.lattices, side, seed=13 + ep, lr=args.learning_rate)
         N = model.N
         gen = torch.Generator(device=model.device); gen.manual_seed(1000 + ep)
-        current_t, max_order, max_step, done_, t0 = 0.3, 0.0, 0, 0, time.time()
-        for t in range(args.time_steps):
-            if t % args.decay_gap == 0:
-                current_t *= args.decay_rate
-            if current_t < args.temperature:
-                current_t = args.temperature
-            mask = None
-            if args.act_rate < 1.0:   # a random act group of int(act_rate * N) sites (main_MFQ_Ising.py:126)
-                k = int(args.act_rate * N)
-                order = torch.rand((args.lattices, N), generator=gen, device=model.device).argsort(dim=1)
-                mask = torch.zeros((args.lattices, N), dtype=torch.uint8, device=model.device)
-                mask.scatter_(1, order[:, :k], 1)
-            n_up, rsum, mse = model.step(current_t, update_mask=mask)
-            order_param = float(model.order_param()[0])
-            ups = int(n_up[0])
-            if order_param > max_order:
-                max_order, max_step = order_param, t
-            done_ = done_ + 1 if abs(max_order - order_param) < 0.001 else 0
-            if done_ == 500:
-                break
-            if not args.quiet:
-                print("E: %d/%d, reward = %f, mse = %f, Order = %f, Up = %d, Down = %d"
-                      % (ep, t, float(rsum[0]), float(mse[0]), order_param, ups, N - ups))
+        max_order, max_step, done_, t0, t = 0.0, 0, 0, time.time(), 0
+        chunked = args.quiet and args.act_rate >= 1.0
+        stop = False
+        while t < args.time_steps and not stop:
+            n = min(args.chunk, args.time_steps - t) if chunked else 1
+            temps = temperature_schedule(t, n, args.decay_rate, args.decay_gap, args.temperature)
+            if chunked:
+                ups_seq = model.run(temps)[0][:, 0].cpu().tolist()          # up counts of lattice 0, per sweep
+                rsum = mse = None
+            else:
+                mask = None
+                if args.act_rate < 1.0:   # a random act group of int(act_rate * N) sites (main_MFQ_Ising.py:126)
+                    k = int(args.act_rate * N)
+                    order = torch.rand((args.lattices, N), generator=gen, device=model.device).argsort(dim=1)
+                    mask = torch.zeros((args.lattices, N), dtype=torch.uint8, device=model.device)
+                    mask.scatter_(1, order[:, :k], 1)
+                n_up, rsum, mse = model.step(temps[0], update_mask=mask)
+                ups_seq = [int(n_up[0])]
+            for ups in ups_seq:
+                order_param = abs(2 * ups - N) / N                           # core.py:106-110
+                if order_param > max_order:
+                    max_order, max_step = order_param, t
+                done_ = done_ + 1 if abs(max_order - order_param) < 0.001 else 0
+                t += 1
+                if done_ == 500:
+                    stop = True
+                    break
+                if not args.quiet:
+                    print("E: %d/%d, reward = %f, mse = %f, Order = %f, Up = %d, Down = %d"
+                          % (ep, t - 1, float(rsum[0]), float(mse[0]), order_param, ups, N - ups))
         print("Episode: %d, MaxO = %f at %d (%.1f site-steps/s)"
-              % (ep, max_order, max_step, (t + 1) * N * args.lattices / (time.time() - t0)))
+              % (ep, max_order, max_step, t * N * args.lattices / (time.time() - t0)))
         results.append((max_order, max_step))
     return results
 

@@ -180,3 +180,25 @@ def test_resident_kernel_matches_oracle_fp64_with_injected_uniforms():
         np.testing.assert_allclose(rsum[k].cpu().numpy(), info["reward_sum"], rtol=1e-12, atol=1e-12)
     assert np.array_equal(m.spins.cpu().numpy(), spins)
     np.testing.assert_allclose(m.Q.cpu().numpy(), Q, rtol=1e-13, atol=1e-15)
+
+
+def test_cli_chunked_quiet_mode_equals_stepwise(capsys):
+    """`python -m mfmarl_b200.ising --quiet` runs --chunk sweeps per launch (resident kernel) and applies the reference's
+    stagnation stop to the per-sweep up counts: same MaxO / step as the one-launch-per-step loop, with the schedule of
+    main_MFQ_Ising.py:103-112."""
+    from mfmarl_b200 import ising
+    args = ["-n", "400", "-t", "0.25", "-ts", "700", "-dg", "50", "-dr", "0.97"]
+    stepwise = ising.run(args)
+    out = capsys.readouterr().out
+    assert out.count("E: 0/") >= 100 and "Order" in out
+    chunked = ising.run(args + ["--quiet", "--chunk", "64"])
+    assert chunked == stepwise
+    sched = ising.temperature_schedule(0, 120, 0.97, 50, 0.25)
+    cur, want = 0.3, []          # independent restatement of :103-112
+    for t in range(120):
+        if t % 50 == 0:
+            cur *= 0.97
+        if cur < 0.25:
+            cur = 0.25
+        want.append(cur)
+    assert sched == want and ising.temperature_schedule(60, 60, 0.97, 50, 0.25) == want[60:]
