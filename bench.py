@@ -350,7 +350,7 @@ def run_ours(args):
     # ---- the same loop with the observations ALSO copied to pinned host memory every step, i.e. what a policy that
     #      lives on the host (the reference's own TF feed) would cost: PCIe-bound, reported for completeness ----
     obs_host = None
-    if args.obs_to_host_steps > 0:
+    if args.obs_to_host_steps > 0 and world == 1:     # (a single-GPU figure: 2.5 GB of pinned memory per rank otherwise)
         view0, feat0 = envs[0].observe()
         h_view = torch.empty(view0.shape, dtype=torch.float32).pin_memory()
         h_feat = torch.empty(feat0.shape, dtype=torch.float32).pin_memory()
