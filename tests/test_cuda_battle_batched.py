@@ -299,3 +299,15 @@ def test_annihilated_group_keeps_stepping_without_nan():
     reward, alive, done, mean = env.step(acts)
     assert done.tolist() == [1] * E and torch.isfinite(reward[:, 0, :4]).all()
     assert float(mean[:, 1].abs().sum()) == 0.0 and abs(float(mean[0, 0].sum()) - 1.0) < 1e-6
+
+
+def test_batched_largest_supported_shape_128x128_1024v1024():
+    """Maximum sizes: 1024 agent slots per group is the widest k_step CTA (1024 threads) and a 128x128 map the
+    largest occupancy grid exercised; dense placement (stride 1 blocks, one empty column apart) so that attacks, kills and
+    move collisions all happen.  Every output bit against the C oracle."""
+    from scenarios import block_positions
+    pos = (block_positions(48, 32, 16, 64, stride=1), block_positions(65, 32, 16, 64, stride=1))
+    assert len(pos[0]) == len(pos[1]) == 1024
+    env, oracles = make(2, map_size=128, cap=1024, pos=pos)
+    assert env.capacity == 1024
+    lockstep_batched(env, oracles, steps=24, seed=9, check_obs_every=6, min_deaths=10)
