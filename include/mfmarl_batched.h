@@ -134,16 +134,17 @@ int mfi_step(int dtype, int n_lattices, int side, int8_t *d_spins, void *d_q, do
 /* K6r: `n_sweeps` sweeps in ONE launch with the Q table resident in shared memory (a lattice is split over a
  * thread-block cluster of mfi_resident_cluster_size() CTAs; 1 for side <= 64, 16 for side 256 in fp32).
  * Same semantics and the same Philox keys as n_sweeps calls of mfi_step with step = step0 .. step0+n_sweeps-1
- * (bit-identical results), every site updating Q.  HBM traffic: the Q table is read and written once per launch.
+ * (bit-identical results).  HBM traffic: the Q table is read and written once per launch.
  *   d_temperatures  T    [n_sweeps]                          in (the schedule of main_MFQ_Ising.py:108-112)
  *   d_uniforms      T    [n_sweeps][n_lattices][side*side]   or NULL (test hook)
+ *   d_update_mask   uint8[n_sweeps][n_lattices][side*side]   or NULL: the act group of every sweep (act_rate < 1)
  *   d_n_up          int32[n_sweeps][n_lattices]              out, MUST be zeroed by the caller
  *   d_reward_sum    T    [n_sweeps][n_lattices]              out or NULL, MUST be zeroed by the caller
  * mfi_resident_cluster_size returns 0 when the shape is not supported (then loop over mfi_step). */
 int mfi_resident_cluster_size(int dtype, int side);
 int mfi_run(int dtype, int n_lattices, int side, int n_sweeps, int8_t *d_spins, void *d_q,
-            const void *d_temperatures, double lr, const void *d_uniforms, unsigned seed, unsigned lattice_base,
-            unsigned step0, int32_t *d_n_up, void *d_reward_sum, void *stream);
+            const void *d_temperatures, double lr, const void *d_uniforms, const uint8_t *d_update_mask, unsigned seed,
+            unsigned lattice_base, unsigned step0, int32_t *d_n_up, void *d_reward_sum, void *stream);
 
 #ifdef __cplusplus
 }

@@ -284,6 +284,7 @@ struct IsingRunArgs {
     const T *temperatures;          // [K] device
     T lr;
     const T *u;                     // optional injected uniforms [K][B][L*L]
+    const uint8_t *mask;            // optional act groups [K][B][L*L] (act_rate < 1): which sites update Q in sweep k
     uint32_t seed, lattice_base, step0;
     int32_t *n_up;                  // [K][B] out, must be zeroed by the caller
     T *reward_sum;                  // [K][B] out or null, zeroed by the caller
@@ -419,7 +420,8 @@ __global__ void __launch_bounds__(1024, 1) k_ising_resident(const IsingRunArgs<T
                     const int a = a_cur[j];
                     const int ri = (2 * a - 1) * (ups[j] - 2);                       // Ising.py:101-111, in {-2..2}
                     const T reward = (T)0.5 * (T)(2 * a - 1) * (T)(2 * ups[j] - 4);
-                    s_q[((size_t)keep_s[j] * strip + r * L + x) * 2 + a] = keep_q[j] + A.lr * (reward - keep_q[j]);
+                    if (A.mask == nullptr || A.mask[((size_t)(k - 1) * A.B + b) * N + (size_t)(row0 + r) * L + x])
+                        s_q[((size_t)keep_s[j] * strip + r * L + x) * 2 + a] = keep_q[j] + A.lr * (reward - keep_q[j]);
                     nup += a; rsum += ri;
                 }
             }
@@ -528,7 +530,7 @@ __device__ __forceinline__ void st_async_u32(uint32_t remote_addr, uint32_t v, u
                  :: "r"(remote_addr), "r"(v), "r"(remote_bar) : "memory");
 }
 
-template <int L, int ROWS, int RPT>
+template <int L, int ROWS, int RPT, bool MASK>
 __global__ void __launch_bounds__(L * (ROWS / RPT), 1) k_ising_resident_f32(const IsingRunArgs<float> A) {
     static_assert(L % 32 == 0 && ROWS % RPT == 0 && RPT % kIsingRB == 0, "shape");
     constexpr int N = L * L, WPR = L / 32, HR = ROWS + 2, STRIP = ROWS * L, NT = L * (ROWS / RPT);
@@ -638,12 +640,19 @@ __global__ void __launch_bounds__(L * (ROWS / RPT), 1) k_ising_resident_f32(cons
         // ---- finish sweep k-1: reward on the new lattice, Q update in shared memory, statistics ----
         if (k > 0) {
             int packed = 0;
+            uint32_t upd = 0xFFFFFFFFu;                                            // bit j: site j updates Q this sweep
+            if (MASK) {                                                            // act_rate < 1
+                const uint8_t *m = A.mask + ((size_t)(k - 1) * A.B + b) * N + (size_t)(row0 + rb) * L + x;
+                upd = 0;
+#pragma unroll
+                for (int j = 0; j < RPT; j++) upd |= (m[j * L] ? 1u : 0u) << j;
+            }
 #pragma unroll
             for (int j = 0; j < RPT; j++) {
                 const int d = ups[j] - 2;
                 const int ri = a_cur[j] ? d : -d;                                  // (2a-1)(ups-2) = Ising.py:101-111
                 const float reward = (float)ri;                                    // == 0.5f * (2a-1) * (2 ups - 4), exactly
-                sts_f32(keep_addr[j], keep_q[j] + A.lr * (reward - keep_q[j]));
+                if (!MASK || ((upd >> j) & 1u)) sts_f32(keep_addr[j], keep_q[j] + A.lr * (reward - keep_q[j]));
                 packed += a_cur[j] + ((ri + 2) << 16);
             }
 #pragma unroll
@@ -723,8 +732,8 @@ static void specialised_resident_kernel(const IsingRunArgs<float> &A, void (*&ke
     if (env && atoi(env) == 0) return;                 // 0 = force the generic kernel (tests)
 #define MF_PICK(LL, RR) \
     if (A.L == LL && A.rows_per == RR) { \
-        if (rpt == 8) { kern = k_ising_resident_f32<LL, RR, 8>; threads = LL * (RR / 8); } \
-        else { kern = k_ising_resident_f32<LL, RR, 4>; threads = LL * (RR / 4); } \
+        if (rpt == 8) { kern = A.mask ? k_ising_resident_f32<LL, RR, 8, true> : k_ising_resident_f32<LL, RR, 8, false>; threads = LL * (RR / 8); } \
+        else { kern = A.mask ? k_ising_resident_f32<LL, RR, 4, true> : k_ising_resident_f32<LL, RR, 4, false>; threads = LL * (RR / 4); } \
         return; \
     }
     MF_PICK(256, 16) MF_PICK(128, 32) MF_PICK(64, 64)
@@ -788,18 +797,19 @@ extern "C" int mfi_resident_cluster_size(int dtype, int side) {
 }
 
 extern "C" int mfi_run(int dtype, int n_lattices, int side, int n_sweeps, int8_t *d_spins, void *d_q,
-                       const void *d_temperatures, double lr, const void *d_uniforms, unsigned seed,
-                       unsigned lattice_base, unsigned step0, int32_t *d_n_up, void *d_reward_sum, void *stream) {
+                       const void *d_temperatures, double lr, const void *d_uniforms, const uint8_t *d_update_mask,
+                       unsigned seed, unsigned lattice_base, unsigned step0, int32_t *d_n_up, void *d_reward_sum,
+                       void *stream) {
     try {
         if (n_sweeps < 1 || n_lattices < 1) throw Fatal("mfi_run: need at least one sweep and one lattice");
         if (dtype == 0) {
             IsingRunArgs<float> A{n_lattices, side, n_sweeps, 0, d_spins, (float *)d_q, (const float *)d_temperatures,
-                                  (float)lr, (const float *)d_uniforms, seed, lattice_base, step0, d_n_up,
+                                  (float)lr, (const float *)d_uniforms, d_update_mask, seed, lattice_base, step0, d_n_up,
                                   (float *)d_reward_sum};
             launch_ising_resident(A, (cudaStream_t)stream);
         } else if (dtype == 1) {
             IsingRunArgs<double> A{n_lattices, side, n_sweeps, 0, d_spins, (double *)d_q, (const double *)d_temperatures,
-                                   lr, (const double *)d_uniforms, seed, lattice_base, step0, d_n_up,
+                                   lr, (const double *)d_uniforms, d_update_mask, seed, lattice_base, step0, d_n_up,
                                    (double *)d_reward_sum};
             launch_ising_resident(A, (cudaStream_t)stream);
         } else throw Fatal("mfi_run: dtype must be 0 (f32) or 1 (f64)");

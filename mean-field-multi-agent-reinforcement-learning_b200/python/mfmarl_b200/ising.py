@@ -35,8 +35,8 @@ class IsingMFQ:
         self.lib.mfi_step.restype = ctypes.c_int
         self.lib.mfi_run.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p,
-                                     ctypes.c_uint, ctypes.c_uint, ctypes.c_uint, ctypes.c_void_p, ctypes.c_void_p,
-                                     ctypes.c_void_p]
+                                     ctypes.c_void_p, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint, ctypes.c_void_p,
+                                     ctypes.c_void_p, ctypes.c_void_p]
         self.lib.mfi_run.restype = ctypes.c_int
         self.lib.mfi_resident_cluster_size.argtypes = [ctypes.c_int, ctypes.c_int]
         self.lib.mfi_resident_cluster_size.restype = ctypes.c_int
@@ -77,9 +77,10 @@ class IsingMFQ:
         """CTAs per lattice of the shared-memory-resident kernel, 0 if this shape only streams."""
         return self.lib.mfi_resident_cluster_size(_DTYPES[self.dtype], self.L)
 
-    def run(self, temperatures, uniforms=None, resident=None):
+    def run(self, temperatures, uniforms=None, resident=None, update_mask=None):
         """len(temperatures) sweeps.  With the resident kernel (default when the shape allows) they run in ONE
         launch with Q in shared memory; otherwise one streaming launch per sweep.  Both give the same bits.
+        update_mask uint8 [K, B, N]: the act group of every sweep (act_rate < 1).
         Returns (n_up int32 [K, B], reward_sum [K, B])."""
         temps = torch.as_tensor(temperatures, dtype=self.dtype, device=self.device).contiguous()
         K = int(temps.numel())
@@ -90,10 +91,14 @@ class IsingMFQ:
         if uniforms is not None:
             assert uniforms.dtype == self.dtype and uniforms.is_cuda and uniforms.is_contiguous()
             assert tuple(uniforms.shape) == (K, self.B, self.N)
+        if update_mask is not None:
+            assert update_mask.dtype == torch.uint8 and update_mask.is_cuda and update_mask.is_contiguous()
+            assert tuple(update_mask.shape) == (K, self.B, self.N)
         if resident:
             with torch.cuda.device(self.device):
                 check(self.lib.mfi_run(_DTYPES[self.dtype], self.B, self.L, K, _ptr(self.spins), _ptr(self.Q),
-                                       _ptr(temps), float(self.lr), _ptr(uniforms), self.seed, self.lattice_base,
+                                       _ptr(temps), float(self.lr), _ptr(uniforms), _ptr(update_mask), self.seed,
+                                       self.lattice_base,
                                        self.t, _ptr(n_up), _ptr(rsum),
                                        ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
             self.t += K
@@ -101,7 +106,8 @@ class IsingMFQ:
         else:
             host_t = temps.cpu().tolist()
             for k in range(K):
-                self.step(host_t[k], uniforms=None if uniforms is None else uniforms[k])
+                self.step(host_t[k], uniforms=None if uniforms is None else uniforms[k],
+                          update_mask=None if update_mask is None else update_mask[k])
                 n_up[k].copy_(self.n_up)
                 rsum[k].copy_(self.reward_sum)
         return n_up, rsum
@@ -159,22 +165,27 @@ def run(argv=None):
         N = model.N
         gen = torch.Generator(device=model.device); gen.manual_seed(1000 + ep)
         max_order, max_step, done_, t0, t = 0.0, 0, 0, time.time(), 0
-        chunked = args.quiet and args.act_rate >= 1.0
+        chunked = args.quiet
+
+        def act_groups(n):   # a random act group of int(act_rate * N) sites per sweep (main_MFQ_Ising.py:126)
+            if args.act_rate >= 1.0:
+                return None
+            k = int(args.act_rate * N)
+            order = torch.rand((n, args.lattices, N), generator=gen, device=model.device).argsort(dim=2)
+            mask = torch.zeros((n, args.lattices, N), dtype=torch.uint8, device=model.device)
+            mask.scatter_(2, order[:, :, :k], 1)
+            return mask
+
         stop = False
         while t < args.time_steps and not stop:
             n = min(args.chunk, args.time_steps - t) if chunked else 1
             temps = temperature_schedule(t, n, args.decay_rate, args.decay_gap, args.temperature)
+            masks = act_groups(n)
             if chunked:
-                ups_seq = model.run(temps)[0][:, 0].cpu().tolist()          # up counts of lattice 0, per sweep
+                ups_seq = model.run(temps, update_mask=masks)[0][:, 0].cpu().tolist()   # up counts of lattice 0, per sweep
                 rsum = mse = None
             else:
-                mask = None
-                if args.act_rate < 1.0:   # a random act group of int(act_rate * N) sites (main_MFQ_Ising.py:126)
-                    k = int(args.act_rate * N)
-                    order = torch.rand((args.lattices, N), generator=gen, device=model.device).argsort(dim=1)
-                    mask = torch.zeros((args.lattices, N), dtype=torch.uint8, device=model.device)
-                    mask.scatter_(1, order[:, :k], 1)
-                n_up, rsum, mse = model.step(temps[0], update_mask=mask)
+                n_up, rsum, mse = model.step(temps[0], update_mask=None if masks is None else masks[0])
                 ups_seq = [int(n_up[0])]
             for ups in ups_seq:
                 order_param = abs(2 * ups - N) / N                           # core.py:106-110

@@ -165,6 +165,30 @@ def test_resident_kernel_equals_streaming_bit_for_bit(L, B, K, variant, monkeypa
     assert not torch.equal(a.spins[0], spins[0].cuda())
 
 
+@pytest.mark.parametrize("L,variant", [(20, ""), (64, "8"), (256, "8"), (256, "0")])
+def test_resident_kernel_with_act_groups_equals_streaming(L, variant, monkeypatch):
+    """act_rate < 1 (main_MFQ_Ising.py:126): only a random subset of the sites updates Q each sweep -- the per-sweep
+    masks go through the resident kernel exactly as through K streaming launches."""
+    from mfmarl_b200 import IsingMFQ
+    if variant:
+        monkeypatch.setenv("MFMARL_ISING_RPT", variant)
+    B, K = 2, 7
+    gen = torch.Generator(device="cuda"); gen.manual_seed(L)
+    masks = (torch.rand((K, B, L * L), generator=gen, device="cuda") < 0.6).to(torch.uint8).contiguous()
+    a, b = IsingMFQ(B, L, seed=4), IsingMFQ(B, L, seed=4)
+    n_res, r_res = a.run([0.7] * K, update_mask=masks, resident=True)
+    n_str, r_str = b.run([0.7] * K, update_mask=masks, resident=False)
+    assert torch.equal(a.spins, b.spins) and torch.equal(a.Q, b.Q) and torch.equal(n_res, n_str)
+    c = IsingMFQ(B, L, seed=4)
+    c.run([0.7] * K, resident=True)
+    assert not torch.equal(c.Q, a.Q)                      # the mask really held back updates
+    # a masked-out site keeps its Q row for that sweep: with a single sweep, untouched sites stay exactly 0
+    d = IsingMFQ(B, L, seed=4)
+    d.run([0.7], update_mask=masks[:1].contiguous(), resident=True)
+    touched = (d.Q != 0).sum(dim=(1, 3))                  # [B, N]
+    assert int((touched * (1 - masks[0].to(torch.int64))).sum()) == 0
+
+
 def test_resident_kernel_matches_oracle_fp64_with_injected_uniforms():
     from mfmarl_b200 import IsingMFQ
     B, L, K, T = 3, 20, 25, 0.8
@@ -193,6 +217,9 @@ def test_cli_chunked_quiet_mode_equals_stepwise(capsys):
     assert out.count("E: 0/") >= 100 and "Order" in out
     chunked = ising.run(args + ["--quiet", "--chunk", "64"])
     assert chunked == stepwise
+    # act_rate < 1: the act groups come from the same generator in both modes when the chunk is one sweep
+    assert ising.run(args + ["-ac", "0.5", "-ts", "60"]) == ising.run(args + ["-ac", "0.5", "-ts", "60", "--quiet", "--chunk", "1"])
+    assert len(ising.run(args + ["-ac", "0.5", "-ts", "130", "--quiet", "--chunk", "50"])) == 1
     sched = ising.temperature_schedule(0, 120, 0.97, 50, 0.25)
     cur, want = 0.3, []          # independent restatement of :103-112
     for t in range(120):
