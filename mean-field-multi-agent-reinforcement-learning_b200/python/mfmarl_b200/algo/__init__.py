@@ -15,16 +15,20 @@ AC = ActorCritic
 IL = DQN
 
 
-def spawn_ai(algo_name, env, handle, human_name, max_steps, device=None):
-    """algo/__init__.py:10-19 without the TF session argument."""
+def spawn_ai(algo_name, env, handle, human_name, max_steps, device=None, device_rows=None, batch_size=64):
+    """algo/__init__.py:10-19 without the TF session argument.  device_rows sizes the HBM-resident replay of the batched
+    loop (rows of one agent-step, 4.9 KB each; default: the reference's 80000-row ring / 2^18 episode rows); batch_size is the Q learners' minibatch
+    (q_learning.py:85: 64)."""
     if algo_name == "mfq":
-        return MFQ(human_name, handle, env, max_steps, memory_size=80000, device=device)
+        return MFQ(human_name, handle, env, max_steps, memory_size=80000, batch_size=batch_size, device=device,
+                   device_memory_size=device_rows)
     if algo_name == "mfac":
-        return MFAC(human_name, handle, env, device=device)
+        return MFAC(human_name, handle, env, device=device, sub_len=max_steps, **({"stage_rows": device_rows} if device_rows else {}))
     if algo_name == "ac":
-        return AC(human_name, handle, env, device=device)
+        return AC(human_name, handle, env, device=device, sub_len=max_steps, **({"stage_rows": device_rows} if device_rows else {}))
     if algo_name == "il":
-        return IL(human_name, handle, env, max_steps, memory_size=80000, device=device)
+        return IL(human_name, handle, env, max_steps, memory_size=80000, batch_size=batch_size, device=device,
+                  device_memory_size=device_rows)
     raise ValueError("unknown algorithm %r (choose from mfq, mfac, ac, il)" % (algo_name,))
 
 

@@ -72,7 +72,13 @@ def main(argv=None):
         env = magent.GridWorld('battle', map_size=args.map_size)
         env.set_render_dir(render_dir)
         handles = env.get_handles()
-    models = [spawn_ai(args.algo, env, handles[0], args.algo + '-me', args.max_steps, device=args.device),
+    # batched rounds produce envs x agents x steps rows: give the device replay room for up to 2^20 of them (5 GB)
+    device_rows = min(1 << 20, args.envs * cap * args.max_steps) if args.envs > 0 else None
+    # ... and scale the Q learners' minibatch with the number of recorded environments, so that a round keeps the
+    # reference's number of gradient steps (new rows * 2 / batch, tools.py:352-360) instead of multiplying it
+    rec_envs = max(1, min(args.envs, device_rows // (cap * args.max_steps))) if args.envs > 0 else 1
+    models = [spawn_ai(args.algo, env, handles[0], args.algo + '-me', args.max_steps, device=args.device,
+                       device_rows=device_rows, batch_size=64 * rec_envs),
               spawn_ai(args.algo, env, handles[1], args.algo + '-opponent', args.max_steps, device=args.device)]
     runner = tools.Runner(env, handles, args.map_size, args.max_steps, models, play,
                           render_every=args.save_every if args.render else 0, save_every=args.save_every, tau=0.01,
