@@ -413,6 +413,9 @@ def run_ours(args):
                          # per launch, like `achieved`: the ncu capture is one launch over the workload's full env count
                          "traffic": (lambda t: None if t is None else t * Eh / wl["envs"])(ncu_traffic(args.workload)),
                          "peak_source": peak_src,
+                         "peak_note": "the measured peak is a COPY (read + write); k_obs only writes, and a pure fill_ of the "
+                                      "same 2.55 GB reaches 7.47 TB/s on this part (profiles/write_probe.py), so frac can "
+                                      "exceed 1 -- against that fill rate the one-stream kernel is at 0.92",
                          "bytes_per_agent": BYTES_PER_AGENT_OBS, "agents_per_launch": agents_per_launch,
                          "launch_ms": launch_ms,
                          "launch_ms_rule": "event pair around each k_obs launch" if P == 1 else
