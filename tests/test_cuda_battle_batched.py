@@ -311,3 +311,41 @@ def test_batched_largest_supported_shape_128x128_1024v1024():
     env, oracles = make(2, map_size=128, cap=1024, pos=pos)
     assert env.capacity == 1024
     lockstep_batched(env, oracles, steps=24, seed=9, check_obs_every=6, min_deaths=10)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_randomized_shapes_walls_and_ragged_armies(seed):
+    """Differential fuzzing: random map side (odd and even, small and large), random interior walls, armies of
+    random ragged sizes scattered at random free cells, three environments with independent action streams --
+    every output bit against the C oracle."""
+    from mfmarl_b200 import BatchedGridWorld
+    rng = np.random.RandomState(100 + seed)
+    size = int(rng.choice([14, 17, 23, 32, 40, 57, 64, 90]))
+    cells = [(x, y) for x in range(1, size - 1) for y in range(1, size - 1)]
+    rng.shuffle(cells)
+    n_wall = int(rng.randint(0, size))                       # a few interior obstacles
+    n0 = int(rng.randint(3, min(150, len(cells) // 6)))
+    n1 = int(rng.randint(3, min(150, len(cells) // 6)))
+    walls, rest = cells[:n_wall], cells[n_wall:]
+    # keep the armies close so that they fight: the n0 + n1 free cells nearest to the map centre
+    rest.sort(key=lambda c: (c[0] - size // 2) ** 2 + (c[1] - size // 2) ** 2)
+    picked = rest[:n0 + n1]
+    rng.shuffle(picked)
+    g0 = [[x, y, 0] for x, y in picked[:n0]]
+    g1 = [[x, y, 0] for x, y in picked[n0:]]
+    cap = int(rng.choice([max(n0, n1), max(n0, n1) + 3, 160]))
+    E = 3
+    env = BatchedGridWorld(E, map_size=size, capacity=cap, rng="minstd")
+    env.reset()
+    if walls:
+        env.add_walls([[x, y, 0] for x, y in walls])
+    env.add_agents(0, g0); env.add_agents(1, g1)
+    oracles = []
+    for _ in range(E):
+        o = OracleEngine(size)
+        o.reset()
+        if walls:
+            o.add_walls([[x, y, 0] for x, y in walls])
+        o.add_agents(0, g0); o.add_agents(1, g1)
+        oracles.append(o)
+    lockstep_batched(env, oracles, steps=45, seed=200 + seed, check_obs_every=3)
