@@ -41,10 +41,22 @@ __device__ __forceinline__ int block_scan_flag(bool flag, int *s_warp, int &tota
     __syncthreads();
     const int nw = (blockDim.x + 31) >> 5;
     int before = 0, tot = 0;
-    for (int k = 0; k < nw; k++) {
-        const int c = s_warp[k];
-        before += (k < w) ? c : 0;
-        tot += c;
+    if (nw <= 4) {                     // narrow CTAs (64 v 64): a 2-4 term loop is shorter than a shuffle scan
+        for (int k = 0; k < nw; k++) {
+            const int c = s_warp[k];
+            before += (k < w) ? c : 0;
+            tot += c;
+        }
+    } else {                           // wide CTAs: lane k reads warp k's count, one shuffle scan serves every lane
+        const int c = lane < nw ? s_warp[lane] : 0;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        before = __shfl_sync(0xFFFFFFFFu, incl - c, w);
     }
     __syncthreads();
     total = tot;
