@@ -158,7 +158,8 @@ class _ActorCriticBase:
         if self.grad_sync:
             sync_gradients(self.net.parameters())
         self.optimizer.step()
-        return float(pg_loss), float(vf_loss), float(neg_entropy), float(value.mean())
+        return (float(pg_loss.detach()), float(vf_loss.detach()), float(neg_entropy.detach()),
+                float(value.detach().mean()))
 
     def train(self, verbose=True):
         if self.device_replay is not None and self.device_replay.has_staged:

@@ -46,6 +46,16 @@ def sync_gradients(parameters):
         offset += n
 
 
+def agree_on_count(n, device):
+    """Every rank must run the same number of synchronised optimiser steps: take the minimum over the ranks."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return n
+    t = torch.tensor([n], dtype=torch.int64, device=device if dist.get_backend() == "nccl" else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return int(t[0])
+
+
 def _dense(n_in, n_out):
     layer = nn.Linear(n_in, n_out)
     nn.init.xavier_uniform_(layer.weight)      # tf.layers default: glorot_uniform, zero bias

@@ -44,7 +44,10 @@ class DQN(_ReplayMixin, base.ValueNet):
         replay = self._active_replay()
         replay.tight()
         losses = []
-        for i in range(replay.get_batch_num(verbose)):
+        n_batches = replay.get_batch_num(verbose)
+        if self.grad_sync:
+            n_batches = base.agree_on_count(n_batches, self.device)
+        for i in range(n_batches):
             obs, feats, obs_next, feat_next, dones, rewards, actions, masks = replay.sample()
             target_q = self.calc_target_q(obs=obs_next, feature=feat_next, rewards=rewards, dones=dones)
             loss, q = base.ValueNet.train(self, state=[obs, feats], target_q=target_q, acts=actions, masks=masks)
@@ -74,7 +77,10 @@ class MFQ(_ReplayMixin, base.ValueNet):
         replay = self._active_replay()
         replay.tight()
         losses = []
-        for i in range(replay.get_batch_num(verbose)):
+        n_batches = replay.get_batch_num(verbose)
+        if self.grad_sync:
+            n_batches = base.agree_on_count(n_batches, self.device)
+        for i in range(n_batches):
             (obs, feat, acts, act_prob, obs_next, feat_next, act_prob_next, rewards, dones,
              masks) = replay.sample()
             target_q = self.calc_target_q(obs=obs_next, feature=feat_next, rewards=rewards, dones=dones,

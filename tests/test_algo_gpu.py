@@ -158,3 +158,27 @@ def test_train_battle_and_battle_scripts_end_to_end(tmp_path):
     win = battle.main(["--algo", "mfq", "--oppo", "mfac", "--n_round", "2", "--max_steps", "8", "--idx", "0", "0",
                        "--data_dir", data])
     assert win["main"] + win["opponent"] >= 2
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("algo", ["mfq", "mfac"])
+def test_data_parallel_training_keeps_the_ranks_in_step(algo, tmp_path):
+    """torchrun, two ranks, each with its own shard of lock-stepped environments (env_base = rank * E) and the optional
+    gradient all-reduce: after two rounds both ranks hold bit-identical main-model weights."""
+    import os
+    import subprocess
+    import sys
+    from conftest import PKG
+    script = os.path.join(PKG, "python", "train_battle.py")
+    data = str(tmp_path / "data")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29631", script, "--algo", algo, "--envs", "8", "--n_round", "2",
+           "--max_steps", "8", "--save_every", "1", "--data_dir", data]
+    env = dict(os.environ, MFMARL_SAVE_FINAL="1")
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    a = torch.load(os.path.join(data, "final_rank0.pt"), map_location="cpu")
+    b = torch.load(os.path.join(data, "final_rank1.pt"), map_location="cpu")
+    assert len(a) == len(b) > 0
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
