@@ -461,7 +461,7 @@ __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState
 }
 
 // ----------------------------------------------------------------------------------------------
-// K1: observations.  One CTA per (env, group, tile of agents).
+// K1: observations.  Persistent CTAs take (env, group, tile of agents) work items from a ticket counter.
 //
 // The per-agent view is 13*13*7 fp32 = 4732 B, >90 % zeros, and it is the whole of the HBM traffic
 // of the path.  Rows are composed in shared memory and streamed out by the TMA engine: 8 agents'
@@ -469,15 +469,18 @@ __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState
 // hands the chunk to a single cp.async.bulk shared->global store; two staging buffers keep a store
 // in flight while the next chunk is composed.
 //
-// Composition is incremental.  At CTA start every staging row is filled once with the part all agents
-// of the group share (the two minimap channels).  For each agent its warp then only
-//   - looks the 169 view cells up in the shared-memory occupancy grid (lane = cell, 6 passes; the grid
-//     carries a 6-cell empty margin, so a window never needs a bounds test: one add + one 16-bit load),
-//   - rewrites the five occupancy channels (wall, own has/hp, other has/hp) of every cell,
+// Composition is incremental.  The staging rows are zeroed once per CTA; cells outside the view disc never
+// change again.  For the first two chunks of an item every row also receives the part all agents of the group
+// share (the two minimap channels).  For each agent its warp then only
+//   - looks the 113 in-disc view cells up in the shared-memory occupancy grid (4 passes of 32 lanes on a
+//     host-built schedule, BattleParams::obs_cell; the grid carries a 6-cell empty margin, so a window never
+//     needs a bounds test: one add + one 16-bit load),
+//   - rewrites the five occupancy channels (wall, own has/hp, other has/hp) of those cells,
 //   - moves the "+1" self marker of the two minimap channels.
-// All shared-memory stores are stride-7-word (coprime with the 32 banks): conflict-free.
-// The map is never re-read from HBM: occupancy/hp grid and both minimaps are rebuilt per CTA from the
-// SoA agent arrays.
+// Shared-memory stores are stride-7-word (coprime with the 32 banks) and the schedule keeps a pass's cells in
+// distinct residues mod 32 where it can: (nearly) conflict-free.
+// The map is never re-read from HBM: occupancy/hp grid and both minimaps are rebuilt per item from the
+// SoA agent arrays, whose loads are all issued up front (one memory round trip per item).
 // ----------------------------------------------------------------------------------------------
 #ifndef MF_OBS_CHUNK
 #define MF_OBS_CHUNK 8
