@@ -146,6 +146,7 @@ Engine::Engine(const EngineConfig &cfg) : cfg_(cfg) {
     MF_CUDA(cudaMemset(S_.step_ct, 0, E * sizeof(int32_t)));
     MF_CUDA(cudaMemset(S_.id_counter, 0, E * sizeof(int32_t)));
     h_num_.assign(E * 2, 0);
+    { const char *dbg = getenv("MFMARL_OBS_DEBUG"); obs_debug_ = dbg ? atoi(dbg) : 0; }
     set_seed(cfg.seed);   // seed 0 -> minstd state 1, as GridWorld.cc:31 random_engine.seed(0)
     alloc_state(std::max(4, round_up(cfg.capacity, 4)));
     reset();
@@ -389,7 +390,7 @@ void Engine::observe_groups(float *const d_view[kGroups], float *const d_feature
         if (((group_mask >> g) & 1) && ((uintptr_t)d_view[g] & 15)) throw Fatal("observe: view buffer must be 16-byte aligned");
     }
     io.env_stride = env_stride; io.group_mask = group_mask;
-    { const char *dbg = getenv("MFMARL_OBS_DEBUG"); io.debug = dbg ? atoi(dbg) : 0; }
+    io.debug = obs_debug_;
     const ObsSmem L = obs_smem_layout(P_.W, P_.H, P_.cap);
     if (obs_attr_ != L.total) {
         MF_CUDA(cudaFuncSetAttribute(k_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));

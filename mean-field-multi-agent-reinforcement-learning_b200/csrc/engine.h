@@ -110,6 +110,7 @@ private:
     int n_sm_ = 148;
     int obs_attr_ = -1, step_attr_ = -1;   // dynamic-smem opt-in already set for this size
     int obs_ctas_per_sm_ = 2;              // resident k_obs CTAs per SM at that size (occupancy query)
+    int obs_debug_ = 0;                    // MFMARL_OBS_DEBUG at construction (profiling experiments only)
 
     // host-side placement template (what add_agents has built since the last reset)
     std::vector<unsigned char> h_walls_;          // [H*W]
