@@ -686,8 +686,10 @@ def run_reference(args):
         return
     kind = cpu_kind()
     procs = os.cpu_count() or 1
-    CHUNK = 32  # one reference "step" = every worker advances its own env by CHUNK lockstep steps
-    v, total, secs = run_cpu(kind, wl["map_size"], args.warmup * CHUNK, args.steps * CHUNK, procs)
+    # one reference "step" = every worker advances its own env by CHUNK lockstep steps; CHUNK is sized so that the
+    # timed part is at least ~30000 steps per worker (about 5 s) whatever --steps is -- shorter samples under-report
+    CHUNK = max(32, -(-30000 // max(1, args.steps)))
+    v, total, secs = run_cpu(kind, wl["map_size"], min(args.warmup * CHUNK, 500), args.steps * CHUNK, procs)
     sample = ("%d independent single-thread envs of the %s engine (OMP_NUM_THREADS=1), each step = %d lockstep "
               "steps per env (bounded sample of the %d-env workload), %.1f s"
               % (procs, "reference C++" if kind == "reference" else "C oracle port", CHUNK, wl["envs"], secs))
