@@ -349,3 +349,50 @@ def test_randomized_shapes_walls_and_ragged_armies(seed):
         o.add_agents(0, g0); o.add_agents(1, g1)
         oracles.append(o)
     lockstep_batched(env, oracles, steps=45, seed=200 + seed, check_obs_every=3)
+
+
+def test_sampled_envs_of_a_large_engine_match_the_oracle():
+    """512 lock-stepped environments, three of them (first, middle, last) shadowed by the C oracle on the fight stream
+    while the others run uniform random actions: indexing at scale (env offsets, ticket scheduling, per-env rng)."""
+    from mfmarl_b200 import BatchedGridWorld
+    E, cap, steps = 512, 64, 150
+    watch = [0, 255, 511]
+    left, right = generate_map_positions(40)
+    env = BatchedGridWorld(E, map_size=40, capacity=cap, rng="minstd")
+    env.reset(); env.add_agents(0, left); env.add_agents(1, right)
+    oracles = {}
+    for e in watch:
+        o = OracleEngine(40); o.reset(); o.add_agents(0, left); o.add_agents(1, right)
+        oracles[e] = o
+    rng = np.random.RandomState(77)
+    gen = torch.Generator(device="cuda"); gen.manual_seed(5)
+    deaths = 0
+    for s in range(steps):
+        num, pos = env.get_num(), env.get("pos")
+        view, feat = env.observe()
+        actions = torch.randint(0, 21, (E, 2, cap), generator=gen, device="cuda", dtype=torch.int32)
+        for e, o in oracles.items():
+            for g in range(2):
+                n = num[e, g]
+                assert o.get_num(g) == n
+                if s % 10 == 0:
+                    v, f = o.get_observation(g)
+                    assert_same("view[e%d g%d]" % (e, g), v, view[e, g, :n].cpu().numpy(), s)
+                    assert_same("feat[e%d g%d]" % (e, g), f, feat[e, g, :n].cpu().numpy(), s)
+                a = fight_actions(rng, pos[e, g, :n], 40)
+                actions[e, g, :n] = torch.from_numpy(a).cuda()
+                o.set_action(g, a)
+        reward, alive, done, mean = env.step(actions)
+        reward, alive = reward.cpu().numpy(), alive.cpu().numpy()
+        for e, o in oracles.items():
+            assert o.step() == bool(done[e])
+            for g in range(2):
+                n = num[e, g]
+                assert_same("reward[e%d g%d]" % (e, g), o.get_reward(g), reward[e, g, :n], s)
+                al = o.get_alive(g)
+                assert_same("alive[e%d g%d]" % (e, g), al, alive[e, g, :n].astype(bool), s)
+                deaths += int((~al).sum())
+            o.clear_dead()
+        if any(min(o.get_num(0), o.get_num(1)) == 0 for o in oracles.values()):
+            break
+    assert deaths > 30
