@@ -394,6 +394,7 @@ void Engine::observe_groups(float *const d_view[kGroups], float *const d_feature
     const ObsSmem L = obs_smem_layout(P_.W, P_.H, P_.cap);
     if (obs_attr_ != L.total) {
         MF_CUDA(cudaFuncSetAttribute(k_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        MF_CUDA(cudaFuncSetAttribute(k_obs, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         MF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&obs_ctas_per_sm_, k_obs, kObsThreads, L.total));
         obs_attr_ = L.total;
     }
@@ -423,6 +424,9 @@ void Engine::step(const StepIO &io, cudaStream_t st) {
     const StepSmem L = step_smem_layout(P_.W, P_.H, P_.cap);
     if (step_attr_ != L.total) {
         MF_CUDA(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        // the same L1 / shared-memory split as k_obs: the two kernels alternate every step (and overlap on two streams),
+        // and an SM has to drain before it can change its carve-out
+        MF_CUDA(cudaFuncSetAttribute(k_step, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         step_attr_ = L.total;
     }
     int threads = cfg_.step_threads > 0 ? cfg_.step_threads : std::min(1024, std::max(64, P_.cap));
