@@ -667,19 +667,28 @@ __global__ void __launch_bounds__(L * (ROWS / RPT), 1) k_ising_resident_f32(cons
                 uu[j] = A.u[((size_t)k * A.B + b) * N + (size_t)(row0 + rb + j) * L + x] * 4294967296.0f;
         }
         const uint32_t nxt = cur ^ BUF;
+        // staged so that the RPT sites' load -> exp -> compare -> ballot chains overlap instead of running one after
+        // the other (the shared-memory stores of one site would otherwise order the next site's load behind them)
+        float2 pr[RPT];
 #pragma unroll
         for (int j = 0; j < RPT; j++) {
-            const uint32_t addr = q_site0 + (uint32_t)ups[j] * PLANE + (uint32_t)j * (L * 8u);
-            const float2 pr = lds_f32x2(addr);
-            const int a = draw_action_scaled(uu[j], pr.x, pr.y, tparam);
-            const uint32_t word = __ballot_sync(0xFFFFFFFFu, a != 0);
-            if (lane == 0) {
-                sts_u32(own_w + nxt + (uint32_t)j * WPR * 4u, word);
-                if (first_band && j == 0) st_async_u32(halo_up + nxt, word, bar_up + (nxt ? 8u : 0u));
-                if (last_band && j == RPT - 1) st_async_u32(halo_dn + nxt, word, bar_dn + (nxt ? 8u : 0u));
-            }
-            keep_q[j] = a ? pr.y : pr.x; keep_addr[j] = addr + (uint32_t)a * 4u;
-            a_cur[j] = a; w_cur[j] = word;
+            keep_addr[j] = q_site0 + (uint32_t)ups[j] * PLANE + (uint32_t)j * (L * 8u);
+            pr[j] = lds_f32x2(keep_addr[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < RPT; j++) a_cur[j] = draw_action_scaled(uu[j], pr[j].x, pr[j].y, tparam);
+#pragma unroll
+        for (int j = 0; j < RPT; j++) w_cur[j] = __ballot_sync(0xFFFFFFFFu, a_cur[j] != 0);
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < RPT; j++) sts_u32(own_w + nxt + (uint32_t)j * WPR * 4u, w_cur[j]);
+            if (first_band) st_async_u32(halo_up + nxt, w_cur[0], bar_up + (nxt ? 8u : 0u));
+            if (last_band) st_async_u32(halo_dn + nxt, w_cur[RPT - 1], bar_dn + (nxt ? 8u : 0u));
+        }
+#pragma unroll
+        for (int j = 0; j < RPT; j++) {
+            keep_q[j] = a_cur[j] ? pr[j].y : pr[j].x;
+            keep_addr[j] += (uint32_t)a_cur[j] * 4u;
         }
         // ---- the next sweep's Philox draws and temperature (independent of the lattice) ----
         if (k + 1 < A.K) {
