@@ -703,18 +703,23 @@ k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO i
                 float *row = (buf ? s_stage1 : s_stage0) + warp * kViewRow;
                 // window top-left corner (ax - 6, ay - 6) in padded coordinates is simply (ax, ay)
                 const uint16_t *win = s_code + ay * PW + ax;
+                // staged (all grid look-ups, then all hp look-ups, then the stores): a store of one pass would otherwise
+                // order the next pass's loads behind it and the four load -> load -> store chains would run back to back
+                uint32_t code[kDiscPasses]; float hpv[kDiscPasses];
+#pragma unroll
+                for (int it = 0; it < kDiscPasses; it++) code[it] = (uint32_t)win[off[it]];      // idle lanes read offset 0
+#pragma unroll
+                for (int it = 0; it < kDiscPasses; it++) hpv[it] = s_hp10[code[it] & 0x3FFFu];
 #pragma unroll
                 for (int it = 0; it < kDiscPasses; it++) {
                     if (cell7[it] >= 0) {               // only the last pass has idle lanes
-                        const uint32_t code = (uint32_t)win[off[it]];
-                        const uint32_t k = code >> 14;
-                        const float hp = s_hp10[code & 0x3FFFu];
+                        const uint32_t k = code[it] >> 14;
                         float *o = row + cell7[it];
                         o[0] = k == KIND_WALL ? 1.0f : 0.0f;
                         o[1] = k == KIND_OWN ? 1.0f : 0.0f;
-                        o[2] = k == KIND_OWN ? hp : 0.0f;
+                        o[2] = k == KIND_OWN ? hpv[it] : 0.0f;
                         o[4] = k == KIND_OTHER ? 1.0f : 0.0f;
-                        o[5] = k == KIND_OTHER ? hp : 0.0f;
+                        o[5] = k == KIND_OTHER ? hpv[it] : 0.0f;
                     }
                 }
                 if (stale > 0) {                        // new item: refresh the part all its agents share
