@@ -32,12 +32,13 @@ __device__ __forceinline__ uint32_t make_state(uint32_t dead, uint32_t op, uint3
     return dead | (op << 8) | (act << 16);
 }
 
-// Block-wide exclusive scan of a predicate (ballot + popc inside each warp, per-warp totals through
-// shared memory).  Must be reached by every thread of the block.  s_warp needs 32 ints.
-__device__ __forceinline__ int block_scan_flag(bool flag, int *s_warp, int &total) {
-    const unsigned ballot = __ballot_sync(0xFFFFFFFFu, flag);
+// Block-wide exclusive scan of TWO predicates at once (ballot + popc inside each warp, per-warp totals through
+// shared memory, both counts packed into one int: low half a, high half b -- counts stay below 65536).  Must be
+// reached by every thread of the block.  s_warp needs 32 ints.  Returns the packed exclusive prefix.
+__device__ __forceinline__ int block_scan_flags2(bool fa, bool fb, int *s_warp, int &total) {
+    const unsigned ba = __ballot_sync(0xFFFFFFFFu, fa), bb = __ballot_sync(0xFFFFFFFFu, fb);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0) s_warp[w] = __popc(ballot);
+    if (lane == 0) s_warp[w] = __popc(ba) | (__popc(bb) << 16);
     __syncthreads();
     const int nw = (blockDim.x + 31) >> 5;
     int before = 0, tot = 0;
@@ -60,14 +61,30 @@ __device__ __forceinline__ int block_scan_flag(bool flag, int *s_warp, int &tota
     }
     __syncthreads();
     total = tot;
-    return before + __popc(ballot & ((1u << lane) - 1u));
+    const unsigned lt = (1u << lane) - 1u;
+    return before + (__popc(ba & lt) | (__popc(bb & lt) << 16));
+}
+__device__ __forceinline__ int block_scan_flag(bool flag, int *s_warp, int &total) {
+    return block_scan_flags2(flag, false, s_warp, total);
+}
+
+// minstd_rand0 after n steps from state s: s * 16807^n mod (2^31 - 1), square and multiply over a table of
+// 16807^(2^b) -- the reference's sequential chain (GridWorld.cc:510-515 draws one number per attack) without the chain.
+__device__ __forceinline__ uint32_t minstd_jump(uint32_t s, uint32_t n) {
+    const uint32_t pw[12] = {16807u, 282475249u, 984943658u, 1457850878u, 1137522503u, 1636807826u,
+                             685118024u, 515204530u, 897054849u, 2038299453u, 1836275591u, 349037107u};
+    uint64_t acc = s;
+#pragma unroll
+    for (int b = 0; b < 12; b++)
+        if ((n >> b) & 1u) acc = (acc * pw[b]) % 2147483647ull;
+    return (uint32_t)acc;
 }
 
 // ----------------------------------------------------------------------------------------------
 // K2: fused step
 // ----------------------------------------------------------------------------------------------
 struct StepSmem {  // byte offsets into dynamic shared memory
-    int pos, hp, nr, state, att, aux, mv, mvt, tag_a, tag_v, mvidx, grid, misc, total;
+    int pos, hp, nr, state, att, aux, mv, mvt, tag_a, tag_v, mvidx, scr0, scr1, grid, claim, misc, total;
 };
 __host__ __device__ inline StepSmem step_smem_layout(int W, int H, int cap) {
     StepSmem L;
@@ -77,20 +94,27 @@ __host__ __device__ inline StepSmem step_smem_layout(int W, int H, int cap) {
     L.hp = o;    o += 4 * n;
     L.nr = o;    o += 4 * n;
     L.state = o; o += 4 * n;
-    L.att = o;   o += 4 * n;   // shuffled attack list: slot | attack index << 16
-    L.aux = o;   o += 4 * n;   // shuffle scratch, then victim slot per attack (-1 = miss)
+    L.att = o;   o += 4 * n;   // attack list: slot | attack index << 16 (| 1 << 31 once it acted)
+    L.aux = o;   o += 4 * n;   // shuffle draws, then victim slot per attack (-1 = miss)
     L.mv = o;    o += 4 * n;   // move list: slot | move index << 16
-    L.mvt = o;   o += 4 * n;   // target per move: packed (x, y), or -1 = outside the board
+    L.mvt = o;   o += 4 * n;   // target cell per move, or -1 = no attempt (outside the board, dead mover)
+    L.scr0 = o;  o += 4 * n;   // shuffle: list heads | attacks: hits per slot, attacker flag | moves: result per mover
+    L.scr1 = o;  o += 4 * n;   // shuffle: list links | attacks: the entangled attacks, in order | moves: dependency
     L.tag_a = o; o += 2 * n;   // batch tag: slot attacks in the current 32-attack batch
     L.tag_v = o; o += 2 * n;   // batch tag: slot is attacked in the current batch
-    L.mvidx = o; o += 2 * n;   // 1 + index in the move list (0 = does not move this step)
-    L.misc = o;  o += 4 * 64;  // warp totals [32], counters
-    L.grid = o;  o += 2 * W * H;
+    L.mvidx = o; o += 2 * n;   // 1 + index in the move list of a mover that tries to leave its cell (0 = it stays)
+    L.misc = o;  o += 4 * 128; // warp totals [32], counters, action histogram [2][32]
+    L.grid = o;  o += (2 * W * H + 3) & ~3;
+    L.claim = o; o += 4 * W * H;   // per target cell: the first mover entitled to it (min over list indices)
     L.total = (o + 15) & ~15;
     return L;
 }
 
-enum { MISC_WARP = 0, MISC_N = 32, MISC_DEAD = 34, MISC_NA = 36, MISC_NM = 37, MISC_DONE = 38, MISC_RESET = 39 };
+enum { MISC_WARP = 0, MISC_N = 32, MISC_DEAD = 34, MISC_NA = 36, MISC_NM = 37, MISC_DONE = 38, MISC_RESET = 39,
+       MISC_FLAG = 40, MISC_NENT = 41, MISC_HIST = 64 };
+
+// mover results while the move phase runs
+enum : int { MV_FAIL = 0, MV_OK = 1, MV_WAIT = 2 };
 
 __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState S, const StepIO io) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -103,11 +127,14 @@ __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState
     int *s_aux = (int *)(smem_raw + L.aux);
     uint32_t *s_mv = (uint32_t *)(smem_raw + L.mv);
     int *s_mvt = (int *)(smem_raw + L.mvt);
+    int *s_scr0 = (int *)(smem_raw + L.scr0);
+    int *s_scr1 = (int *)(smem_raw + L.scr1);
     uint16_t *s_tag_a = (uint16_t *)(smem_raw + L.tag_a);
     uint16_t *s_tag_v = (uint16_t *)(smem_raw + L.tag_v);
     uint16_t *s_mvidx = (uint16_t *)(smem_raw + L.mvidx);
     int *s_misc = (int *)(smem_raw + L.misc);
     uint16_t *s_grid = (uint16_t *)(smem_raw + L.grid);
+    uint32_t *s_claim = (uint32_t *)(smem_raw + L.claim);
 
     const int e = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     const int cap = P.cap, W = P.W, H = P.H, cells = W * H;
@@ -127,6 +154,8 @@ __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState
     } else {
         for (int c = tid; c < cells; c += nt) s_grid[c] = walls[c];
     }
+    if (phases & PH_STEP)
+        for (int c = tid; c < cells; c += nt) s_claim[c] = 0xFFFFFFFFu;
     __syncthreads();
     const int n0 = s_misc[MISC_N], n1 = s_misc[MISC_N + 1];
     for (int s = tid; s < 2 * cap; s += nt) {
@@ -143,84 +172,97 @@ __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState
             s_state[s] = st;
             if (!st_dead(st)) s_grid[pos_y(p) * W + pos_x(p)] = (uint16_t)(2 + s);
         }
-        s_tag_a[s] = 0; s_tag_v[s] = 0; s_mvidx[s] = 0;
+        s_tag_a[s] = 0; s_tag_v[s] = 0; s_mvidx[s] = 0; s_scr0[s] = 0;
     }
     __syncthreads();
 
     int done = 0;
     if (phases & PH_STEP) {
-        // ---- attack / move lists in set_action call order (GridWorld.cc:481-495) ----
+        // ---- attack / move lists in set_action call order (GridWorld.cc:481-495).  On a large map (W*H > 99*99,
+        //      GridWorld.cc:79-88) the reference files the moves into x-band buffers at set_action (:443-463) and runs
+        //      buffer 0 .. NUM_SEP-1, then the boundary buffer (:662-672): the move list is built pass by pass in
+        //      that order, each pass in call order ----
         int nA = 0, nM = 0;
-        for (int gi = 0; gi < kGroups; gi++) {
-            const int g = io.group_seq[gi];
-            if (g < 0) continue;
-            const int ng = g ? n1 : n0;
-            for (int base = 0; base < ng; base += nt) {
-                const int i = base + tid, s = g * cap + i;
-                const bool valid = i < ng;
-                const int a = valid ? (int)st_act(s_state[s]) : n_action;
-                const bool is_mv = valid && a < P.n_move, is_at = valid && a >= P.n_move && a < n_action;
-                int tot;
-                int p = block_scan_flag(is_at, s_misc + MISC_WARP, tot);
-                if (is_at) s_att[nA + p] = (uint32_t)s | ((uint32_t)(a - P.n_move) << 16);
-                nA += tot;
-                p = block_scan_flag(is_mv, s_misc + MISC_WARP, tot);
-                if (is_mv) s_mv[nM + p] = (uint32_t)s | ((uint32_t)a << 16);
-                nM += tot;
+        const int n_pass = P.move_bands > 0 ? P.move_bands + 1 : 1;
+        for (int pass = 0; pass < n_pass; pass++) {
+            for (int gi = 0; gi < kGroups; gi++) {
+                const int g = io.group_seq[gi];
+                if (g < 0) continue;
+                const int ng = g ? n1 : n0;
+                for (int base = 0; base < ng; base += nt) {
+                    const int i = base + tid, s = g * cap + i;
+                    const bool valid = i < ng;
+                    const int a = valid ? (int)st_act(s_state[s]) : n_action;
+                    bool is_mv = valid && a < P.n_move;
+                    const bool is_at = pass == 0 && valid && a >= P.n_move && a < n_action;
+                    if (is_mv && n_pass > 1) {
+                        const int x = pos_x(s_pos[s]), xr = x % P.band_width;
+                        const int band = (xr < 4 || xr > P.band_width - 4) ? P.move_bands : x / P.band_width;
+                        is_mv = band == pass;
+                    }
+                    int tot;
+                    const int p = block_scan_flags2(is_at, is_mv, s_misc + MISC_WARP, tot);
+                    if (is_at) s_att[nA + (p & 0xFFFF)] = (uint32_t)s | ((uint32_t)(a - P.n_move) << 16);
+                    if (is_mv) s_mv[nM + (p >> 16)] = (uint32_t)s | ((uint32_t)a << 16);
+                    nA += tot & 0xFFFF; nM += tot >> 16;
+                }
             }
         }
         __syncthreads();
 
-        // ---- shuffle attacks (GridWorld.cc:510-515): inside-out Fisher-Yates, draw i picks j in [0, i] ----
+        // ---- shuffle attacks (GridWorld.cc:510-515): inside-out Fisher-Yates, draw i picks j_i in [0, i] and swaps
+        //      positions i and j_i ----
         if (P.rng_mode == RNG_INJECT) {
             const int32_t *perm = io.attack_perm + (size_t)e * 2 * cap;
             for (int i = tid; i < nA; i += nt) s_aux[i] = (int)s_att[perm[i]];
             __syncthreads();
             for (int i = tid; i < nA; i += nt) s_att[i] = (uint32_t)s_aux[i];
-        } else {
-            // draw i picks j in [0, i]:  Philox draws are independent of each other (all in parallel); the reference's
-            // minstd_rand0 is a chain (one thread, ALU only)
-            if (P.rng_mode == RNG_PHILOX) {
-                for (int i = tid; i < nA; i += nt) {
+        } else if (nA > 0) {
+            // the draws, all at once: Philox is counter based; the reference's minstd_rand0 chain is jumped ahead
+            // (state after i+1 steps = state * 16807^(i+1))
+            const uint32_t rs0 = P.rng_mode == RNG_MINSTD ? S.rng[e] : 0u;
+            for (int i = tid; i < nA; i += nt) {
+                if (P.rng_mode == RNG_PHILOX) {
                     const uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)step_before, 0u, 0u),
                                                   make_uint2(P.seed, (uint32_t)(P.env_base + e)));
                     s_aux[i] = (int)(r.x % (uint32_t)(i + 1));
+                } else {
+                    const uint32_t rs = minstd_jump(rs0, (uint32_t)(i + 1));
+                    s_aux[i] = (int)rs % (i + 1);
+                    if (i == nA - 1) S.rng[e] = rs;
                 }
-            } else if (tid == 0) {
-                uint32_t rs = S.rng[e];
-                for (int i = 0; i < nA; i++) { rs = minstd_next(rs); s_aux[i] = (int)rs % (i + 1); }
-                S.rng[e] = rs;
+                s_scr0[i] = -1;
             }
             __syncthreads();
-            // The swaps swap(a[i], a[j_i]), i = 0, 1, ..., are order dependent only where they share a position.  One
-            // warp takes 32 consecutive i at a time: a lane whose j lies before the batch and is picked by no other
-            // lane touches two positions nobody else in the batch touches and swaps in parallel; the other lanes
-            // (j inside the batch, or a j shared with another lane) then swap one at a time in index order -- the
-            // same permutation as the one-by-one loop, in ~1/6 of its time at 400 attacks.
-            if (tid < 32) {
-                const int lane = tid;
-                for (int i0 = 0; i0 < nA; i0 += 32) {
-                    const int i = i0 + lane;
-                    const bool valid = i < nA;
-                    const int j = valid ? s_aux[i] : -1 - lane;
-                    const unsigned same_j = __match_any_sync(0xFFFFFFFFu, j);
-                    const bool complex = valid && j != i && (j >= i0 || __popc(same_j) > 1);   // j == i: nothing to swap
-                    if (valid && !complex && j != i) { const uint32_t t = s_att[i]; s_att[i] = s_att[j]; s_att[j] = t; }
-                    __syncwarp();
-                    unsigned todo = __ballot_sync(0xFFFFFFFFu, complex);
-                    while (todo) {
-                        const int l = __ffs(todo) - 1;
-                        todo &= todo - 1;
-                        if (lane == l) { const uint32_t t = s_att[i]; s_att[i] = s_att[j]; s_att[j] = t; }
-                        __syncwarp();
-                    }
+            // No swap is executed.  Position i still holds element i when step i runs, so the content of position q
+            // after all steps < t is: element i* if i* is the LAST step in (q, t) that swapped into q (j_i* = q);
+            // otherwise what position j_q held after the steps < q (step q itself moved it in).  Every final position
+            // follows that trace on its own -- O(log n) hops expected -- through per-position lists of the steps
+            // that swap into it.  (tests/test_parallel_resolve_model.py checks this against the swap loop.)
+            for (int i = tid; i < nA; i += nt) s_scr1[i] = atomicExch(&s_scr0[s_aux[i]], i);
+            __syncthreads();
+            for (int p = tid; p < nA; p += nt) {
+                int q = p, t = nA, src;
+                for (;;) {
+                    int best = -1;
+                    for (int i = s_scr0[q]; i >= 0; i = s_scr1[i])
+                        if (i > q && i < t && i > best) best = i;
+                    if (best >= 0) { src = best; break; }
+                    const int jq = s_aux[q];
+                    if (jq == q) { src = q; break; }
+                    t = q; q = jq;
                 }
+                s_mvt[p] = (int)s_att[src];                     // (s_mvt is free until the move phase)
             }
+            __syncthreads();
+            for (int p = tid; p < nA; p += nt) s_att[p] = (uint32_t)s_mvt[p];
+            for (int s = tid; s < 2 * cap; s += nt) s_scr0[s] = 0;
         }
         __syncthreads();
 
         // ---- victims (Map::get_attack_obj, Map.cc:220-263): positions are frozen during the attack
-        //      phase, so the only thing that can change before an attack's turn is the victim dying ----
+        //      phase, so the only thing that can change before an attack's turn is the victim dying.
+        //      s_scr0[slot] counts the attacks aimed at the slot (low half) and flags the slot as an attacker ----
         for (int i = tid; i < nA; i += nt) {
             const uint32_t ent = s_att[i];
             const int k = ent & 0xFFFF, a = ent >> 16, p = s_pos[k];
@@ -231,16 +273,12 @@ __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState
                 if (code >= 2 && ((code - 2) >= cap) != (k >= cap)) v = code - 2;
             }
             s_aux[i] = v;
+            atomicAdd(&s_scr0[k], 0x10000);
+            if (v >= 0) atomicAdd(&s_scr0[v], 1);
         }
         __syncthreads();
 
         // ---- ordered attack resolve (GridWorld.cc:524-557 run single-threaded, Map::do_attack Map.cc:266-321) ----
-        // Sequential semantics, executed by warp 0 in batches of 32 consecutive attacks of the shuffled
-        // order.  An attack (k -> v) whose attacker is attacked by nobody else in the batch and whose victim
-        // neither is attacked by another lane nor attacks in this batch touches state no other lane of the
-        // batch reads or writes: those lanes run in parallel.  The rest ("complex") run one lane at a time
-        // in lane order, i.e. in the shuffled order; since the simple lanes commute with them the result is
-        // bit-identical to the one-by-one loop.
         auto one_attack = [&](int k, int v, int i) {
             if (st_dead(s_state[k])) return;                               // attacker died earlier this step
             s_att[i] |= 0x80000000u;                                       // it acted: a render attack event (GridWorld.cc:533)
@@ -265,11 +303,43 @@ __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState
             }
             s_nr[k] = s_nr[k] + (reward + P.attack_penalty);               // GridWorld.cc:556
         };
+        // (1) ISOLATED attacks, all at once.  (k -> v) is isolated when nobody attacks k this step -- so k is alive at
+        // its turn whenever that is -- and either it hits nothing, or it is the only attack on v and cannot change what
+        // v itself does (v does not attack, or survives the hit).  Such an attack reads and writes nothing any other
+        // attack of the step reads or writes, so its place in the shuffled order does not matter.  kill_supply > 0
+        // would let a kill change the killer's hp, which a later hit on the killer reads: then nothing is isolated.
+        // (2) The entangled rest keeps its order: compacted in order, resolved below.
+        int nE = 0;
+        for (int base = 0; base < nA; base += nt) {
+            const int i = base + tid;
+            bool entangled = false;
+            if (i < nA) {
+                const int k = (int)(s_att[i] & 0xFFFF), v = s_aux[i];
+                bool iso = P.kill_supply == 0.0f && (s_scr0[k] & 0xFFFF) == 0;
+                if (iso && v >= 0) {
+                    const int cv = s_scr0[v];
+                    iso = (cv & 0xFFFF) == 1 && ((cv >> 16) == 0 || !(s_hp[v] - P.damage < 0.0f));
+                }
+                if (iso) one_attack(k, v, i);
+                entangled = !iso;
+            }
+            int tot;
+            const int p = block_scan_flag(entangled, s_misc + MISC_WARP, tot);
+            if (entangled) s_scr1[nE + p] = i;
+            nE += tot;
+        }
+        __syncthreads();
+        // Sequential semantics for the entangled attacks, executed by warp 0 in batches of 32 consecutive entries.
+        // An attack (k -> v) whose attacker is attacked by nobody else in the batch and whose victim
+        // neither is attacked by another lane nor attacks in this batch touches state no other lane of the
+        // batch reads or writes: those lanes run in parallel.  The rest ("complex") run one lane at a time
+        // in lane order, i.e. in the shuffled order; since the simple lanes commute with them the result is
+        // bit-identical to the one-by-one loop.
         if (tid < 32) {
             const int lane = tid;
-            for (int i0 = 0, bid = 1; i0 < nA; i0 += 32, bid++) {
-                const int i = i0 + lane;
-                const bool valid = i < nA;
+            for (int i0 = 0, bid = 1; i0 < nE; i0 += 32, bid++) {
+                const bool valid = i0 + lane < nE;
+                const int i = valid ? s_scr1[i0 + lane] : 0;
                 const int k = valid ? (int)(s_att[i] & 0xFFFF) : 0;
                 const int v = valid ? s_aux[i] : -1;
                 if (valid) s_tag_a[k] = (uint16_t)bid;
@@ -318,68 +388,77 @@ __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState
                 }
             }
         }
-        // ---- move targets (Map::do_move bounds test, Map.cc:326,466-468) + who moves, and when ----
+        __syncthreads();
+
+        // ---- ordered moves, first come first served (GridWorld.cc:631-672, Map::do_move Map.cc:324-369), resolved
+        //      without walking the list.  What mover m finds in its target cell at its turn depends only on
+        //        * what stands there before the move phase: nothing, a wall, or an agent o, and
+        //        * o's own turn j_o if o tries to leave (a mover staying put -- move (0, 0) -- never frees its cell):
+        //      movers with m < j_o find o still there; of those with m > j_o (or all, if the cell was empty) only the
+        //      FIRST can get the cell -- an atomicMin over list indices per cell -- and it does iff the cell was empty
+        //      or o really left, i.e. iff o won ITS target: a chain, followed by pointer jumping until every mover
+        //      knows.  Everybody else collides with whoever holds the cell at their turn (or, at a wall, does nothing).
+        //      Then all winners vacate, then enter.  (Model + exactness test: tests/test_parallel_resolve_model.py.)
         for (int m = tid; m < nM; m += nt) {
             const uint32_t ent = s_mv[m];
             const int k = ent & 0xFFFF, a = ent >> 16, p = s_pos[k];
             const int nx = pos_x(p) + P.move_dx[a], ny = pos_y(p) + P.move_dy[a];
-            s_mvt[m] = (nx < 0 || ny < 0 || nx + 1 >= W || ny + 1 >= H) ? -1 : pack_pos(nx, ny);
-            s_mvidx[k] = (uint16_t)(m + 1);
+            const bool cand = !(nx < 0 || ny < 0 || nx + 1 >= W || ny + 1 >= H) && !st_dead(s_state[k]);   // Map.cc:466-468
+            s_mvt[m] = cand ? ny * W + nx : -1;
+            if (cand && pack_pos(nx, ny) != p) s_mvidx[k] = (uint16_t)(m + 1);
         }
         __syncthreads();
-
-        // ---- ordered moves, first come first served (GridWorld.cc:631-672, Map::do_move Map.cc:324-369) ----
-        // Same batching as the attacks.  A mover is simple when its target cell is targeted by no other lane
-        // of the batch and is either free at batch start (it moves) or held by something that cannot have
-        // left by its turn -- a wall, an agent that does not move, moves in a later batch, or sits at a higher
-        // lane (it is blocked).  It is complex when another lane shares its target or the occupant moves at a
-        // lower lane of this batch; complex lanes run in lane order against the live grid, except that an
-        // occupant from a higher lane still blocks them (it has not moved yet at their turn).
-        if (tid < 32) {
-            const int lane = tid;
-            for (int i0 = 0; i0 < nM; i0 += 32) {
-                const int m = i0 + lane;
-                const bool valid = m < nM;
-                const int k = valid ? (int)(s_mv[m] & 0xFFFF) : 0;
-                const int tgt = valid ? s_mvt[m] : -1;
-                const bool cand = valid && tgt >= 0 && !st_dead(s_state[k]);
-                const int tc = cand ? pos_y(tgt) * W + pos_x(tgt) : -1;
-                const int self = 2 + k;
-                const int occ = cand ? (int)s_grid[tc] : 1;
-                const unsigned same_t = __match_any_sync(0xFFFFFFFFu, cand ? tc : -1 - lane);
-                int occ_lane = 64;                      // lane at which the occupant moves (64 = it cannot leave in time)
-                if (cand && occ >= 2 && occ != self) {
+        for (int m = tid; m < nM; m += nt) {
+            const int tc = s_mvt[m], k = (int)(s_mv[m] & 0xFFFF);
+            int res = MV_FAIL, dep = -1;
+            if (tc >= 0) {
+                const int occ = s_grid[tc];
+                if (occ == 0) res = MV_WAIT;                                   // contender for an empty cell
+                else if (occ >= 2 && occ != 2 + k) {
                     const int j = (int)s_mvidx[occ - 2] - 1;
-                    if (j >= i0 && j < i0 + 32) occ_lane = j - i0;
-                }
-                const bool free0 = occ == 0 || occ == self;
-                const bool complex = cand && (__popc(same_t) > 1 || (!free0 && occ_lane < lane));
-                auto commit_move = [&]() {
-                    const int p = s_pos[k];
-                    s_grid[pos_y(p) * W + pos_x(p)] = 0;
-                    s_grid[tc] = (uint16_t)self;
-                    s_pos[k] = tgt;
-                };
-                if (cand && !complex) {
-                    if (free0) commit_move();
-                    else if (occ >= 2) s_state[k] = st_with_op(s_state[k], OP_COLLIDE);   // no reward effect in battle
-                }
-                __syncwarp();
-                unsigned todo = __ballot_sync(0xFFFFFFFFu, complex);
-                while (todo) {
-                    const int l = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    if (lane == l) {
-                        const int now = s_grid[tc];
-                        const bool held_by_later = !free0 && occ_lane > lane;   // occupant has not moved yet at this turn
-                        if (occ == 1) { /* wall: never free, and no collide object (Map.cc:498-513) */ }
-                        else if (!held_by_later && (now == 0 || now == self)) commit_move();
-                        else s_state[k] = st_with_op(s_state[k], OP_COLLIDE);
-                    }
-                    __syncwarp();
+                    if (j >= 0 && j < m) { res = MV_WAIT; dep = j; }           // the occupant had its turn before m
+                    else s_state[k] = st_with_op(s_state[k], OP_COLLIDE);      // it is still there (no reward effect in battle)
+                }                                                              // own cell: stays; wall: nothing (Map.cc:498-513)
+                if (res == MV_WAIT) atomicMin(&s_claim[tc], (uint32_t)m);
+            }
+            s_scr0[m] = res; s_scr1[m] = dep;
+        }
+        __syncthreads();
+        for (int m = tid; m < nM; m += nt) {
+            if (s_scr0[m] != MV_WAIT) continue;
+            if (s_claim[s_mvt[m]] != (uint32_t)m) {                            // an earlier contender is entitled to the cell
+                s_scr0[m] = MV_FAIL;
+                const int k = (int)(s_mv[m] & 0xFFFF);
+                s_state[k] = st_with_op(s_state[k], OP_COLLIDE);
+            } else if (s_scr1[m] < 0) s_scr0[m] = MV_OK;
+        }
+        for (;;) {
+            __syncthreads();
+            if (tid == 0) s_misc[MISC_FLAG] = 0;
+            __syncthreads();
+            bool waiting = false;
+            for (int m = tid; m < nM; m += nt) {
+                if (s_scr0[m] != MV_WAIT) continue;
+                const int d = s_scr1[m], r = s_scr0[d];        // a racing writer can only turn WAIT into the final value
+                if (r == MV_WAIT) { s_scr1[m] = s_scr1[d]; waiting = true; }   // same fate as the occupant's occupant
+                else {
+                    s_scr0[m] = r;
+                    if (r == MV_FAIL) { const int k = (int)(s_mv[m] & 0xFFFF); s_state[k] = st_with_op(s_state[k], OP_COLLIDE); }
                 }
             }
+            if (waiting) s_misc[MISC_FLAG] = 1;
+            __syncthreads();
+            if (!s_misc[MISC_FLAG]) break;
         }
+        for (int m = tid; m < nM; m += nt)
+            if (s_scr0[m] == MV_OK) { const int p = s_pos[s_mv[m] & 0xFFFF]; s_grid[pos_y(p) * W + pos_x(p)] = 0; }
+        __syncthreads();
+        for (int m = tid; m < nM; m += nt)
+            if (s_scr0[m] == MV_OK) {
+                const int k = (int)(s_mv[m] & 0xFFFF), tc = s_mvt[m];
+                s_grid[tc] = (uint16_t)(2 + k);
+                s_pos[k] = pack_pos(tc % W, tc / W);
+            }
         __syncthreads();
 
         // ---- reward rules (calc_reward GridWorld.cc:744-758): for the battle rule set an agent whose
@@ -408,22 +487,24 @@ __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState
             }
         }
         if (io.mean_action) {
-            // 21-bin one-hot mean with ballots: warp g counts group g, lane b owns bin b
-            const int w = tid >> 5, lane = tid & 31;
-            for (int g = w; g < kGroups; g += (nt >> 5)) {
-                const int ng = g ? n1 : n0;
-                int cnt = 0;
-                for (int base = 0; base < ng; base += 32) {
-                    const int i = base + lane;
-                    const int a = i < ng ? (int)st_act(s_state[g * cap + i]) : -1;
-                    for (int b = 0; b < n_action; b++) {
-                        const int c = __popc(__ballot_sync(0xFFFFFFFFu, a == b));
-                        if (lane == b) cnt += c;
-                    }
-                }
-                if (lane < n_action)
-                    io.mean_action[((size_t)e * 2 + g) * n_action + lane] =
-                        ng > 0 ? __fdiv_rn((float)cnt, (float)ng) : 0.0f;
+            // one-hot mean = action histogram / n: lanes of a warp holding the same (group, action) elect one of them
+            // to add their count to the shared histogram
+            if (tid < 64) s_misc[MISC_HIST + tid] = 0;
+            __syncthreads();
+            for (int base = 0; base < 2 * cap; base += nt) {
+                const int s = base + tid, g = s >= cap, i = s - g * cap;
+                const bool valid = s < 2 * cap && i < (g ? n1 : n0);
+                const int a = valid ? (int)st_act(s_state[s]) : n_action;
+                const int key = (valid && a < n_action) ? g * 32 + a : -1 - (int)(tid & 31);
+                const unsigned peers = __match_any_sync(0xFFFFFFFFu, key);
+                if (key >= 0 && (int)(tid & 31) == __ffs(peers) - 1) atomicAdd(&s_misc[MISC_HIST + key], __popc(peers));
+            }
+            __syncthreads();
+            if (tid < 64) {
+                const int g = tid >> 5, b = tid & 31, ng = g ? n1 : n0;
+                if (b < n_action)
+                    io.mean_action[((size_t)e * 2 + g) * n_action + b] =
+                        ng > 0 ? __fdiv_rn((float)s_misc[MISC_HIST + tid], (float)ng) : 0.0f;
             }
         }
     }
@@ -694,7 +775,11 @@ k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO i
             if (tid == 0) bulk_wait_read<1>();
             __syncthreads();
             int self_new = -1;
+            #ifdef MF_PROFILE_BUILD
             if (warp < cn && !(io.debug & 1)) {
+#else
+            if (warp < cn) {
+#endif
                 const int4 rec = s_rec[c0 - a_begin + warp];
                 const int p = rec.x, ax = pos_x(p), ay = pos_y(p);
                 const int id = rec.y;

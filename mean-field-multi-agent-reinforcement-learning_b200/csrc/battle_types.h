@@ -27,6 +27,7 @@ constexpr int kGroups = 2;
 constexpr int kMaxMoves = 32;    // |move range| (13 for speed 2)
 constexpr int kMaxAttacks = 32;  // |attack range| (8 for radius 1.5)
 constexpr int kMaxActions = 64;
+constexpr int kObsTicketRing = 8;   // k_obs launches of one engine that may be in flight at once
 constexpr int kObsDiscSlots = 128;   // 4 passes x 32 lanes cover the <= 113 in-disc cells of the 13x13 window
 // battle observation geometry (view disc radius 6 -> 13x13 window, 1 wall + 2 x (has, hp, minimap) channels)
 constexpr int kView = 13, kViewCells = 169, kChan = 7, kViewRow = kViewCells * kChan;   // 1183 floats
@@ -59,6 +60,8 @@ struct BattleParams {
     int wall_stride;        // H*W, or 0 when every env shares one wall map
     int rng_mode;
     int max_steps;          // auto-reset horizon (0 = none)
+    int move_bands;         // 0, or the reference's NUM_SEP_BUFFER when W*H > 99*99 ("large map mode", GridWorld.cc:79-88):
+    int band_width;         //   moves run x-band by x-band, then the band-boundary buffer (GridWorld.cc:443-463,662-672)
     uint32_t seed;
     float hp, damage, step_recover, kill_supply;
     float step_reward, kill_reward, dead_penalty, attack_penalty;
@@ -77,7 +80,7 @@ struct BattleState {   // device pointers
     uint16_t *grid_template;           // [(H+12)*(W+12)] padded occupancy grid holding only the walls (kind << 14)
     uint8_t *mini_lut;                 // [W] x / scale_w, then [H] (y / scale_h) * view: minimap cell of a position
     unsigned long long *agent_steps;   // [E] running count of agents taken through a step (statistic)
-    int32_t *obs_ticket;               // [2] k_obs work distribution: next item, CTAs finished (rewound by the last CTA)
+    int32_t *obs_ticket;               // [2] of this launch (ring of kObsTicketRing pairs): next item, CTAs finished (rewound by the last CTA)
     // episode template for auto-reset
     int32_t *init_pos; int32_t *init_num;   // [2][cap], [2]
 };
@@ -103,7 +106,7 @@ struct ObsIO {
     int group_mask;  // which groups to produce
     int tile_agents; // agents per CTA tile
     int tiles_per_group;
-    int debug;       // profiling experiments only (MFMARL_OBS_DEBUG): 1 = skip row composition
+    int debug;       // only read by -DMF_PROFILE_BUILD binaries (profiling experiments): 1 = skip row composition
 };
 
 }  // namespace mfmarl

@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 
 #include "battle_kernels.cuh"
 
@@ -51,10 +53,35 @@ CircleRange::CircleRange(float radius, float inner_radius, int parity) {
         }
 }
 
+// E == 1, device state is newer than the template: pull the full records, patch, push back.
+struct Engine::LateRecords {
+    std::vector<int32_t> pos, id; std::vector<float> hp, nr, lr; std::vector<uint32_t> state;
+    int num[2], dead[2];
+};
+
+
 // ---------------------------------------------------------------------------------------------
 // construction
 // ---------------------------------------------------------------------------------------------
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-function, per-device setting shared by every engine of the
+// process: it is only ever RAISED, so that an engine of a small geometry cannot pull it below what a larger engine
+// (created earlier, launching later) still needs.
+static void raise_dynamic_smem(const void *func, int bytes, int device) {
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, int> granted;
+    std::lock_guard<std::mutex> lock(mu);
+    int &cur = granted[std::make_pair(func, device)];
+    if (bytes <= cur) return;
+    if (bytes > 227 * 1024)
+        throw Fatal("geometry needs " + std::to_string(bytes) + " B of shared memory per CTA (limit 232448): map or capacity too large");
+    MF_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    // the same L1 / shared-memory split for k_obs and k_step: the two kernels alternate every step (and overlap on two
+    // streams), and an SM has to drain before it can change its carve-out
+    MF_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    cur = bytes;
+}
 
 Engine::Engine(const EngineConfig &cfg) : cfg_(cfg) {
     int ndev = 0;
@@ -75,8 +102,8 @@ Engine::Engine(const EngineConfig &cfg) : cfg_(cfg) {
     if (view_.width != kView)
         throw Fatal("view range " + std::to_string(view_.width) + "x" + std::to_string(view_.width) +
                     " unsupported: the observation kernel is specialised for the 13x13 battle view");
-    if (move_.count > kMaxMoves || attack_.count > kMaxAttacks)
-        throw Fatal("move/attack range too large");
+    if (move_.count > kMaxMoves || attack_.count > kMaxAttacks || move_.count + attack_.count > 32)
+        throw Fatal("move/attack range too large (at most 32 actions)");
 
     P_.E = cfg.n_envs; P_.W = cfg.width; P_.H = cfg.height;
     P_.env_base = cfg.env_base;
@@ -88,6 +115,11 @@ Engine::Engine(const EngineConfig &cfg) : cfg_(cfg) {
     P_.scale_h = (cfg.height + kView - 1) / kView;
     P_.wall_stride = 0;
     P_.rng_mode = cfg.rng_mode; P_.max_steps = cfg.max_steps; P_.seed = cfg.seed;
+    P_.move_bands = 0; P_.band_width = cfg.width;
+    if (cfg.width * cfg.height > 99 * 99) {                       // GridWorld.cc:79-88 "large_map_mode"
+        P_.move_bands = cfg.width * cfg.height > 1000 * 1000 ? 16 : 8;
+        P_.band_width = (cfg.width + P_.move_bands - 1) / P_.move_bands;   // GridWorld.cc:439
+    }
     P_.hp = cfg.type.hp; P_.damage = cfg.type.damage; P_.step_recover = cfg.type.step_recover;
     P_.kill_supply = cfg.type.kill_supply; P_.step_reward = cfg.type.step_reward;
     P_.kill_reward = cfg.type.kill_reward; P_.dead_penalty = cfg.type.dead_penalty;
@@ -139,14 +171,16 @@ Engine::Engine(const EngineConfig &cfg) : cfg_(cfg) {
     }
     MF_CUDA(cudaMalloc(&S_.agent_steps, E * sizeof(unsigned long long)));
     MF_CUDA(cudaMemset(S_.agent_steps, 0, E * sizeof(unsigned long long)));
-    MF_CUDA(cudaMalloc(&S_.obs_ticket, 2 * sizeof(int32_t)));
-    MF_CUDA(cudaMemset(S_.obs_ticket, 0, 2 * sizeof(int32_t)));
+    MF_CUDA(cudaMalloc(&S_.obs_ticket, 2 * kObsTicketRing * sizeof(int32_t)));
+    MF_CUDA(cudaMemset(S_.obs_ticket, 0, 2 * kObsTicketRing * sizeof(int32_t)));
     MF_CUDA(cudaMemset(S_.num, 0, E * 2 * sizeof(int32_t)));
     MF_CUDA(cudaMemset(S_.dead_ct, 0, E * 2 * sizeof(int32_t)));
     MF_CUDA(cudaMemset(S_.step_ct, 0, E * sizeof(int32_t)));
     MF_CUDA(cudaMemset(S_.id_counter, 0, E * sizeof(int32_t)));
     h_num_.assign(E * 2, 0);
+#ifdef MF_PROFILE_BUILD
     { const char *dbg = getenv("MFMARL_OBS_DEBUG"); obs_debug_ = dbg ? atoi(dbg) : 0; }
+#endif
     set_seed(cfg.seed);   // seed 0 -> minstd state 1, as GridWorld.cc:31 random_engine.seed(0)
     alloc_state(std::max(4, round_up(cfg.capacity, 4)));
     reset();
@@ -242,17 +276,11 @@ int Engine::add_agents(int group, int n, const int *xs, const int *ys) {
     return added;
 }
 
-// E == 1, device state is newer than the template: pull the full records, patch, push back.
-struct LateRecords {
-    std::vector<int32_t> pos, id; std::vector<float> hp, nr, lr; std::vector<uint32_t> state;
-    int num[2], dead[2];
-};
-static LateRecords g_late;   // only touched between sync_down and sync_up of one add_agents call
-
 void Engine::late_add_sync_down() {
     MF_CUDA(cudaDeviceSynchronize());
     const size_t n = slots();
-    LateRecords &R = g_late;
+    if (!late_) late_.reset(new LateRecords());
+    LateRecords &R = *late_;
     R.pos.resize(n); R.id.resize(n); R.hp.resize(n); R.nr.resize(n); R.lr.resize(n); R.state.resize(n);
     MF_CUDA(cudaMemcpy(R.pos.data(), S_.pos, n * 4, cudaMemcpyDeviceToHost));
     MF_CUDA(cudaMemcpy(R.id.data(), S_.id, n * 4, cudaMemcpyDeviceToHost));
@@ -274,7 +302,7 @@ void Engine::late_add_sync_down() {
 }
 
 void Engine::late_add_sync_up() {
-    LateRecords &R = g_late;
+    LateRecords &R = *late_;
     const int old_cap = P_.cap;
     int need = 0;
     for (int g = 0; g < kGroups; g++) need = std::max(need, R.num[g] + (int)h_tpos_[g].size());
@@ -359,6 +387,9 @@ void Engine::commit(cudaStream_t st) {
     MF_CUDA(cudaStreamSynchronize(st));
     k_place<<<P_.E, 128, 0, st>>>(P_, S_);
     MF_CUDA(cudaGetLastError());
+    // a placement is a per-episode event: wait for it, so that whatever stream the next launch uses (the legacy
+    // stream of mfb_query, a non-blocking side stream of the caller) it is ordered after the new state
+    MF_CUDA(cudaStreamSynchronize(st));
     for (int e = 0; e < P_.E; e++) { h_num_[e * 2] = num[0]; h_num_[e * 2 + 1] = num[1]; }
     placement_dirty_ = false;
     stepped_ = false;
@@ -392,9 +423,8 @@ void Engine::observe_groups(float *const d_view[kGroups], float *const d_feature
     io.env_stride = env_stride; io.group_mask = group_mask;
     io.debug = obs_debug_;
     const ObsSmem L = obs_smem_layout(P_.W, P_.H, P_.cap);
+    raise_dynamic_smem((const void *)k_obs, L.total, device_);
     if (obs_attr_ != L.total) {
-        MF_CUDA(cudaFuncSetAttribute(k_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-        MF_CUDA(cudaFuncSetAttribute(k_obs, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         MF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&obs_ctas_per_sm_, k_obs, kObsThreads, L.total));
         obs_attr_ = L.total;
     }
@@ -415,20 +445,18 @@ void Engine::observe_groups(float *const d_view[kGroups], float *const d_feature
     io.tiles_per_group = (P_.cap + io.tile_agents - 1) / io.tile_agents;
     const size_t items = (size_t)P_.E * (group_mask == 3 ? 2 : 1) * io.tiles_per_group;
     const unsigned grid = (unsigned)std::min<size_t>(items, ctas);
-    k_obs<<<grid, kObsThreads, L.total, st>>>(P_, S_, io);
+    // every launch takes its own ticket pair from a small ring, so observe launches of one engine may overlap on
+    // different streams (the last CTA of a launch rewinds its pair)
+    BattleState S = S_;
+    S.obs_ticket += 2 * (obs_launches_++ % kObsTicketRing);
+    k_obs<<<grid, kObsThreads, L.total, st>>>(P_, S, io);
     MF_CUDA(cudaGetLastError());
 }
 
 void Engine::step(const StepIO &io, cudaStream_t st) {
     commit(st);
     const StepSmem L = step_smem_layout(P_.W, P_.H, P_.cap);
-    if (step_attr_ != L.total) {
-        MF_CUDA(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-        // the same L1 / shared-memory split as k_obs: the two kernels alternate every step (and overlap on two streams),
-        // and an SM has to drain before it can change its carve-out
-        MF_CUDA(cudaFuncSetAttribute(k_step, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        step_attr_ = L.total;
-    }
+    raise_dynamic_smem((const void *)k_step, L.total, device_);
     int threads = cfg_.step_threads > 0 ? cfg_.step_threads : std::min(1024, std::max(64, P_.cap));
     // a few environments cannot fill the GPU anyway: wider CTAs shorten the parallel phases (grid load, lists, scans)
     if (cfg_.step_threads <= 0 && P_.E <= n_sm_ / 2) threads = std::max(threads, 256);

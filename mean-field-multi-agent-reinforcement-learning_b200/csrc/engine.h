@@ -5,6 +5,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -102,13 +103,17 @@ private:
     void late_add_sync_down();   // E == 1 only: device state -> host records
     void late_add_sync_up();
 
+    struct LateRecords;                    // scratch of one late add_agents call (E == 1)
+    std::unique_ptr<LateRecords> late_;
+
     EngineConfig cfg_;
     BattleParams P_{};
     BattleState S_{};
     CircleRange view_, attack_, move_;
     int device_ = 0;
     int n_sm_ = 148;
-    int obs_attr_ = -1, step_attr_ = -1;   // dynamic-smem opt-in already set for this size
+    int obs_attr_ = -1;                    // shared-memory size the occupancy below was queried for
+    unsigned obs_launches_ = 0;            // k_obs launches so far (picks the ticket pair)
     int obs_ctas_per_sm_ = 2;              // resident k_obs CTAs per SM at that size (occupancy query)
     int obs_debug_ = 0;                    // MFMARL_OBS_DEBUG at construction (profiling experiments only)
 

@@ -647,11 +647,13 @@ int gridworld_add_agents(EnvHandle game, GroupHandle group, int n, const char *m
         }
         E.push_rng0(rs);
         if (group != -1) { E.commit(g->st); }
+        g->invalidate();                      // the host mirror predates the new agents
         return 0;
     } else throw Fatal(std::string("unsupported method in GridWorld::add_agents : ") + method);
 
     if (group == -1) E.add_walls((int)xs.size(), xs.data(), ys.data());
     else { g->type_of(group); E.add_agents(group, (int)xs.size(), xs.data(), ys.data()); }
+    g->invalidate();                          // rows of the new agents are not in the host mirror yet (also after a late add)
     API_END("gridworld_add_agents")
 }
 

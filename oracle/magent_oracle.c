@@ -36,7 +36,7 @@ typedef struct { /* Map.h:23-29 plus the split-out channel id (Map.h:74) */
     int channel_id;
 } mo_slot;
 
-typedef struct { mo_agent *agent; int action; } mo_act;
+typedef struct { mo_agent *agent; int action; int band; } mo_act;
 
 typedef struct {
     mo_agent **agents;
@@ -265,18 +265,30 @@ void mo_get_observation(mo_env *e, int group, float *view, float *feature) {
     free(minimap);
 }
 
-/* ---- GridWorld.cc:481-495 (small-map branch) ------------------------------------------------ */
+/* ---- GridWorld.cc:430-496: small-map branch :481-495; on a large map (w*h > 99*99, :79-88) a move is filed by
+ * the x-band of its agent (:443-455): NUM_SEP_BUFFER bands of `bandwidth` columns, or the boundary buffer when the
+ * agent stands within 4 columns of a band edge.  The band is kept next to the move; step() runs band 0 ..
+ * NUM_SEP-1, then the boundary buffer (:662-672), each in call order. -------------------------------------------- */
+static int move_band(const mo_env *e, int x) {
+    if (e->w * e->h <= 99 * 99) return 0;
+    const int nsep = e->w * e->h > 1000 * 1000 ? 16 : 8;
+    const int bandwidth = (e->w + nsep - 1) / nsep;
+    const int xr = x % bandwidth;
+    return (xr < 4 || xr > bandwidth - 4) ? nsep : x / bandwidth;
+}
 static void push(mo_act **buf, int *n, int *cap, mo_agent *a, int action) {
     if (*n == *cap) { *cap = *cap ? 2 * *cap : 256; *buf = (mo_act *)realloc(*buf, sizeof(mo_act) * *cap); }
-    (*buf)[*n].agent = a; (*buf)[*n].action = action; (*n)++;
+    (*buf)[*n].agent = a; (*buf)[*n].action = action; (*buf)[*n].band = 0; (*n)++;
 }
 void mo_set_action(mo_env *e, int group, const int *actions) {
     mo_group *g = &e->groups[group];
     for (int i = 0; i < g->n; i++) {
         mo_agent *a = g->agents[i];
         a->last_action = actions[i];
-        if (actions[i] < e->attack_base) push(&e->move_buf, &e->n_move, &e->cap_move, a, actions[i]);
-        else push(&e->attack_buf, &e->n_attack, &e->cap_attack, a, actions[i] - e->attack_base);
+        if (actions[i] < e->attack_base) {
+            push(&e->move_buf, &e->n_move, &e->cap_move, a, actions[i]);
+            e->move_buf[e->n_move - 1].band = move_band(e, a->x);
+        } else push(&e->attack_buf, &e->n_attack, &e->cap_attack, a, actions[i] - e->attack_base);
     }
 }
 
@@ -355,10 +367,12 @@ int mo_step(mo_env *e) {
         gr->dead_ct += starve_ct;
     }
 
-    /* moves in set_action order (:631-672 + Map::do_move Map.cc:324-369) */
+    /* moves in set_action order (:631-672 + Map::do_move Map.cc:324-369); band by band on a large map */
+    const int n_band = e->w * e->h <= 99 * 99 ? 1 : (e->w * e->h > 1000 * 1000 ? 17 : 9);
+    for (int band = 0; band < n_band; band++)
     for (int j = 0; j < e->n_move; j++) {
         mo_agent *a = e->move_buf[j].agent;
-        if (a->dead) continue;
+        if (e->move_buf[j].band != band || a->dead) continue;
         int nx = a->x + e->move.dx[e->move_buf[j].action], ny = a->y + e->move.dy[e->move_buf[j].action];
         if (is_blank(e, nx, ny, a)) {
             mo_slot *olds = &e->slots[a->y * e->w + a->x];

@@ -136,3 +136,60 @@ def test_global_minimap_and_getters_match_the_reference_engine():
                 assert np.array_equal(ref.get_alive(g), cu.get_alive(g)) and ref.get_num(g) == cu.get_num(g)
         ref.clear_dead(); cu.clear_dead()
     assert ref.get_num(0) + ref.get_num(1) < 128
+
+
+@pytest.mark.parametrize("size", [100, 104])
+def test_large_map_mode_moves_run_band_by_band(size):
+    """W*H > 99*99: the reference resolves moves x-band by x-band, then the band-boundary buffer
+    (GridWorld.cc:79-88,443-463,662-672); k_step builds its move list in that order."""
+    from scenarios import block_positions
+    ora, cu = OracleEngine(size), CudaEngine(size)
+    left, right = block_positions(20, 30, 28, 20, stride=1), block_positions(size - 50, 30, 28, 20, stride=1)
+    setup_pair([ora, cu], left, right)
+    st = run_lockstep(ora, cu, steps=50, seed=size, stream="fight", check_obs_every=10)
+    assert st["deaths"] > 20, st
+
+
+def test_queries_after_a_late_or_random_add_see_the_new_agents():
+    """add_agents after a step (late path) and method="random" rewrite the device state: the host mirror that answers
+    get_pos / get_agent_id / get_observation must be refreshed (runtime_api.cu gridworld_add_agents)."""
+    ora, cu = OracleEngine(40), CudaEngine(40)
+    left, right = generate_map_positions(40)
+    setup_pair([ora, cu], left[:20], right[:20])
+    run_lockstep(ora, cu, steps=5, seed=1, stream="fight")
+    for g in range(2):                         # warm the mirror, then add: the next getters must not answer from it
+        cu.get_pos(g); cu.get_observation(g)
+    extra0 = np.array([[30, 3, 0], [31, 3, 0], [32, 3, 0]], np.int32)
+    extra1 = np.array([[30, 36, 0], [31, 36, 0]], np.int32)
+    for eng in (ora, cu):
+        eng.add_agents(0, extra0); eng.add_agents(1, extra1)
+    for g in range(2):
+        assert ora.get_num(g) == cu.get_num(g)
+        assert_same("pos", ora.get_pos(g), cu.get_pos(g), 0)
+        assert_same("id", ora.get_agent_id(g), cu.get_agent_id(g), 0)
+        va, fa = ora.get_observation(g); vb, fb = cu.get_observation(g)
+        assert_same("view", va, vb, 0); assert_same("feature", fa, fb, 0)
+    run_lockstep(ora, cu, steps=20, seed=2, stream="fight")
+    # method="random": positions come from the engine RNG; a getter between two random adds must see the first one
+    cu2 = CudaEngine(40)
+    cu2.reset()
+    cu2.env.add_agents(cu2.h[0], method="random", n=10)
+    p0 = cu2.get_pos(0).copy()
+    assert len(p0) == 10 and (p0 > 0).all()
+    cu2.env.add_agents(cu2.h[1], method="random", n=7)
+    p1 = cu2.get_pos(1)
+    assert len(p1) == 7 and (p1 > 0).all()
+    assert len({tuple(p) for p in np.concatenate([p0, p1])}) == 17
+
+
+def test_two_engine_shapes_interleaved_in_one_process():
+    """cudaFuncAttributeMaxDynamicSharedMemorySize is per function and process wide: a small engine created after a
+    large one must not lower the limit the large one still needs (engine.cu)."""
+    big_o, big = OracleEngine(80), CudaEngine(80)
+    setup_pair([big_o, big], *c4_positions())
+    run_lockstep(big_o, big, steps=3, seed=5, stream="fight", check_obs_every=1)
+    small_o, small = OracleEngine(40), CudaEngine(40)
+    setup_pair([small_o, small], *generate_map_positions(40))
+    run_lockstep(small_o, small, steps=3, seed=6, stream="fight", check_obs_every=1)
+    run_lockstep(big_o, big, steps=3, seed=7, stream="fight", check_obs_every=1)
+    run_lockstep(small_o, small, steps=3, seed=8, stream="fight", check_obs_every=1)

@@ -52,27 +52,87 @@ def test_fp64_trajectory_matches_oracle_exactly(L, T):
         Q[...] = new_Q
 
 
-def test_fp32_step_within_1e6_of_the_fp64_reference():
-    """Production precision: every single step, started from the oracle's state, gives the oracle's
-    actions (except draws within 1e-5 of the threshold) and Q within 1e-6 relative (north_star)."""
+def _neighbourhood(mask):
+    """sites whose reward (hence Q update) can see a site of `mask`: the site itself and its 4 torus neighbours"""
+    return mask | np.roll(mask, 1, -2) | np.roll(mask, -1, -2) | np.roll(mask, 1, -1) | np.roll(mask, -1, -1)
+
+
+@pytest.mark.parametrize("L,B,mode", [(20, 2, "stream"), (256, 2, "stream"), (256, 2, "0"), (256, 2, "4"), (256, 2, "8"),
+                                        (64, 3, "8"), (128, 2, "8")])
+def test_fp32_every_sweep_from_the_oracle_state(L, B, mode, monkeypatch, capsys):
+    """Production precision, production kernels (BASELINE config 5 shape, main_MFQ_Ising.py:55-67,105-134): 20 sweeps,
+    each started from the oracle's state and driven by the same injected uniforms.  The fp32 decision
+    u (1 + e) >= 1 uses ex2.approx, so a draw closer than 1e-5 to the fp64 threshold may legitimately fall on the other
+    side: such flips are COUNTED and reported, every flip must be such a draw, and Q is checked to 1e-6 relative
+    on every site whose update cannot see a flipped spin -- unconditionally.
+    mode: "stream" = mfi_step (K6); "0"/"4"/"8" = mfi_run (K6r) generic / 4 / 8 rows per thread, one sweep per launch."""
     from mfmarl_b200 import IsingMFQ
-    B, L, T = 2, 20, 0.8
-    rng = np.random.RandomState(3)
+    if mode != "stream":
+        monkeypatch.setenv("MFMARL_ISING_RPT", mode)
+    T, sweeps = 0.8, 20
+    rng = np.random.RandomState(L + 3)
     spins = rng.randint(0, 2, size=(B, L, L)).astype(np.int8)
     Q = np.zeros((B, 5, L * L, 2))
     m = IsingMFQ(B, L, dtype=torch.float32, spins=torch.from_numpy(spins))
-    for t in range(60):
+    flips = near = checked = 0
+    for t in range(sweeps):
         u = rng.random_sample((B, L * L)).astype(np.float32)
         m.spins.copy_(torch.from_numpy(spins)); m.Q.copy_(torch.from_numpy(Q.astype(np.float32)))
         Q32 = Q.astype(np.float32).astype(np.float64)     # the state the kernel actually starts from
-        m.step(T, uniforms=torch.from_numpy(u).cuda())
+        ud = torch.from_numpy(u).cuda()
+        if mode == "stream":
+            m.step(T, uniforms=ud)
+        else:
+            m.run([T], uniforms=ud.unsqueeze(0).contiguous(), resident=True)
         new_spins, new_Q, info = ising_oracle.step(spins, Q32, T, 0.1, u.astype(np.float64))
-        safe = (np.abs(u - info["threshold"]) > 1e-5).reshape(B, L, L)
+        close = (np.abs(u - info["threshold"]) < 1e-5).reshape(B, L, L)
         got = m.spins.cpu().numpy()
-        assert np.array_equal(got[safe], new_spins[safe])
-        if np.array_equal(got, new_spins):
-            np.testing.assert_allclose(m.Q.cpu().numpy(), new_Q, rtol=1e-6, atol=1e-7)
+        flipped = got != new_spins
+        assert not (flipped & ~close).any(), "sweep %d: an action differs although the draw is not near the threshold" % t
+        flips += int(flipped.sum()); near += int(close.sum())
+        ok = ~_neighbourhood(flipped).reshape(B, 1, L * L, 1)
+        ok = np.broadcast_to(ok, new_Q.shape)
+        np.testing.assert_allclose(m.Q.cpu().numpy()[ok], new_Q[ok], rtol=1e-6, atol=1e-7)
+        checked += int(ok.sum())
         spins, Q = new_spins.astype(np.int8), new_Q
+    with capsys.disabled():
+        print("\n[ising fp32 %s L=%d] %d sweeps x %d sites: %d draws within 1e-5 of the threshold, %d flipped; "
+              "Q checked at 1e-6 on %d entries" % (mode, L, sweeps, B * L * L, near, flips, checked))
+    assert flips <= near
+    assert flips <= max(4, near // 2)       # the fp32 decision is far more accurate than the 1e-5 window
+
+
+@pytest.mark.parametrize("L,B,mode", [(256, 2, "8"), (256, 2, "4"), (256, 2, "0"), (64, 2, "8"), (20, 3, "")])
+def test_fp32_resident_run_of_20_sweeps_follows_the_oracle_trajectory(L, B, mode, monkeypatch, capsys):
+    """K = 20 sweeps in ONE launch of the resident kernel against the fp64 oracle trajectory.  The uniforms are fixed
+    up front: the oracle walks its own trajectory and every draw that comes closer than 1e-5 to its threshold is
+    moved 1e-3 away (counted), so the two trajectories cannot part on a rounding tie.  Then spins and per-sweep up
+    counts must be EQUAL and Q within 1e-6 relative everywhere, with no exception."""
+    from mfmarl_b200 import IsingMFQ
+    if mode:
+        monkeypatch.setenv("MFMARL_ISING_RPT", mode)
+    T, K = 0.8, 20
+    rng = np.random.RandomState(L + 11)
+    spins0 = rng.randint(0, 2, size=(B, L, L)).astype(np.int8)
+    spins, Q = spins0.copy(), np.zeros((B, 5, L * L, 2))
+    us, ups, moved = [], [], 0
+    for k in range(K):
+        u = rng.random_sample((B, L * L)).astype(np.float32)
+        thr = ising_oracle.step(spins, Q, T, 0.1, u.astype(np.float64))[2]["threshold"]
+        close = np.abs(u - thr) < 1e-5
+        u = np.where(close, np.where(thr < 0.5, thr + 1e-3, thr - 1e-3), u).astype(np.float32)
+        moved += int(close.sum())
+        spins, Q, info = ising_oracle.step(spins, Q, T, 0.1, u.astype(np.float64))
+        assert np.abs(u - info["threshold"]).min() > 1e-5
+        us.append(u); ups.append(info["n_up"])
+    m = IsingMFQ(B, L, dtype=torch.float32, spins=torch.from_numpy(spins0))
+    n_up, _ = m.run([T] * K, uniforms=torch.from_numpy(np.stack(us)).cuda().contiguous(), resident=True)
+    assert np.array_equal(n_up.cpu().numpy(), np.stack(ups))
+    assert np.array_equal(m.spins.cpu().numpy(), spins)
+    np.testing.assert_allclose(m.Q.cpu().numpy(), Q, rtol=1e-6, atol=1e-7)
+    with capsys.disabled():
+        print("\n[ising fp32 resident %r L=%d] %d sweeps in one launch: spins equal, Q within 1e-6 on all %d entries "
+              "(%d near-threshold draws moved)" % (mode, L, K, Q.size, moved))
 
 
 def test_act_rate_mask_and_lr():

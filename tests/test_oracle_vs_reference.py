@@ -93,3 +93,16 @@ def test_mean_info_matches():
             assert_same("mean_info", A.get_mean_info(g), B.get_mean_info(g), s)
 
     run_lockstep(ref, ora, steps=30, seed=2, stream="fight", check_obs_every=0, on_step=check)
+
+
+@pytest.mark.parametrize("size", [100, 104])
+def test_large_map_mode_moves_run_band_by_band(size):
+    """W*H > 99*99 switches the reference to large_map_mode (GridWorld.cc:79-88): moves are filed into x-band
+    buffers at set_action (:443-463) and resolved band by band, then the boundary buffer (:662-672) -- a different
+    collision order than plain set_action order.  Dense blocks that straddle several bands, crowded fight stream."""
+    from scenarios import block_positions
+    ref, ora = RefEngine(size), OracleEngine(size)
+    left, right = block_positions(20, 30, 28, 20, stride=1), block_positions(size - 50, 30, 28, 20, stride=1)
+    setup_pair([ref, ora], left, right)
+    st = run_lockstep(ref, ora, steps=50, seed=size, stream="fight", check_obs_every=10)
+    assert st["deaths"] > 20, st
