@@ -36,6 +36,8 @@ typedef struct mfb_config {
     int device;            /* CUDA device ordinal, -1 = current                                      */
     int step_threads;      /* 0 = auto                                                               */
     int obs_tile_agents;   /* agents per observation CTA, 0 = auto: clamp(capacity, 64, 256)         */
+    int obs_record;        /* per-env observation record kept by k_step for k_obs: -1 = auto (on for
+                              capacity >= 256), 0 = off, 1 = on; same observations either way          */
     /* agent type (python/magent/builtin/config/battle.py:16-29) and the attack reward rules (:41-42) */
     float hp, speed, view_radius, attack_radius, damage, step_recover, kill_supply;
     float step_reward, kill_reward, dead_penalty, attack_penalty, attack_bonus[2];
@@ -145,6 +147,20 @@ int mfi_resident_cluster_size(int dtype, int side);
 int mfi_run(int dtype, int n_lattices, int side, int n_sweeps, int8_t *d_spins, void *d_q,
             const void *d_temperatures, double lr, const void *d_uniforms, const uint8_t *d_update_mask, unsigned seed,
             unsigned lattice_base, unsigned step0, int32_t *d_n_up, void *d_reward_sum, void *stream);
+
+/* The Ising ENVIRONMENT interface (examples/ising_model/multiagent/environment.py:49-92 `_step` / `_reset`,
+ * multiagent/core.py:99-125 `IsingWorld.step`, Ising.py:101-118 reward / observation) for callers that bring their
+ * own policy, e.g. the unmodified main_MFQ_Ising.py over python/examples/ising_model (same package layout as the
+ * reference).  All pointers are DEVICE memory; N = side * side.
+ *   d_spins    int8 [n_lattices][N]      in/out
+ *   d_actions  int32[n_lattices][N] or NULL: spin_i <- (action_i <= 0 ? 0 : 1) first (environment.py:112-114);
+ *              NULL = observe the lattice as it is (`_reset`)
+ *   d_obs      uint8[n_lattices][N][4] or NULL: the 4 torus neighbours' spins, ascending flat index of the
+ *              neighbour -- the order of global_state.flatten()[np.where(spin_mask == 1)] (Ising.py:113-118)
+ *   d_reward   float[n_lattices][N] or NULL: 0.5 * sigma_i * sum_nbr sigma_j on the new lattice (Ising.py:101-111)
+ *   d_n_up     int32[n_lattices] or NULL: up spins (order parameter |2 up - N| / N, core.py:106-110) */
+int mfi_env_step(int n_lattices, int side, int8_t *d_spins, const int32_t *d_actions, uint8_t *d_obs,
+                 float *d_reward, int32_t *d_n_up, void *stream);
 
 #ifdef __cplusplus
 }

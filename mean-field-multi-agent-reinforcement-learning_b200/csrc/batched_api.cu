@@ -59,7 +59,7 @@ int mfb_default_config(mfb_config *c) {
     MFB_BEGIN
     memset(c, 0, sizeof(*c));
     c->n_envs = 1; c->map_width = c->map_height = 40; c->capacity = 64; c->embedding_size = 10;
-    c->rng_mode = MFB_RNG_MINSTD; c->device = -1; c->obs_tile_agents = 0;
+    c->rng_mode = MFB_RNG_MINSTD; c->device = -1; c->obs_tile_agents = 0; c->obs_record = -1;
     AgentTypeParams t;
     c->hp = t.hp; c->speed = t.speed; c->view_radius = t.view_radius; c->attack_radius = t.attack_radius;
     c->damage = t.damage; c->step_recover = t.step_recover; c->kill_supply = t.kill_supply;
@@ -74,7 +74,7 @@ int mfb_create(const mfb_config *c, mfb_engine **out) {
     ec.n_envs = c->n_envs; ec.width = c->map_width; ec.height = c->map_height; ec.capacity = c->capacity;
     ec.embedding_size = c->embedding_size; ec.rng_mode = c->rng_mode; ec.seed = c->seed;
     ec.env_base = c->env_base; ec.max_steps = c->max_steps; ec.device = c->device;
-    ec.step_threads = c->step_threads; ec.obs_tile_agents = c->obs_tile_agents;
+    ec.step_threads = c->step_threads; ec.obs_tile_agents = c->obs_tile_agents; ec.obs_cached = c->obs_record;
     ec.type.hp = c->hp; ec.type.speed = c->speed; ec.type.view_radius = c->view_radius;
     ec.type.attack_radius = c->attack_radius; ec.type.damage = c->damage; ec.type.step_recover = c->step_recover;
     ec.type.kill_supply = c->kill_supply; ec.type.step_reward = c->step_reward; ec.type.kill_reward = c->kill_reward;

@@ -68,6 +68,59 @@ __device__ __forceinline__ int block_scan_flag(bool flag, int *s_warp, int &tota
     return block_scan_flags2(flag, false, s_warp, total);
 }
 
+// ----------------------------------------------------------------------------------------------
+// Observation record (large groups only, BattleParams::obs_cached): what k_obs needs to know about an environment,
+// laid out exactly as k_obs wants it in shared memory, so that an observation work item starts with ONE bulk copy
+// instead of re-deriving it from the agent arrays (at 512 v 512 that set-up was 18 % of k_obs, ncu round 1, and it
+// forced 128-agent tiles -- 512 items for 296 CTAs).  Written by whoever changes the state: k_step at its end,
+// k_obs_record after a placement.
+//   grid   u16 [(H+12)*(W+12)]  padded occupancy: kind << 14 | slot, kind 1 = wall, 2 = group 0, 3 = group 1 (alive only)
+//   hp10   f32 [2*cap]          hp / max_hp per slot (Map.cc:208)
+//   mini   f32 [2][169]         minimap of each group: count / num over everything still listed (GridWorld.cc:341-380)
+// ----------------------------------------------------------------------------------------------
+constexpr int kPad = kView / 2;   // the padded grid carries a 6-cell empty margin: view windows never need a bounds test
+struct ObsRecord { int grid, hp10, mini, total; };
+__host__ __device__ inline ObsRecord obs_record_layout(int W, int H, int cap) {
+    ObsRecord R;
+    R.grid = 0;
+    R.hp10 = ((W + 2 * kPad) * (H + 2 * kPad) * 2 + 15) & ~15;
+    R.mini = R.hp10 + 4 * 2 * cap;                 // cap is a multiple of 4: stays 16-byte aligned
+    R.total = (R.mini + 4 * 2 * kViewCells + 15) & ~15;
+    return R;
+}
+
+// Builds env e's record from the state arrays in HBM (as the calling CTA left them: call after a __syncthreads that
+// follows the write-back).  s_pg: shared scratch of R.hp10 bytes (16-byte aligned), s_cnt: 2*169 ints.
+__device__ __forceinline__ void build_obs_record(const BattleParams &P, const BattleState &S, int e, uint16_t *s_pg, int *s_cnt) {
+    const int tid = threadIdx.x, nt = blockDim.x, W = P.W, cap = P.cap, PW = W + 2 * kPad;
+    const ObsRecord R = obs_record_layout(P.W, P.H, cap);
+    unsigned char *rec = S.obs_record + (size_t)e * R.total;
+    const size_t ebase = (size_t)e * 2 * cap;
+    for (int c = tid; c < R.hp10 / 16; c += nt) ((uint4 *)s_pg)[c] = ((const uint4 *)S.grid_template)[c];
+    for (int c = tid; c < 2 * kViewCells; c += nt) s_cnt[c] = 0;
+    const int n0 = S.num[e * 2], n1 = S.num[e * 2 + 1];
+    __syncthreads();
+    const uint8_t *lut = S.mini_lut;
+    float *hp10 = (float *)(rec + R.hp10);
+    for (int s = tid; s < 2 * cap; s += nt) {
+        const int gg = s >= cap, i = s - gg * cap;
+        if (i >= (gg ? n1 : n0)) continue;
+        const int p = S.pos[ebase + s], x = pos_x(p), y = pos_y(p);
+        atomicAdd(&s_cnt[gg * kViewCells + lut[W + y] + lut[x]], 1);       // dead or not (GridWorld.cc:359-370)
+        if (!st_dead(S.state[ebase + s])) {
+            s_pg[(y + kPad) * PW + x + kPad] = (uint16_t)(((2 + gg) << 14) | s);
+            hp10[s] = __fdiv_rn(S.hp[ebase + s], P.hp);
+        }
+    }
+    __syncthreads();
+    for (int c = tid; c < R.hp10 / 16; c += nt) ((uint4 *)rec)[c] = ((const uint4 *)s_pg)[c];
+    float *mini = (float *)(rec + R.mini);
+    for (int c = tid; c < 2 * kViewCells; c += nt) {
+        const int tot = c >= kViewCells ? n1 : n0;
+        mini[c] = tot > 0 ? __fdiv_rn((float)s_cnt[c], (float)tot) : 0.0f;   // GridWorld.cc:372-377; 0/0 defined as 0
+    }
+}
+
 // minstd_rand0 after n steps from state s: s * 16807^n mod (2^31 - 1), square and multiply over a table of
 // 16807^(2^b) -- the reference's sequential chain (GridWorld.cc:510-515 draws one number per attack) without the chain.
 __device__ __forceinline__ uint32_t minstd_jump(uint32_t s, uint32_t n) {
@@ -84,9 +137,9 @@ __device__ __forceinline__ uint32_t minstd_jump(uint32_t s, uint32_t n) {
 // K2: fused step
 // ----------------------------------------------------------------------------------------------
 struct StepSmem {  // byte offsets into dynamic shared memory
-    int pos, hp, nr, state, att, aux, mv, mvt, tag_a, tag_v, mvidx, scr0, scr1, grid, claim, misc, total;
+    int pos, hp, nr, state, att, aux, mv, mvt, tag_a, tag_v, mvidx, scr0, scr1, grid, misc, total;
 };
-__host__ __device__ inline StepSmem step_smem_layout(int W, int H, int cap) {
+__host__ __device__ inline StepSmem step_smem_layout(int W, int H, int cap, int obs_cached) {
     StepSmem L;
     const int n = 2 * cap;
     int o = 0;
@@ -104,8 +157,13 @@ __host__ __device__ inline StepSmem step_smem_layout(int W, int H, int cap) {
     L.tag_v = o; o += 2 * n;   // batch tag: slot is attacked in the current batch
     L.mvidx = o; o += 2 * n;   // 1 + index in the move list of a mover that tries to leave its cell (0 = it stays)
     L.misc = o;  o += 4 * 128; // warp totals [32], counters, action histogram [2][32]
-    L.grid = o;  o += (2 * W * H + 3) & ~3;
-    L.claim = o; o += 4 * W * H;   // per target cell: the first mover entitled to it (min over list indices)
+    L.grid = o;                    // per cell: occupant code (low half: 0 empty, 1 wall, 2 + slot) | claim << 16, the first
+    {                              // mover entitled to the cell (min over move-list indices, 0xFFFF = nobody);
+        int bytes = 4 * W * H;     // afterwards the scratch of build_obs_record (padded u16 grid + minimap counts)
+        const int need = obs_record_layout(W, H, cap).hp10 + 4 * 2 * kViewCells;
+        if (obs_cached && need > bytes) bytes = need;
+        o += (bytes + 15) & ~15;
+    }
     L.total = (o + 15) & ~15;
     return L;
 }
@@ -118,7 +176,7 @@ enum : int { MV_FAIL = 0, MV_OK = 1, MV_WAIT = 2 };
 
 __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState S, const StepIO io) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const StepSmem L = step_smem_layout(P.W, P.H, P.cap);
+    const StepSmem L = step_smem_layout(P.W, P.H, P.cap, P.obs_cached);
     int *s_pos = (int *)(smem_raw + L.pos);
     float *s_hp = (float *)(smem_raw + L.hp);
     float *s_nr = (float *)(smem_raw + L.nr);
@@ -133,8 +191,8 @@ __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState
     uint16_t *s_tag_v = (uint16_t *)(smem_raw + L.tag_v);
     uint16_t *s_mvidx = (uint16_t *)(smem_raw + L.mvidx);
     int *s_misc = (int *)(smem_raw + L.misc);
-    uint16_t *s_grid = (uint16_t *)(smem_raw + L.grid);
-    uint32_t *s_claim = (uint32_t *)(smem_raw + L.claim);
+    uint32_t *s_grid = (uint32_t *)(smem_raw + L.grid);
+    constexpr uint32_t kNoClaim = 0xFFFF0000u;
 
     const int e = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     const int cap = P.cap, W = P.W, H = P.H, cells = W * H;
@@ -146,16 +204,15 @@ __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState
     // ---- load: agent records -> smem, occupancy grid from walls + alive agents ----
     if (tid < 2) { s_misc[MISC_N + tid] = S.num[e * 2 + tid]; s_misc[MISC_DEAD + tid] = S.dead_ct[e * 2 + tid]; }
     const uint8_t *walls = S.walls + (size_t)e * P.wall_stride;
-    if ((cells & 3) == 0) {   // 4 wall bytes -> 4 u16 grid codes per thread
+    if ((cells & 3) == 0) {   // 4 wall bytes -> 4 grid words per thread
         for (int c = tid; c < (cells >> 2); c += nt) {
             const uint32_t w4 = ((const uint32_t *)walls)[c];
-            ((uint2 *)s_grid)[c] = make_uint2((w4 & 0xFFu) | ((w4 & 0xFF00u) << 8), ((w4 >> 16) & 0xFFu) | ((w4 >> 8) & 0xFF0000u));
+            ((uint4 *)s_grid)[c] = make_uint4(kNoClaim | (w4 & 0xFFu), kNoClaim | ((w4 >> 8) & 0xFFu),
+                                              kNoClaim | ((w4 >> 16) & 0xFFu), kNoClaim | (w4 >> 24));
         }
     } else {
-        for (int c = tid; c < cells; c += nt) s_grid[c] = walls[c];
+        for (int c = tid; c < cells; c += nt) s_grid[c] = kNoClaim | walls[c];
     }
-    if (phases & PH_STEP)
-        for (int c = tid; c < cells; c += nt) s_claim[c] = 0xFFFFFFFFu;
     __syncthreads();
     const int n0 = s_misc[MISC_N], n1 = s_misc[MISC_N + 1];
     for (int s = tid; s < 2 * cap; s += nt) {
@@ -170,7 +227,7 @@ __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState
             }
             s_pos[s] = p; s_hp[s] = S.hp[ebase + s]; s_nr[s] = S.next_rew[ebase + s];
             s_state[s] = st;
-            if (!st_dead(st)) s_grid[pos_y(p) * W + pos_x(p)] = (uint16_t)(2 + s);
+            if (!st_dead(st)) s_grid[pos_y(p) * W + pos_x(p)] = kNoClaim | (uint32_t)(2 + s);
         }
         s_tag_a[s] = 0; s_tag_v[s] = 0; s_mvidx[s] = 0; s_scr0[s] = 0;
     }
@@ -269,7 +326,7 @@ __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState
             const int tx = pos_x(p) + P.att_dx[a], ty = pos_y(p) + P.att_dy[a];
             int v = -1;
             if (tx >= 0 && tx < W && ty >= 0 && ty < H) {
-                const int code = s_grid[ty * W + tx];
+                const int code = (int)(s_grid[ty * W + tx] & 0xFFFFu);
                 if (code >= 2 && ((code - 2) >= cap) != (k >= cap)) v = code - 2;
             }
             s_aux[i] = v;
@@ -293,7 +350,7 @@ __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState
                 s_state[v] |= 1u;
                 s_nr[v] = P.dead_penalty;
                 const int pv = s_pos[v];
-                s_grid[pos_y(pv) * W + pos_x(pv)] = 0;                     // Map::remove_agent
+                s_grid[pos_y(pv) * W + pos_x(pv)] = kNoClaim;              // Map::remove_agent
                 atomicAdd(&s_misc[MISC_DEAD + (v >= cap)], 1);
                 s_state[k] = st_with_op(s_state[k], OP_KILL);
                 s_hp[k] = fminf(P.hp, s_hp[k] + P.kill_supply);            // Agent::add_hp
@@ -383,7 +440,7 @@ __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState
                 s_hp[s] = hp;
                 if (hp < 0.0f) {
                     s_state[s] |= 1u; s_nr[s] = P.dead_penalty;
-                    s_grid[pos_y(s_pos[s]) * W + pos_x(s_pos[s])] = 0;
+                    s_grid[pos_y(s_pos[s]) * W + pos_x(s_pos[s])] = kNoClaim;
                     atomicAdd(&s_misc[MISC_DEAD + g], 1);
                 }
             }
@@ -412,21 +469,21 @@ __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState
             const int tc = s_mvt[m], k = (int)(s_mv[m] & 0xFFFF);
             int res = MV_FAIL, dep = -1;
             if (tc >= 0) {
-                const int occ = s_grid[tc];
+                const int occ = (int)(s_grid[tc] & 0xFFFFu);
                 if (occ == 0) res = MV_WAIT;                                   // contender for an empty cell
                 else if (occ >= 2 && occ != 2 + k) {
                     const int j = (int)s_mvidx[occ - 2] - 1;
                     if (j >= 0 && j < m) { res = MV_WAIT; dep = j; }           // the occupant had its turn before m
                     else s_state[k] = st_with_op(s_state[k], OP_COLLIDE);      // it is still there (no reward effect in battle)
                 }                                                              // own cell: stays; wall: nothing (Map.cc:498-513)
-                if (res == MV_WAIT) atomicMin(&s_claim[tc], (uint32_t)m);
+                if (res == MV_WAIT) atomicMin(&s_grid[tc], ((uint32_t)m << 16) | (uint32_t)occ);   // every contender sees the same occupant
             }
             s_scr0[m] = res; s_scr1[m] = dep;
         }
         __syncthreads();
         for (int m = tid; m < nM; m += nt) {
             if (s_scr0[m] != MV_WAIT) continue;
-            if (s_claim[s_mvt[m]] != (uint32_t)m) {                            // an earlier contender is entitled to the cell
+            if ((s_grid[s_mvt[m]] >> 16) != (uint32_t)m) {                            // an earlier contender is entitled to the cell
                 s_scr0[m] = MV_FAIL;
                 const int k = (int)(s_mv[m] & 0xFFFF);
                 s_state[k] = st_with_op(s_state[k], OP_COLLIDE);
@@ -451,13 +508,14 @@ __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState
             if (!s_misc[MISC_FLAG]) break;
         }
         for (int m = tid; m < nM; m += nt)
-            if (s_scr0[m] == MV_OK) { const int p = s_pos[s_mv[m] & 0xFFFF]; s_grid[pos_y(p) * W + pos_x(p)] = 0; }
+            if (s_scr0[m] == MV_OK) { const int p = s_pos[s_mv[m] & 0xFFFF]; s_grid[pos_y(p) * W + pos_x(p)] = kNoClaim; }
         __syncthreads();
         for (int m = tid; m < nM; m += nt)
             if (s_scr0[m] == MV_OK) {
                 const int k = (int)(s_mv[m] & 0xFFFF), tc = s_mvt[m];
-                s_grid[tc] = (uint16_t)(2 + k);
-                s_pos[k] = pack_pos(tc % W, tc / W);
+                s_grid[tc] = kNoClaim | (uint32_t)(2 + k);
+                const int ty = tc / W;
+                s_pos[k] = pack_pos(tc - ty * W, ty);
             }
         __syncthreads();
 
@@ -559,6 +617,17 @@ __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState
         }
         if (tid < 2) S.dead_ct[e * 2 + tid] = s_misc[MISC_DEAD + tid];
     }
+    if (P.obs_cached && (phases & (PH_STEP | PH_CLEAR))) {        // positions / alive flags / slot indices changed
+        __syncthreads();                                          // the write-back above is visible to the whole CTA
+        build_obs_record(P, S, e, (uint16_t *)(smem_raw + L.grid),
+                         (int *)(smem_raw + L.grid + obs_record_layout(P.W, P.H, P.cap).hp10));
+    }
+}
+
+// the observation record of every env after a placement (commit / late add); one CTA per env
+__global__ void k_obs_record(const __grid_constant__ BattleParams P, const BattleState S) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    build_obs_record(P, S, blockIdx.x, (uint16_t *)smem_raw, (int *)(smem_raw + obs_record_layout(P.W, P.H, P.cap).hp10));
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -593,25 +662,32 @@ constexpr int kObsStageBytes = kObsChunk * kViewRow * 4;       // 37 856, a mult
 constexpr int kObsPasses = (kViewCells + 31) / 32;             // 6
 static_assert(kObsChunk == kObsWarps, "one warp composes one row of a chunk");
 
-constexpr int kPad = kView / 2;   // the smem grid carries a 6-cell empty margin: view windows never need a bounds test
-
-struct ObsSmem { int stage0, stage1, rec, hp10, mini, cnt, code, fxy, tmpl, total; };
+struct ObsSmem { int stage0, stage1, rec, hp10, mini, cnt, code, fxy, tmpl, record, bar, total; };
 constexpr int kObsMaxTile = kObsThreads;   // agents per CTA tile, upper bound (one record per thread)
 // The pristine wall template is kept in shared memory when two CTAs per SM still fit with it (40x40: +5.4 KB);
 // larger maps copy it from global memory (L2) per item instead.
 __host__ __device__ inline bool obs_template_in_smem(int W, int H) { return (W + 2 * kPad) * (H + 2 * kPad) * 2 <= 8 * 1024; }
-__host__ __device__ inline ObsSmem obs_smem_layout(int W, int H, int cap) {
+__host__ __device__ inline ObsSmem obs_smem_layout(int W, int H, int cap, int cached) {
     ObsSmem L; int o = 0;
     L.stage0 = o; o += kObsStageBytes;
     L.stage1 = o; o += kObsStageBytes;
     L.rec = o;    o += 16 * kObsMaxTile;                              // (pos, id, state, last_rew) of the tile's agents
-    L.hp10 = o;   o += 4 * 2 * cap;                                   // hp / max_hp per agent slot
-    L.mini = o;   o += 4 * 2 * kViewCells;
-    L.cnt = o;    o += 4 * 2 * kViewCells;
-    L.code = o;   o += (2 * (W + 2 * kPad) * (H + 2 * kPad) + 3) & ~3;  // u16 per padded cell: kind << 14 | slot
-    L.fxy = o;    o += 4 * (W + H);                                    // x / W and y / H as tables (features 32, 33)
-    o = (o + 15) & ~15;
-    L.tmpl = o;   if (obs_template_in_smem(W, H)) o += (2 * (W + 2 * kPad) * (H + 2 * kPad) + 15) & ~15;
+    L.record = L.bar = L.cnt = L.tmpl = 0;
+    if (cached) {                                                     // the env's observation record, as one bulk copy lands it
+        const ObsRecord R = obs_record_layout(W, H, cap);
+        L.record = o; L.code = o + R.grid; L.hp10 = o + R.hp10; L.mini = o + R.mini; o += R.total;
+        L.fxy = o;    o += 4 * (W + H);
+        o = (o + 15) & ~15;
+        L.bar = o;    o += 16;                                        // mbarrier the bulk copy completes on
+    } else {
+        L.hp10 = o;   o += 4 * 2 * cap;                                   // hp / max_hp per agent slot
+        L.mini = o;   o += 4 * 2 * kViewCells;
+        L.cnt = o;    o += 4 * 2 * kViewCells;
+        L.code = o;   o += (2 * (W + 2 * kPad) * (H + 2 * kPad) + 3) & ~3;  // u16 per padded cell: kind << 14 | slot
+        L.fxy = o;    o += 4 * (W + H);                                    // x / W and y / H as tables (features 32, 33)
+        o = (o + 15) & ~15;
+        L.tmpl = o;   if (obs_template_in_smem(W, H)) o += (2 * (W + 2 * kPad) * (H + 2 * kPad) + 15) & ~15;
+    }
     L.total = (o + 127) & ~127;
     return L;
 }
@@ -632,13 +708,34 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// cell kinds in the CTA-local grid, relative to the observing group
+__device__ __forceinline__ void obs_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void obs_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void obs_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_load_g2s(void *sdst, const void *gsrc, uint32_t bytes, uint32_t bar) {
+    const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(sdst);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(saddr), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
+
+// cell kinds in the CTA-local grid.  Rebuilt per item (CACHED = false) they are relative to the observing group; in the
+// observation record (CACHED = true) they name the group: 2 + group
 enum : uint32_t { KIND_EMPTY = 0, KIND_WALL = 1, KIND_OWN = 2, KIND_OTHER = 3 };
 
+template <bool CACHED>
 __global__ void __launch_bounds__(kObsThreads, kObsCtasPerSm)
 k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO io) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const ObsSmem L = obs_smem_layout(P.W, P.H, P.cap);
+    const ObsSmem L = obs_smem_layout(P.W, P.H, P.cap, CACHED);
     float *const s_stage0 = (float *)(smem_raw + L.stage0), *const s_stage1 = (float *)(smem_raw + L.stage1);
     int4 *s_rec = (int4 *)(smem_raw + L.rec);
     float *s_hp10 = (float *)(smem_raw + L.hp10);
@@ -646,8 +743,15 @@ k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO i
     int *s_cnt = (int *)(smem_raw + L.cnt);
     uint16_t *s_code = (uint16_t *)(smem_raw + L.code);
     float *s_fxy = (float *)(smem_raw + L.fxy);
-    const bool tmpl_smem = obs_template_in_smem(P.W, P.H);
+    const bool tmpl_smem = !CACHED && obs_template_in_smem(P.W, P.H);
     const uint4 *s_tmpl = tmpl_smem ? (const uint4 *)(smem_raw + L.tmpl) : (const uint4 *)S.grid_template;
+    const uint32_t rec_bar = (uint32_t)__cvta_generic_to_shared(smem_raw + L.bar);
+    const uint32_t rec_bytes = (uint32_t)obs_record_layout(P.W, P.H, P.cap).total;
+    uint32_t rec_phase = 0;
+    if (CACHED && threadIdx.x == 0) {
+        obs_mbar_init(rec_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // visible to the async proxy
+    }
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = P.W, H = P.H, cap = P.cap;
@@ -700,13 +804,37 @@ k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO i
         const int tile = t % io.tiles_per_group; t /= io.tiles_per_group;
         int g, e;
         if (io.group_mask == 3) { g = t & 1; e = t >> 1; } else { g = io.group_mask >> 1; e = t; }
-        // Every global read of the item is issued here, up front and independent of the others (none waits for
-        // `num`): slot state for the occupancy grid and the minimaps, and the tile's agent records.  One memory
-        // round trip per item instead of four dependent ones.
         const size_t ebase = (size_t)e * 2 * cap;
         const size_t gbase = ebase + (size_t)g * cap;
         const int a_begin = tile * io.tile_agents;
-        const int n0 = S.num[e * 2], n1 = S.num[e * 2 + 1];
+        int n0, n1, ng, a_end;
+        if constexpr (CACHED) {
+            // The env's observation record (occupancy grid, hp / 10 per slot, both minimaps -- written by k_step) lands in
+            // shared memory with ONE bulk copy; every warp has finished with the previous item's record (barriers above).
+            if (tid == 0) {
+                obs_mbar_expect_tx(rec_bar, rec_bytes);
+                bulk_load_g2s(smem_raw + L.record, S.obs_record + (size_t)e * rec_bytes, rec_bytes, rec_bar);
+            }
+            n0 = S.num[e * 2]; n1 = S.num[e * 2 + 1];
+            int4 my_rec = make_int4(0, 0, 0, 0);                                   // agent a_begin + tid of the tile
+            if (tid < io.tile_agents && a_begin + tid < cap) {
+                const size_t s = gbase + a_begin + tid;
+                my_rec = make_int4(S.pos[s], S.id[s], (int)S.state[s], __float_as_int(S.last_rew[s]));
+            }
+            ng = g ? n1 : n0;
+            a_end = min(ng, a_begin + io.tile_agents);
+            if (tid < a_end - a_begin) s_rec[tid] = my_rec;
+            obs_mbar_wait(rec_bar, rec_phase);            // (also before skipping an empty tile: one copy per phase)
+            rec_phase ^= 1u;
+            if (a_begin >= ng) {                          // nothing to do (uniform across the CTA)
+                if (tid == 0) s_next = next_ticket;
+                continue;
+            }
+        } else {
+        // Every global read of the item is issued here, up front and independent of the others (none waits for
+        // `num`): slot state for the occupancy grid and the minimaps, and the tile's agent records.  One memory
+        // round trip per item instead of four dependent ones.
+        n0 = S.num[e * 2]; n1 = S.num[e * 2 + 1];
         constexpr int kPre = 4;                       // slots tid + j*256, j < 4, in registers (covers cap <= 512)
         int slot_pos[kPre]; uint32_t slot_state[kPre]; float slot_hp[kPre];
 #pragma unroll
@@ -720,12 +848,12 @@ k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO i
             const size_t s = gbase + a_begin + tid;
             my_rec = make_int4(S.pos[s], S.id[s], (int)S.state[s], __float_as_int(S.last_rew[s]));
         }
-        const int ng = g ? n1 : n0;
+        ng = g ? n1 : n0;
         if (a_begin >= ng) {                              // nothing to do (uniform across the CTA)
             if (tid == 0) s_next = next_ticket;
             continue;
         }
-        const int a_end = min(ng, a_begin + io.tile_agents);
+        a_end = min(ng, a_begin + io.tile_agents);
 
         // ---- padded occupancy grid (kind << 14 | slot per cell), hp/10 per slot, minimap counts ----
         for (int c = tid; c < (pcells * 2 + 15) / 16; c += kObsThreads) ((uint4 *)s_code)[c] = s_tmpl[c];
@@ -760,6 +888,9 @@ k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO i
             const int tot = gg ? n1 : n0;
             s_mini[c] = tot > 0 ? __fdiv_rn((float)s_cnt[c], (float)tot) : 0.0f;
         }
+        }
+        const uint32_t kind_own = CACHED ? 2u + (uint32_t)g : (uint32_t)KIND_OWN;
+        const uint32_t kind_oth = CACHED ? 3u - (uint32_t)g : (uint32_t)KIND_OTHER;
         // (the barrier at the top of the first chunk orders s_mini before its readers)
         const float *mini_own = s_mini + g * kViewCells, *mini_oth = s_mini + (1 - g) * kViewCells;
 
@@ -801,10 +932,10 @@ k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO i
                         const uint32_t k = code[it] >> 14;
                         float *o = row + cell7[it];
                         o[0] = k == KIND_WALL ? 1.0f : 0.0f;
-                        o[1] = k == KIND_OWN ? 1.0f : 0.0f;
-                        o[2] = k == KIND_OWN ? hpv[it] : 0.0f;
-                        o[4] = k == KIND_OTHER ? 1.0f : 0.0f;
-                        o[5] = k == KIND_OTHER ? hpv[it] : 0.0f;
+                        o[1] = k == kind_own ? 1.0f : 0.0f;
+                        o[2] = k == kind_own ? hpv[it] : 0.0f;
+                        o[4] = k == kind_oth ? 1.0f : 0.0f;
+                        o[5] = k == kind_oth ? hpv[it] : 0.0f;
                     }
                 }
                 if (stale > 0) {                        // new item: refresh the part all its agents share

@@ -60,6 +60,7 @@ struct BattleParams {
     int wall_stride;        // H*W, or 0 when every env shares one wall map
     int rng_mode;
     int max_steps;          // auto-reset horizon (0 = none)
+    int obs_cached;         // k_obs starts an item from the per-env observation record (large groups) instead of the agent arrays
     int move_bands;         // 0, or the reference's NUM_SEP_BUFFER when W*H > 99*99 ("large map mode", GridWorld.cc:79-88):
     int band_width;         //   moves run x-band by x-band, then the band-boundary buffer (GridWorld.cc:443-463,662-672)
     uint32_t seed;
@@ -79,6 +80,7 @@ struct BattleState {   // device pointers
     uint8_t *walls;
     uint16_t *grid_template;           // [(H+12)*(W+12)] padded occupancy grid holding only the walls (kind << 14)
     uint8_t *mini_lut;                 // [W] x / scale_w, then [H] (y / scale_h) * view: minimap cell of a position
+    unsigned char *obs_record;         // [E][obs_record_layout().total] when obs_cached (battle_kernels.cuh)
     unsigned long long *agent_steps;   // [E] running count of agents taken through a step (statistic)
     int32_t *obs_ticket;               // [2] of this launch (ring of kObsTicketRing pairs): next item, CTAs finished (rewound by the last CTA)
     // episode template for auto-reset

@@ -115,6 +115,12 @@ Engine::Engine(const EngineConfig &cfg) : cfg_(cfg) {
     P_.scale_h = (cfg.height + kView - 1) / kView;
     P_.wall_stride = 0;
     P_.rng_mode = cfg.rng_mode; P_.max_steps = cfg.max_steps; P_.seed = cfg.seed;
+    {   // observation record (battle_kernels.cuh): worth it when groups are large -- the per-item rebuild of the occupancy
+        // grid from the agent arrays then dominates k_obs's set-up and forces coarse tiles
+        const char *env = getenv("MFMARL_OBS_CACHED");
+        const int want = cfg.obs_cached >= 0 ? cfg.obs_cached : (env ? atoi(env) : -1);
+        P_.obs_cached = want >= 0 ? (want != 0) : (round_up(cfg.capacity, 4) >= 256);
+    }
     P_.move_bands = 0; P_.band_width = cfg.width;
     if (cfg.width * cfg.height > 99 * 99) {                       // GridWorld.cc:79-88 "large_map_mode"
         P_.move_bands = cfg.width * cfg.height > 1000 * 1000 ? 16 : 8;
@@ -205,6 +211,12 @@ void Engine::alloc_state(int cap) {
     MF_CUDA(cudaMalloc(&S_.id, n * 4)); MF_CUDA(cudaMalloc(&S_.state, n * 4));
     MF_CUDA(cudaMalloc(&S_.next_rew, n * 4)); MF_CUDA(cudaMalloc(&S_.last_rew, n * 4));
     MF_CUDA(cudaMalloc(&S_.init_pos, (size_t)4 * cap * 4));
+    S_.obs_record = nullptr;
+    if (P_.obs_cached) {
+        const size_t bytes = (size_t)P_.E * obs_record_layout(P_.W, P_.H, cap).total;
+        MF_CUDA(cudaMalloc(&S_.obs_record, bytes));
+        MF_CUDA(cudaMemset(S_.obs_record, 0, bytes));
+    }
     MF_CUDA(cudaMemset(S_.pos, 0, n * 4)); MF_CUDA(cudaMemset(S_.hp, 0, n * 4));
     MF_CUDA(cudaMemset(S_.id, 0, n * 4)); MF_CUDA(cudaMemset(S_.state, 0, n * 4));
     MF_CUDA(cudaMemset(S_.next_rew, 0, n * 4)); MF_CUDA(cudaMemset(S_.last_rew, 0, n * 4));
@@ -212,7 +224,8 @@ void Engine::alloc_state(int cap) {
 
 void Engine::free_state() {
     cudaFree(S_.pos); cudaFree(S_.hp); cudaFree(S_.id); cudaFree(S_.state);
-    cudaFree(S_.next_rew); cudaFree(S_.last_rew); cudaFree(S_.init_pos);
+    cudaFree(S_.next_rew); cudaFree(S_.last_rew); cudaFree(S_.init_pos); cudaFree(S_.obs_record);
+    S_.obs_record = nullptr;
     S_.pos = nullptr; S_.hp = nullptr; S_.id = nullptr; S_.state = nullptr;
     S_.next_rew = S_.last_rew = nullptr; S_.init_pos = nullptr;
 }
@@ -333,6 +346,16 @@ void Engine::late_add_sync_up() {
     MF_CUDA(cudaMemcpy(S_.num, num, 8, cudaMemcpyHostToDevice));
     MF_CUDA(cudaMemcpy(S_.id_counter, &h_id_counter_, 4, cudaMemcpyHostToDevice));
     h_num_[0] = num[0]; h_num_[1] = num[1];
+    rebuild_obs_records(nullptr);
+    MF_CUDA(cudaStreamSynchronize(nullptr));
+}
+
+void Engine::rebuild_obs_records(cudaStream_t st) {
+    if (!P_.obs_cached) return;
+    const int smem = obs_record_layout(P_.W, P_.H, P_.cap).hp10 + 4 * 2 * kViewCells;
+    raise_dynamic_smem((const void *)k_obs_record, smem, device_);
+    k_obs_record<<<P_.E, 256, smem, st>>>(P_, S_);
+    MF_CUDA(cudaGetLastError());
 }
 
 uint32_t Engine::pull_rng0() {
@@ -387,6 +410,7 @@ void Engine::commit(cudaStream_t st) {
     MF_CUDA(cudaStreamSynchronize(st));
     k_place<<<P_.E, 128, 0, st>>>(P_, S_);
     MF_CUDA(cudaGetLastError());
+    rebuild_obs_records(st);
     // a placement is a per-episode event: wait for it, so that whatever stream the next launch uses (the legacy
     // stream of mfb_query, a non-blocking side stream of the caller) it is ordered after the new state
     MF_CUDA(cudaStreamSynchronize(st));
@@ -422,10 +446,11 @@ void Engine::observe_groups(float *const d_view[kGroups], float *const d_feature
     }
     io.env_stride = env_stride; io.group_mask = group_mask;
     io.debug = obs_debug_;
-    const ObsSmem L = obs_smem_layout(P_.W, P_.H, P_.cap);
-    raise_dynamic_smem((const void *)k_obs, L.total, device_);
+    const ObsSmem L = obs_smem_layout(P_.W, P_.H, P_.cap, P_.obs_cached);
+    void (*kern)(const BattleParams, const BattleState, const ObsIO) = P_.obs_cached ? k_obs<true> : k_obs<false>;
+    raise_dynamic_smem((const void *)kern, L.total, device_);
     if (obs_attr_ != L.total) {
-        MF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&obs_ctas_per_sm_, k_obs, kObsThreads, L.total));
+        MF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&obs_ctas_per_sm_, kern, kObsThreads, L.total));
         obs_attr_ = L.total;
     }
     // persistent CTAs (two per SM, shared-memory bound) take (env, group, tile) work items from a ticket counter
@@ -434,7 +459,11 @@ void Engine::observe_groups(float *const d_view[kGroups], float *const d_feature
     // but the items must stay numerous enough to balance over the CTAs: measured at cap 512 x 128 envs, 128-agent
     // tiles (1024 items) beat 256 (512 items for 296 CTAs) and 64
     int want_tile = cfg_.obs_tile_agents;
-    if (want_tile <= 0) {
+    if (want_tile <= 0 && P_.obs_cached) {
+        // an item starts with one bulk copy of the env's record, so tiles can be small: many items per CTA, and the
+        // last wave is short
+        want_tile = 32;
+    } else if (want_tile <= 0) {
         want_tile = std::min(256, std::max(64, P_.cap));
         const size_t groups = (size_t)P_.E * (group_mask == 3 ? 2 : 1);
         while (want_tile > 128 && groups * ((P_.cap + want_tile - 1) / want_tile) < 3 * ctas) want_tile /= 2;
@@ -449,13 +478,13 @@ void Engine::observe_groups(float *const d_view[kGroups], float *const d_feature
     // different streams (the last CTA of a launch rewinds its pair)
     BattleState S = S_;
     S.obs_ticket += 2 * (obs_launches_++ % kObsTicketRing);
-    k_obs<<<grid, kObsThreads, L.total, st>>>(P_, S, io);
+    kern<<<grid, kObsThreads, L.total, st>>>(P_, S, io);
     MF_CUDA(cudaGetLastError());
 }
 
 void Engine::step(const StepIO &io, cudaStream_t st) {
     commit(st);
-    const StepSmem L = step_smem_layout(P_.W, P_.H, P_.cap);
+    const StepSmem L = step_smem_layout(P_.W, P_.H, P_.cap, P_.obs_cached);
     raise_dynamic_smem((const void *)k_step, L.total, device_);
     int threads = cfg_.step_threads > 0 ? cfg_.step_threads : std::min(1024, std::max(64, P_.cap));
     // a few environments cannot fill the GPU anyway: wider CTAs shorten the parallel phases (grid load, lists, scans)

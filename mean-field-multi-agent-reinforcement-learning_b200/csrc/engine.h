@@ -44,7 +44,8 @@ struct AgentTypeParams {   // the attributes of AgentType.h:21-45 that reach the
 struct EngineConfig {
     int n_envs = 1, width = 40, height = 40, capacity = 64, embedding_size = 10;
     int rng_mode = RNG_MINSTD, max_steps = 0, env_base = 0, device = -1 /* current */;
-    int step_threads = 0 /* auto */, obs_tile_agents = 0 /* auto: clamp(cap, 64, 256) */;
+    int step_threads = 0 /* auto */, obs_tile_agents = 0 /* auto: clamp(cap, 64, 256); 32 with the observation record */;
+    int obs_cached = -1 /* observation record: -1 auto (capacity >= 256, or MFMARL_OBS_CACHED), 0 off, 1 on */;
     unsigned seed = 0;
     AgentTypeParams type;
     float attack_bonus[kGroups] = {0.2f, 0.2f};
@@ -102,6 +103,7 @@ private:
     void grow(int need_cap);
     void late_add_sync_down();   // E == 1 only: device state -> host records
     void late_add_sync_up();
+    void rebuild_obs_records(cudaStream_t st);   // observation records of every env from the state arrays (obs_cached)
 
     struct LateRecords;                    // scratch of one late add_agents call (E == 1)
     std::unique_ptr<LateRecords> late_;

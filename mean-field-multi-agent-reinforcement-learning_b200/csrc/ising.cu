@@ -27,6 +27,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "../../include/mfmarl_batched.h"
 #include "rng.cuh"
 #include "engine.h"
@@ -713,6 +716,209 @@ __global__ void __launch_bounds__(L * (ROWS / RPT), 1) k_ising_resident_f32(cons
     cluster.sync();       // nobody leaves while a neighbour's last remote store may still be in flight
 }
 
+// ---- K6p: the same sweep as K6r-f32, PERSISTENT and without thread-block clusters --------------------------------
+// A 16-CTA cluster has to sit inside one GPC, and the B200's GPCs (16-20 SMs) hold one such cluster each: only 7 of
+// them are resident, 112 of 148 SMs (ncu launch__waves_per_multiprocessor, round 1).  Here a lattice is still cut into
+// C = L / ROWS strips, one CTA each, but the CTAs are ordinary ones: the grid is exactly n_slots * C <= (resident CTAs)
+// co-scheduled CTAs (cooperative launch, so they are guaranteed to be resident together), slot s sweeps lattices
+// s, s + n_slots, ... one after the other, and the halo words travel through L2.  One 8-byte store carries a halo
+// word and a sequence number -- data and flag in one single-copy-atomic message, so neither side needs a fence -- and
+// the receiving warp polls exactly the word it needs with ld.relaxed.gpu (all lanes the same address: one request).
+// Sequence numbers count lattice states over the whole launch (state k of the it-th lattice of a slot has number
+// it * (K + 1) + k + 1); the parity of that number picks the buffer, in shared memory as in L2, so the last state of
+// one lattice and the first of the next never share a buffer.  A strip can be at most one state ahead of its
+// neighbours (it needs their halo of state k to publish state k + 1), which is what makes two buffers enough.
+// Same Philox keys, same arithmetic, same bits as K6 / K6r.
+__device__ __forceinline__ void st_halo(unsigned long long *p, uint32_t word, uint32_t seq) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(((unsigned long long)seq << 32) | word) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_halo(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <int L, int ROWS, int RPT, bool MASK>
+__global__ void __launch_bounds__(L * (ROWS / RPT), 1) k_ising_persist_f32(const IsingRunArgs<float> A, const int n_slots,
+                                                                           unsigned long long *const halo) {
+    static_assert(L % 32 == 0 && ROWS % RPT == 0 && RPT % kIsingRB == 0 && L % ROWS == 0, "shape");
+    constexpr int N = L * L, WPR = L / 32, HR = ROWS + 2, STRIP = ROWS * L, NT = L * (ROWS / RPT), C = L / ROWS;
+    constexpr int NPH = RPT / kIsingRB;                         // Philox calls per thread per sweep
+    constexpr uint32_t PLANE = (uint32_t)STRIP * 8u;            // bytes between the Q planes of consecutive s
+    constexpr uint32_t BUF = (uint32_t)HR * WPR * 4u;           // bytes per bit buffer
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const int slot = blockIdx.x / C, rank = blockIdx.x % C, row0 = rank * ROWS;
+    float *s_q = (float *)s_raw;                                                    // [5][STRIP][2]
+    uint32_t *s_bits = (uint32_t *)(s_raw + (size_t)5 * STRIP * 8);                 // [2][HR][WPR]
+    int *s_stat = (int *)(s_bits + 2 * HR * WPR);                                   // [2] packed statistics per sweep parity
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int x = tid % L, band = tid / L, w = x >> 5;
+    const int rb = band * RPT;
+    const int wl = w == 0 ? WPR - 1 : w - 1, wr = w == WPR - 1 ? 0 : w + 1;
+    const int up_rank = (rank + C - 1) % C, dn_rank = (rank + 1) % C;
+    const uint32_t bits0 = smem_addr(s_bits);
+    const uint32_t q_site0 = smem_addr(s_q) + (uint32_t)(rb * L + x) * 8u;          // Q pair of (s = 0, row rb, column x)
+    const uint32_t own_w = bits0 + (uint32_t)((rb + 1) * WPR + w) * 4u;             // this thread's word of local row rb, buffer 0
+    const uint32_t own_l = bits0 + (uint32_t)((rb + 1) * WPR + wl) * 4u, own_r = bits0 + (uint32_t)((rb + 1) * WPR + wr) * 4u;
+    const bool first_band = rb == 0, last_band = rb + RPT == ROWS;
+    // halo mailboxes in L2: [slot][rank][parity][top | bottom][WPR] -- rank r READS its own, neighbours write into it
+    auto mailbox = [&](int r, int parity, int bottom) {
+        return halo + ((((size_t)slot * C + r) * 2 + parity) * 2 + bottom) * WPR + w;
+    };
+
+    uint32_t state_no = 0;                                      // lattice states published so far by this slot
+    for (int b = slot; b < A.B; b += n_slots, state_no += (uint32_t)A.K + 1u) {
+        const size_t lbase = (size_t)b * N;
+        __syncthreads();                                        // the previous lattice's Q strip has been stored
+        if (tid < 2) s_stat[tid] = 0;
+        for (int sp = 0; sp < 5; sp++) {
+            const float4 *s4 = (const float4 *)(A.Q + (lbase * 5 + (size_t)sp * N + (size_t)row0 * L) * 2);
+            float4 *d4 = (float4 *)(s_q + (size_t)sp * STRIP * 2);
+#pragma unroll 4
+            for (int i = tid; i < STRIP / 2; i += NT) d4[i] = s4[i];
+        }
+        int a_cur[RPT]; uint32_t w_cur[RPT];
+        {
+            const uint32_t par = state_no & 1u, seq = state_no + 1u;
+#pragma unroll
+            for (int j = 0; j < RPT; j++) {
+                a_cur[j] = (int)A.spins[lbase + (size_t)(row0 + rb + j) * L + x];
+                w_cur[j] = __ballot_sync(0xFFFFFFFFu, a_cur[j] != 0);
+                if (lane == 0) sts_u32(own_w + par * BUF + (uint32_t)j * WPR * 4u, w_cur[j]);
+            }
+            if (lane == 0) {
+                if (first_band) st_halo(mailbox(up_rank, (int)par, 1), w_cur[0], seq);       // I am the row below up_rank's last row
+                if (last_band) st_halo(mailbox(dn_rank, (int)par, 0), w_cur[RPT - 1], seq);  // ... and the row above dn_rank's first
+            }
+        }
+        const uint2 key = make_uint2(A.seed, A.lattice_base + (uint32_t)b);
+        const uint32_t gband = (uint32_t)((row0 + rb) >> 2);
+        float uu[RPT];
+        auto draw_uniforms = [&](uint32_t step) {
+#pragma unroll
+            for (int h = 0; h < NPH; h++) {
+                const uint4 rnd = philox4x32_10(make_uint4((uint32_t)x, gband + (uint32_t)h, step, 0u), key);
+                uu[4 * h + 0] = __uint2float_rz(rnd.x); uu[4 * h + 1] = __uint2float_rz(rnd.y);   // u * 2^32
+                uu[4 * h + 2] = __uint2float_rz(rnd.z); uu[4 * h + 3] = __uint2float_rz(rnd.w);
+            }
+        };
+        if (A.u == nullptr) draw_uniforms(A.step0);
+        float tparam = temperature_param(A.temperatures[0]);
+        float keep_q[RPT]; uint32_t keep_addr[RPT];
+#pragma unroll
+        for (int j = 0; j < RPT; j++) { keep_q[j] = 0.0f; keep_addr[j] = q_site0; }
+
+        for (int k = 0; k <= A.K; k++) {
+            const uint32_t par = (state_no + (uint32_t)k) & 1u, seq = state_no + (uint32_t)k + 1u;
+            const uint32_t cur = par * BUF;
+            __syncthreads();                              // own words of the lattice after sweep k-1 are in buffer `cur`
+            if (tid == 0 && k >= 2) {                     // statistics of sweep k-2: all warps added before this barrier
+                const int pk = s_stat[k & 1];
+                s_stat[k & 1] = 0;
+                atomicAdd(&A.n_up[(size_t)(k - 2) * A.B + b], pk & 0xFFFF);
+                if (A.reward_sum) atomicAdd(&A.reward_sum[(size_t)(k - 2) * A.B + b], (float)((pk >> 16) - 2 * RPT * NT));
+            }
+            // ---- halo words of state k: the boundary warps poll their own mailbox word ----
+            uint32_t top_word = 0, bot_word = 0;
+            if (first_band) {
+                const unsigned long long *mb = mailbox(rank, (int)par, 0);
+                unsigned long long v;
+                do { v = ld_halo(mb); } while ((uint32_t)(v >> 32) != seq);
+                top_word = (uint32_t)v;
+            } else top_word = lds_u32(own_w + cur - WPR * 4u);
+            if (last_band) {
+                const unsigned long long *mb = mailbox(rank, (int)par, 1);
+                unsigned long long v;
+                do { v = ld_halo(mb); } while ((uint32_t)(v >> 32) != seq);
+                bot_word = (uint32_t)v;
+            } else bot_word = lds_u32(own_w + cur + (uint32_t)RPT * WPR * 4u);
+            // ---- up-neighbour counts of the current lattice ----
+            int ups[RPT];
+            {
+                const int v_top = (int)((top_word >> lane) & 1u), v_bot = (int)((bot_word >> lane) & 1u);
+#pragma unroll
+                for (int j = 0; j < RPT; j++) {
+                    const int up = j == 0 ? v_top : a_cur[j - 1];
+                    const int dn = j == RPT - 1 ? v_bot : a_cur[j + 1];
+                    const uint32_t Wl = lds_u32(own_l + cur + (uint32_t)j * WPR * 4u), Wr = lds_u32(own_r + cur + (uint32_t)j * WPR * 4u);
+                    const uint32_t lf = __funnelshift_l(Wl, w_cur[j], 1), rt = __funnelshift_r(w_cur[j], Wr, 1);
+                    ups[j] = up + dn + (int)((lf >> lane) & 1u) + (int)((rt >> lane) & 1u);
+                }
+            }
+            // ---- finish sweep k-1: reward on the new lattice, Q update in shared memory, statistics ----
+            if (k > 0) {
+                int packed = 0;
+                uint32_t upd = 0xFFFFFFFFu;
+                if (MASK) {
+                    const uint8_t *m = A.mask + ((size_t)(k - 1) * A.B + b) * N + (size_t)(row0 + rb) * L + x;
+                    upd = 0;
+#pragma unroll
+                    for (int j = 0; j < RPT; j++) upd |= (m[j * L] ? 1u : 0u) << j;
+                }
+#pragma unroll
+                for (int j = 0; j < RPT; j++) {
+                    const int d = ups[j] - 2;
+                    const int ri = a_cur[j] ? d : -d;                                  // (2a-1)(ups-2) = Ising.py:101-111
+                    const float reward = (float)ri;
+                    if (!MASK || ((upd >> j) & 1u)) sts_f32(keep_addr[j], keep_q[j] + A.lr * (reward - keep_q[j]));
+                    packed += a_cur[j] + ((ri + 2) << 16);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) packed += __shfl_xor_sync(0xFFFFFFFFu, packed, o);
+                if (lane == 0) atomicAdd(&s_stat[(k - 1) & 1], packed);
+            }
+            if (k == A.K) break;
+            // ---- draw sweep k, publish state k+1 into the other buffer and the neighbours' mailboxes ----
+            if (A.u != nullptr) {
+#pragma unroll
+                for (int j = 0; j < RPT; j++)
+                    uu[j] = A.u[((size_t)k * A.B + b) * N + (size_t)(row0 + rb + j) * L + x] * 4294967296.0f;
+            }
+            const uint32_t nxt = cur ^ BUF;
+            float2 pr[RPT];
+#pragma unroll
+            for (int j = 0; j < RPT; j++) {
+                keep_addr[j] = q_site0 + (uint32_t)ups[j] * PLANE + (uint32_t)j * (L * 8u);
+                pr[j] = lds_f32x2(keep_addr[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < RPT; j++) a_cur[j] = draw_action_scaled(uu[j], pr[j].x, pr[j].y, tparam);
+#pragma unroll
+            for (int j = 0; j < RPT; j++) w_cur[j] = __ballot_sync(0xFFFFFFFFu, a_cur[j] != 0);
+            if (lane == 0) {
+                if (first_band) st_halo(mailbox(up_rank, (int)(par ^ 1u), 1), w_cur[0], seq + 1u);
+                if (last_band) st_halo(mailbox(dn_rank, (int)(par ^ 1u), 0), w_cur[RPT - 1], seq + 1u);
+#pragma unroll
+                for (int j = 0; j < RPT; j++) sts_u32(own_w + nxt + (uint32_t)j * WPR * 4u, w_cur[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < RPT; j++) {
+                keep_q[j] = a_cur[j] ? pr[j].y : pr[j].x;
+                keep_addr[j] += (uint32_t)a_cur[j] * 4u;
+            }
+            if (k + 1 < A.K) {
+                if (A.u == nullptr) draw_uniforms(A.step0 + (uint32_t)(k + 1));
+                tparam = temperature_param(A.temperatures[k + 1]);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const int kk = A.K - 1, pk = s_stat[kk & 1];
+            atomicAdd(&A.n_up[(size_t)kk * A.B + b], pk & 0xFFFF);
+            if (A.reward_sum) atomicAdd(&A.reward_sum[(size_t)kk * A.B + b], (float)((pk >> 16) - 2 * RPT * NT));
+        }
+        for (int sp = 0; sp < 5; sp++) {
+            float4 *d4 = (float4 *)(A.Q + (lbase * 5 + (size_t)sp * N + (size_t)row0 * L) * 2);
+            const float4 *s4 = (const float4 *)(s_q + (size_t)sp * STRIP * 2);
+#pragma unroll 4
+            for (int i = tid; i < STRIP / 2; i += NT) d4[i] = s4[i];
+        }
+#pragma unroll
+        for (int j = 0; j < RPT; j++) A.spins[lbase + (size_t)(row0 + rb + j) * L + x] = (int8_t)a_cur[j];
+    }
+}
+
 template <typename T>
 static size_t resident_smem_bytes(int L, int rows) {
     const int wpr = (L + 31) >> 5;
@@ -749,6 +955,50 @@ static void specialised_resident_kernel(const IsingRunArgs<float> &A, void (*&ke
 #undef MF_PICK
 }
 
+// K6p launcher (fp32, C > 1 strips per lattice): false = no persistent specialisation for this shape / switched off
+static bool launch_ising_persistent(const IsingRunArgs<double> &, cudaStream_t) { return false; }
+static bool launch_ising_persistent(const IsingRunArgs<float> &A, cudaStream_t st) {
+    const char *env = getenv("MFMARL_ISING_PERSIST");
+    if (env && atoi(env) == 0) return false;                        // 0 = the cluster kernel K6r (tests, comparisons)
+    const char *renv = getenv("MFMARL_ISING_RPT");
+    if (renv && atoi(renv) == 0) return false;                      // the generic kernel was asked for
+    const int rpt = renv ? atoi(renv) : 8;
+    void (*kern)(const IsingRunArgs<float>, int, unsigned long long *) = nullptr;
+    unsigned threads = 0;
+#define MF_PICK(LL, RR) \
+    if (A.L == LL && A.rows_per == RR) { \
+        if (rpt == 8) { kern = A.mask ? k_ising_persist_f32<LL, RR, 8, true> : k_ising_persist_f32<LL, RR, 8, false>; threads = LL * (RR / 8); } \
+        else { kern = A.mask ? k_ising_persist_f32<LL, RR, 4, true> : k_ising_persist_f32<LL, RR, 4, false>; threads = LL * (RR / 4); } \
+    }
+    MF_PICK(256, 16) MF_PICK(128, 32)
+#undef MF_PICK
+    if (!kern) return false;
+    const int C = A.L / A.rows_per, wpr = A.L / 32;
+    const size_t smem = resident_smem_bytes<float>(A.L, A.rows_per);
+    MF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, n_sm = 0, per_sm = 0;
+    MF_CUDA(cudaGetDevice(&dev));
+    MF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    MF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (int)threads, smem));
+    const int n_slots = std::min(A.B, per_sm * n_sm / C);           // lattices in flight: 9 of 16 strips on 148 SMs
+    if (n_slots < 1) return false;
+    unsigned long long *halo = nullptr;                              // mailboxes [slot][rank][parity][top|bottom][wpr]
+    const size_t halo_bytes = (size_t)n_slots * C * 2 * 2 * wpr * sizeof(unsigned long long);
+    MF_CUDA(cudaMallocAsync(&halo, halo_bytes, st));
+    MF_CUDA(cudaMemsetAsync(halo, 0, halo_bytes, st));              // sequence numbers start at 1
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(n_slots * C)); cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;                    // the strips of a lattice wait for each other: the
+    attr[0].val.cooperative = 1;                                    // whole grid must be resident at once
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const cudaError_t err = cudaLaunchKernelEx(&cfg, kern, A, n_slots, halo);
+    cudaFreeAsync(halo, st);
+    MF_CUDA(err);
+    return true;
+}
+
 template <typename T>
 static void launch_ising_resident(const IsingRunArgs<T> &A0, cudaStream_t st) {
     IsingRunArgs<T> A = A0;
@@ -756,6 +1006,7 @@ static void launch_ising_resident(const IsingRunArgs<T> &A0, cudaStream_t st) {
     const int C = resident_cluster_size<T>(L);
     if (C == 0) throw Fatal("ising resident kernel: lattice side " + std::to_string(L) + " not supported (use mfi_step)");
     A.rows_per = L / C;
+    if (C > 1 && launch_ising_persistent(A, st)) return;
     const int bands = (A.rows_per + kIsingRB - 1) / kIsingRB;
     const size_t smem = resident_smem_bytes<T>(L, A.rows_per);
     const bool fast = (L % 32 == 0) && (A.rows_per % kIsingRB == 0);
@@ -774,9 +1025,77 @@ static void launch_ising_resident(const IsingRunArgs<T> &A0, cudaStream_t st) {
     MF_CUDA(cudaLaunchKernelEx(&cfg, kern, A));
 }
 
+// ----------------------------------------------------------------------------------------------
+// The Ising ENVIRONMENT step on its own (examples/ising_model/multiagent/environment.py:49-92, core.py:99-125,
+// Ising.py:101-118): a caller-supplied action vector is applied, then every site gets its reward and observation
+// on the NEW lattice.  This is what IsingMultiAgentEnv.step / reset return, for callers that bring their own policy
+// (the unmodified main_MFQ_Ising.py); the fused kernels above are the same step with the tabular policy inside.
+//   k_ising_env_apply    spin_i <- [action_i > 0]                     (environment.py:112-114, core.py:118-125)
+//   k_ising_env_observe  obs_i = the 4 torus neighbours' spins in ascending flat-index order (Ising.py:113-118 returns
+//                        global_state.flatten()[np.where(mask == 1)]), reward_i = 0.5 sigma_i sum_nbr sigma_j
+//                        (Ising.py:101-111), n_up (core.py:106-110)
+// ----------------------------------------------------------------------------------------------
+__global__ void k_ising_env_apply(int8_t *__restrict__ spins, const int32_t *__restrict__ actions, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) spins[i] = actions[i] <= 0 ? 0 : 1;
+}
+
+__global__ void k_ising_env_observe(const int8_t *__restrict__ spins, int L, uint8_t *__restrict__ obs,
+                                    float *__restrict__ reward, int32_t *__restrict__ n_up) {
+    const int b = blockIdx.y, N = L * L;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int8_t *sp = spins + (size_t)b * N;
+    int a = 0;
+    if (i < N) {
+        const int r = i / L, c = i - r * L;
+        const int ru = r == 0 ? L - 1 : r - 1, rd = r == L - 1 ? 0 : r + 1;
+        const int cl = c == 0 ? L - 1 : c - 1, cr = c == L - 1 ? 0 : c + 1;
+        int id[4] = {ru * L + c, rd * L + c, r * L + cl, r * L + cr};
+        // np.where(mask == 1) lists the neighbours by ascending flat index: sort the four (5-comparator network)
+#define MF_CSWAP(x, y) { const int lo = min(id[x], id[y]), hi = max(id[x], id[y]); id[x] = lo; id[y] = hi; }
+        MF_CSWAP(0, 1) MF_CSWAP(2, 3) MF_CSWAP(0, 2) MF_CSWAP(1, 3) MF_CSWAP(1, 2)
+#undef MF_CSWAP
+        int ups = 0;
+        uint32_t packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const int v = sp[id[k]] != 0; ups += v; packed |= (uint32_t)v << (8 * k); }
+        a = sp[i] != 0;
+        if (obs) ((uint32_t *)obs)[(size_t)b * N + i] = packed;
+        if (reward) reward[(size_t)b * N + i] = 0.5f * (float)(2 * a - 1) * (float)(2 * ups - 4);
+    }
+    const unsigned up_mask = __ballot_sync(0xFFFFFFFFu, a != 0);
+    if (n_up && (threadIdx.x & 31) == 0 && up_mask) atomicAdd(&n_up[b], __popc(up_mask));
+}
+
 }  // namespace mfmarl
 
 using namespace mfmarl;
+
+extern "C" int mfi_env_step(int n_lattices, int side, int8_t *d_spins, const int32_t *d_actions, uint8_t *d_obs,
+                            float *d_reward, int32_t *d_n_up, void *stream) {
+    try {
+        if (n_lattices < 1 || side < 3) throw Fatal("mfi_env_step: need at least one lattice of side >= 3");
+        if (!d_spins) throw Fatal("mfi_env_step: null lattice");
+        if (d_obs && ((uintptr_t)d_obs & 3)) throw Fatal("mfi_env_step: d_obs must be 4-byte aligned");
+        cudaStream_t st = (cudaStream_t)stream;
+        const size_t n = (size_t)n_lattices * side * side;
+        if (d_actions) {
+            k_ising_env_apply<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_spins, d_actions, n);
+            MF_CUDA(cudaGetLastError());
+        }
+        if (d_obs || d_reward || d_n_up) {
+            if (d_n_up) MF_CUDA(cudaMemsetAsync(d_n_up, 0, (size_t)n_lattices * sizeof(int32_t), st));
+            const dim3 grid((unsigned)((side * side + 255) / 256), (unsigned)n_lattices);
+            k_ising_env_observe<<<grid, 256, 0, st>>>(d_spins, side, d_obs, d_reward, d_n_up);
+            MF_CUDA(cudaGetLastError());
+        }
+    } catch (const std::exception &ex) {
+        set_last_error(std::string("mfi_env_step: ") + ex.what());
+        return -1;
+    }
+    return 0;
+}
+
 
 extern "C" int mfi_step(int dtype, int n_lattices, int side, int8_t *d_spins, void *d_q, double temperature,
                         double lr, const void *d_uniforms, const uint8_t *d_update_mask, unsigned seed,

@@ -25,7 +25,7 @@ def _stream():
 
 class BatchedGridWorld:
     def __init__(self, n_envs, map_size=40, capacity=64, device=None, rng="minstd", seed=0, env_base=0,
-                 max_steps=0, auto_reset=False, step_threads=0, obs_tile_agents=0, **type_overrides):
+                 max_steps=0, auto_reset=False, step_threads=0, obs_tile_agents=0, obs_record=None, **type_overrides):
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedGridWorld needs a CUDA device: there is no CPU fallback")
         self.lib = load_library()
@@ -36,6 +36,8 @@ class BatchedGridWorld:
         cfg.rng_mode, cfg.seed, cfg.env_base = RNG_MODES[rng], seed, env_base
         cfg.max_steps, cfg.auto_reset, cfg.device = max_steps, int(auto_reset), self.device.index or 0
         cfg.step_threads, cfg.obs_tile_agents = step_threads, obs_tile_agents
+        if obs_record is not None:          # None = the engine decides (on for capacity >= 256)
+            cfg.obs_record = int(obs_record)
         for key, value in type_overrides.items():
             if not hasattr(cfg, key):
                 raise TypeError("unknown agent-type attribute %r" % key)
