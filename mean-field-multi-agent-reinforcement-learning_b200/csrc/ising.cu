@@ -741,7 +741,7 @@ __device__ __forceinline__ unsigned long long ld_halo(const unsigned long long *
 template <int L, int ROWS, int RPT, bool MASK>
 __global__ void __launch_bounds__(L * (ROWS / RPT), 1) k_ising_persist_f32(const IsingRunArgs<float> A, const int n_slots,
                                                                            unsigned long long *const halo) {
-    static_assert(L % 32 == 0 && ROWS % RPT == 0 && RPT % kIsingRB == 0 && L % ROWS == 0, "shape");
+    static_assert(L % 32 == 0 && ROWS % RPT == 0 && RPT % kIsingRB == 0 && L % ROWS == 0 && ROWS > RPT, "shape");
     constexpr int N = L * L, WPR = L / 32, HR = ROWS + 2, STRIP = ROWS * L, NT = L * (ROWS / RPT), C = L / ROWS;
     constexpr int NPH = RPT / kIsingRB;                         // Philox calls per thread per sweep
     constexpr uint32_t PLANE = (uint32_t)STRIP * 8u;            // bytes between the Q planes of consecutive s
@@ -761,11 +761,15 @@ __global__ void __launch_bounds__(L * (ROWS / RPT), 1) k_ising_persist_f32(const
     const uint32_t q_site0 = smem_addr(s_q) + (uint32_t)(rb * L + x) * 8u;          // Q pair of (s = 0, row rb, column x)
     const uint32_t own_w = bits0 + (uint32_t)((rb + 1) * WPR + w) * 4u;             // this thread's word of local row rb, buffer 0
     const uint32_t own_l = bits0 + (uint32_t)((rb + 1) * WPR + wl) * 4u, own_r = bits0 + (uint32_t)((rb + 1) * WPR + wr) * 4u;
-    const bool first_band = rb == 0, last_band = rb + RPT == ROWS;
-    // halo mailboxes in L2: [slot][rank][parity][top | bottom][WPR] -- rank r READS its own, neighbours write into it
-    auto mailbox = [&](int r, int parity, int bottom) {
-        return halo + ((((size_t)slot * C + r) * 2 + parity) * 2 + bottom) * WPR + w;
-    };
+    const bool first_band = rb == 0, last_band = rb + RPT == ROWS;                  // (never both: ROWS > RPT)
+    // halo mailboxes in L2: [slot][rank][parity][top | bottom][WPR] -- rank r READS its own, its neighbours write into it.
+    // A boundary warp reads one word (its 32 columns of the row above / below the strip) and writes one word.
+    constexpr size_t MB_PARITY = 2 * WPR;                                            // mailbox words between the two parities
+    const unsigned long long *const mb_in =
+        halo + (((size_t)slot * C + rank) * 2 * 2 + (last_band ? 1 : 0)) * WPR + w;
+    unsigned long long *const mb_out =
+        halo + (((size_t)slot * C + (first_band ? up_rank : dn_rank)) * 2 * 2 + (first_band ? 1 : 0)) * WPR + w;
+    const bool boundary = first_band || last_band;
 
     uint32_t state_no = 0;                                      // lattice states published so far by this slot
     for (int b = slot; b < A.B; b += n_slots, state_no += (uint32_t)A.K + 1u) {
@@ -779,6 +783,7 @@ __global__ void __launch_bounds__(L * (ROWS / RPT), 1) k_ising_persist_f32(const
             for (int i = tid; i < STRIP / 2; i += NT) d4[i] = s4[i];
         }
         int a_cur[RPT]; uint32_t w_cur[RPT];
+        unsigned long long hv = 0;                              // the halo word last read from the mailbox (word | seq << 32)
         {
             const uint32_t par = state_no & 1u, seq = state_no + 1u;
 #pragma unroll
@@ -787,9 +792,9 @@ __global__ void __launch_bounds__(L * (ROWS / RPT), 1) k_ising_persist_f32(const
                 w_cur[j] = __ballot_sync(0xFFFFFFFFu, a_cur[j] != 0);
                 if (lane == 0) sts_u32(own_w + par * BUF + (uint32_t)j * WPR * 4u, w_cur[j]);
             }
-            if (lane == 0) {
-                if (first_band) st_halo(mailbox(up_rank, (int)par, 1), w_cur[0], seq);       // I am the row below up_rank's last row
-                if (last_band) st_halo(mailbox(dn_rank, (int)par, 0), w_cur[RPT - 1], seq);  // ... and the row above dn_rank's first
+            if (boundary) {
+                if (lane == 0) st_halo(mb_out + par * MB_PARITY, first_band ? w_cur[0] : w_cur[RPT - 1], seq);
+                hv = ld_halo(mb_in + par * MB_PARITY);
             }
         }
         const uint2 key = make_uint2(A.seed, A.lattice_base + (uint32_t)b);
@@ -819,20 +824,12 @@ __global__ void __launch_bounds__(L * (ROWS / RPT), 1) k_ising_persist_f32(const
                 atomicAdd(&A.n_up[(size_t)(k - 2) * A.B + b], pk & 0xFFFF);
                 if (A.reward_sum) atomicAdd(&A.reward_sum[(size_t)(k - 2) * A.B + b], (float)((pk >> 16) - 2 * RPT * NT));
             }
-            // ---- halo words of state k: the boundary warps poll their own mailbox word ----
-            uint32_t top_word = 0, bot_word = 0;
-            if (first_band) {
-                const unsigned long long *mb = mailbox(rank, (int)par, 0);
-                unsigned long long v;
-                do { v = ld_halo(mb); } while ((uint32_t)(v >> 32) != seq);
-                top_word = (uint32_t)v;
-            } else top_word = lds_u32(own_w + cur - WPR * 4u);
-            if (last_band) {
-                const unsigned long long *mb = mailbox(rank, (int)par, 1);
-                unsigned long long v;
-                do { v = ld_halo(mb); } while ((uint32_t)(v >> 32) != seq);
-                bot_word = (uint32_t)v;
-            } else bot_word = lds_u32(own_w + cur + (uint32_t)RPT * WPR * 4u);
+            // ---- halo word of state k.  It was asked for at the end of the previous iteration, and the neighbour sent it
+            //      early in ITS previous iteration (boundary rows are drawn first), so it is normally already here ----
+            if (boundary)
+                while ((uint32_t)(hv >> 32) != seq) hv = ld_halo(mb_in + par * MB_PARITY);
+            const uint32_t top_word = first_band ? (uint32_t)hv : lds_u32(own_w + cur - WPR * 4u);
+            const uint32_t bot_word = last_band ? (uint32_t)hv : lds_u32(own_w + cur + (uint32_t)RPT * WPR * 4u);
             // ---- up-neighbour counts of the current lattice ----
             int ups[RPT];
             {
@@ -869,7 +866,8 @@ __global__ void __launch_bounds__(L * (ROWS / RPT), 1) k_ising_persist_f32(const
                 if (lane == 0) atomicAdd(&s_stat[(k - 1) & 1], packed);
             }
             if (k == A.K) break;
-            // ---- draw sweep k, publish state k+1 into the other buffer and the neighbours' mailboxes ----
+            // ---- draw sweep k.  The strip's boundary row goes FIRST and straight into the neighbour's mailbox, so that
+            //      the L2 round trip of the halo runs under the other rows' draws; the next halo is asked for right away ----
             if (A.u != nullptr) {
 #pragma unroll
                 for (int j = 0; j < RPT; j++)
@@ -882,13 +880,20 @@ __global__ void __launch_bounds__(L * (ROWS / RPT), 1) k_ising_persist_f32(const
                 keep_addr[j] = q_site0 + (uint32_t)ups[j] * PLANE + (uint32_t)j * (L * 8u);
                 pr[j] = lds_f32x2(keep_addr[j]);
             }
+            if (boundary) {
+                if (first_band) { a_cur[0] = draw_action_scaled(uu[0], pr[0].x, pr[0].y, tparam); w_cur[0] = __ballot_sync(0xFFFFFFFFu, a_cur[0] != 0); }
+                else { a_cur[RPT - 1] = draw_action_scaled(uu[RPT - 1], pr[RPT - 1].x, pr[RPT - 1].y, tparam); w_cur[RPT - 1] = __ballot_sync(0xFFFFFFFFu, a_cur[RPT - 1] != 0); }
+                if (lane == 0) st_halo(mb_out + (par ^ 1u) * MB_PARITY, first_band ? w_cur[0] : w_cur[RPT - 1], seq + 1u);
+            }
 #pragma unroll
-            for (int j = 0; j < RPT; j++) a_cur[j] = draw_action_scaled(uu[j], pr[j].x, pr[j].y, tparam);
+            for (int j = 0; j < RPT; j++)
+                if (!((j == 0 && first_band) || (j == RPT - 1 && last_band)))
+                    a_cur[j] = draw_action_scaled(uu[j], pr[j].x, pr[j].y, tparam);
 #pragma unroll
-            for (int j = 0; j < RPT; j++) w_cur[j] = __ballot_sync(0xFFFFFFFFu, a_cur[j] != 0);
+            for (int j = 0; j < RPT; j++)
+                if (!((j == 0 && first_band) || (j == RPT - 1 && last_band)))
+                    w_cur[j] = __ballot_sync(0xFFFFFFFFu, a_cur[j] != 0);
             if (lane == 0) {
-                if (first_band) st_halo(mailbox(up_rank, (int)(par ^ 1u), 1), w_cur[0], seq + 1u);
-                if (last_band) st_halo(mailbox(dn_rank, (int)(par ^ 1u), 0), w_cur[RPT - 1], seq + 1u);
 #pragma unroll
                 for (int j = 0; j < RPT; j++) sts_u32(own_w + nxt + (uint32_t)j * WPR * 4u, w_cur[j]);
             }
@@ -901,6 +906,7 @@ __global__ void __launch_bounds__(L * (ROWS / RPT), 1) k_ising_persist_f32(const
                 if (A.u == nullptr) draw_uniforms(A.step0 + (uint32_t)(k + 1));
                 tparam = temperature_param(A.temperatures[k + 1]);
             }
+            if (boundary) hv = ld_halo(mb_in + (par ^ 1u) * MB_PARITY);   // state k+1's halo: in flight until the next iteration looks
         }
         __syncthreads();
         if (tid == 0) {

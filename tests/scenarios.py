@@ -3,29 +3,7 @@
 import numpy as np
 
 
-def generate_map_positions(map_size):
-    """Placement of senario_battle.generate_map (senario_battle.py:8-37): two square blocks at
-    stride 2, `gap` 3 either side of the centre line.  -> (left [n,3], right [n,3])."""
-    import math
-    width = height = map_size
-    side = int(math.sqrt(map_size * map_size * 0.04)) * 2
-    gap = 3
-    left = [[x, y, 0] for x in range(width // 2 - gap - side, width // 2 - gap, 2)
-            for y in range((height - side) // 2, (height - side) // 2 + side, 2)]
-    right = [[x, y, 0] for x in range(width // 2 + gap, width // 2 + gap + side, 2)
-             for y in range((height - side) // 2, (height - side) // 2 + side, 2)]
-    return np.array(left, np.int32), np.array(right, np.int32)
-
-
-def block_positions(x0, y0, cols, rows, stride=2):
-    return np.array([[x0 + stride * c, y0 + stride * r, 0] for c in range(cols) for r in range(rows)],
-                    np.int32)
-
-
-def c4_positions():
-    """BASELINE config 4 (80x80, 512 v 512): two 16-col x 32-row blocks at stride 2, left x0=5,
-    right x0=43, y0=8."""
-    return block_positions(5, 8, 16, 32), block_positions(43, 8, 16, 32)
+from mfmarl_b200.scenarios import block_positions, c4_positions, generate_map_positions  # noqa: F401  (the product's own placements)
 
 
 # action ids for the battle config (SURVEY.md section 8): 0-12 moves, 13-20 attacks
