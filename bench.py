@@ -265,8 +265,11 @@ class Ctx:
 
 
 def repeat_count(ctx, first_region_ms, min_seconds, cap=400):
-    """how often the K-step region is timed: enough for min_seconds of device time, the same number on every rank"""
+    """how often the K-step region is timed: enough for min_seconds of device time and at least 3 times (a median needs
+    them) unless one region already takes seconds; the same number on every rank"""
     r = int(min(cap, max(1, -(-min_seconds * 1e3 // max(first_region_ms, 1e-3)))))
+    if first_region_ms < 2000.0:
+        r = max(r, 3)
     return int(ctx.reduce([r], "max")[0])
 
 
@@ -304,11 +307,6 @@ def measure_battle(ctx, args, workload, K, W, min_seconds, envs_per_gpu=0, pipel
         env.reset(); env.add_agents(0, left); env.add_agents(1, right)
         envs.append(env)
     streams = [torch.cuda.current_stream()] if P == 1 else [torch.cuda.Stream(device=dev) for _ in range(P)]
-    # --step-priority: k_step on a HIGH-priority stream of its own (chained to the engine's k_obs by events), so that
-    # when SM slots free up the waiting k_step CTAs are placed before the other engine's k_obs CTAs
-    hi = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(P)] if (args.step_priority and P > 1) else None
-    hi_ev = [[torch.cuda.Event() for _ in range(2)] for _ in range(P)] if hi else None
-
     # synthetic actions, uniform{0..20} from torch's Philox generator, resident in HBM: a pool the steps cycle through
     gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
     POOL = 8
@@ -326,15 +324,8 @@ def measure_battle(ctx, args, workload, K, W, min_seconds, envs_per_gpu=0, pipel
             if events: events[0].record(st)
             env.observe()
             if events: events[1].record(st)
-        if hi:
-            hi_ev[h][0].record(st); hi[h].wait_event(hi_ev[h][0])
-            with torch.cuda.stream(hi[h]):
-                env.step(pool[h][k % POOL])
-            hi_ev[h][1].record(hi[h]); st.wait_event(hi_ev[h][1])
-        else:
-            with torch.cuda.stream(st):
-                env.step(pool[h][k % POOL])
-        if events: events[2].record(st)
+            env.step(pool[h][k % POOL])
+            if events: events[2].record(st)
 
     for k in range(W):
         for h, env in enumerate(envs):
@@ -476,7 +467,7 @@ def measure_battle(ctx, args, workload, K, W, min_seconds, envs_per_gpu=0, pipel
     # different engines overlap (with each other and with k_step), so a launch's own event pair contains time it
     # shared the memory system; the duration charged per launch is then the timed region divided by the number of
     # k_obs launches -- conservative, since the region also contains every k_step.
-    launch_ms = obs_ms if P == 1 else region_ms[0] / (K * P)
+    launch_ms = obs_ms if P == 1 else ms / (K * P)
     achieved = agents_per_launch * BYTES_PER_AGENT_OBS / (launch_ms * 1e-3) / 1e9
     return {
         "metric": "battle agent-steps/sec incl. obs+mean-action",
@@ -491,7 +482,7 @@ def measure_battle(ctx, args, workload, K, W, min_seconds, envs_per_gpu=0, pipel
                    "l2": "outputs per step (%.2f GB) exceed the 126 MB L2; no explicit flush"
                          % (E * 2 * cap * BYTES_PER_AGENT_OBS / 1e9),
                    "sharding": "envs [r*E,(r+1)*E) on rank r, no collective on the env path",
-                   "pipeline": "%d engine(s) x %d envs on %d stream(s)%s" % (P, Eh, P, ", k_step on high-priority streams" if hi else ""),
+                   "pipeline": "%d engine(s) x %d envs on %d stream(s)" % (P, Eh, P),
                    "obs_tile_agents": tile or "engine default",
                    "timed_region": "exactly %d steps, repeated %d times (>= %.2f s of device time); the repeat with the "
                                    "median time is reported" % (K, regions["repeats"], min_seconds)},
@@ -569,8 +560,7 @@ def run_ours(args):
     also = {}
     if args.workload == "c3" and not args.no_also:
         # the other two named shapes under the same clock (BASELINE configs[3] and [4]): shorter legs, same rules
-        c4 = measure_battle(ctx, args, "c4", min(args.steps, 50), max(3, min(args.warmup, 10)), 0.25, pipeline=2,
-                            obs_tile=128, extras=False)
+        c4 = measure_battle(ctx, args, "c4", 200, max(3, min(args.warmup, 10)), 0.25, pipeline=2, obs_tile=128, extras=False)
         c5 = measure_ising(ctx, args, min(max(args.steps, 100), 200), max(3, args.warmup), 0.25)
         if ctx.rank == 0:
             keep = ("metric", "value", "unit", "ms_per_step", "scaling", "config", "region_ms", "roofline", "e2e",
@@ -891,8 +881,6 @@ def main():
                     help="c5: Ising sweeps per launch (1 = streaming kernel, >1 = shared-memory-resident kernel, 0 = auto)")
     ap.add_argument("--obs-tile", type=int, default=0, help="agents per k_obs CTA (tuning; 0 = engine default)")
     ap.add_argument("--step-threads", type=int, default=0, help="threads per k_step CTA (tuning; 0 = auto)")
-    ap.add_argument("--step-priority", action="store_true",
-                    help="experiment: k_step on high-priority streams chained to k_obs by events (with --pipeline > 1)")
     ap.add_argument("--no-also", action="store_true",
                     help="skip the extra legs of the default line (C4, C5, and the gradient all-reduce when N > 1)")
     args = ap.parse_args()

@@ -617,6 +617,16 @@ __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState
         }
         if (tid < 2) S.dead_ct[e * 2 + tid] = s_misc[MISC_DEAD + tid];
     }
+    if (io.mirror.pos != nullptr) {                               // single-env ABI: the host's copy of the records
+        __syncthreads();                                          // the write-back above is visible to the whole CTA
+        for (int s = tid; s < 2 * cap; s += nt) {
+            io.mirror.pos[s] = S.pos[ebase + s]; io.mirror.id[s] = S.id[ebase + s]; io.mirror.state[s] = S.state[ebase + s];
+            io.mirror.hp[s] = S.hp[ebase + s]; io.mirror.next_rew[s] = S.next_rew[ebase + s];
+            io.mirror.last_rew[s] = S.last_rew[ebase + s];
+        }
+        if (tid < 2) { io.mirror.head[tid] = S.num[e * 2 + tid]; io.mirror.head[2 + tid] = S.dead_ct[e * 2 + tid]; }
+        if (tid == 0) { io.mirror.head[4] = done; io.mirror.head[5] = S.step_ct[e]; }
+    }
     if (P.obs_cached && (phases & (PH_STEP | PH_CLEAR))) {        // positions / alive flags / slot indices changed
         __syncthreads();                                          // the write-back above is visible to the whole CTA
         build_obs_record(P, S, e, (uint16_t *)(smem_raw + L.grid),

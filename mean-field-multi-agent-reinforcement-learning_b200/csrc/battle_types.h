@@ -87,6 +87,13 @@ struct BattleState {   // device pointers
     int32_t *init_pos; int32_t *init_num;   // [2][cap], [2]
 };
 
+// Host mirror of ONE environment's agent records (single-env ABI): mapped pinned memory k_step writes at its end,
+// so the getters of runtime_api.cu answer without a copy on the critical path.
+struct StepMirror {
+    int32_t *pos; int32_t *id; uint32_t *state; float *hp; float *next_rew; float *last_rew;   // [2][cap] each
+    int32_t *head;   // [8]: num[2], dead_ct[2], done, step_ct, 0, 0
+};
+
 struct StepIO {
     const int32_t *actions;     // [E][2][cap] (PH_SETACT)
     const int32_t *attack_perm; // [E][2*cap]  (RNG_INJECT) new order -> pre-shuffle index
@@ -96,6 +103,7 @@ struct StepIO {
     int32_t *done;              // [E]
     int32_t *attack_events;     // optional [E][1 + 3*2*cap]: count, then per attack of the shuffled order (attacker id or
                                 // -1 when it was dead at its turn, target x, target y) -- the render trace's events
+    StepMirror mirror;          // optional (E == 1, pos != nullptr): the records as this launch leaves them
     int phases;
     int setact_mask;            // groups whose actions are applied by PH_SETACT
     int group_seq[kGroups];     // order in which groups called set_action (-1 = did not act)

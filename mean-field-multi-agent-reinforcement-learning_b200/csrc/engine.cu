@@ -350,6 +350,23 @@ void Engine::late_add_sync_up() {
     MF_CUDA(cudaStreamSynchronize(nullptr));
 }
 
+void Engine::restore_state(const int32_t *pos, const int32_t *id, const uint32_t *state, const float *hp,
+                           const float *next_rew, const float *last_rew, const int32_t *num, const int32_t *dead_ct,
+                           cudaStream_t st) {
+    if (P_.E != 1) throw Fatal("restore_state needs a single env");
+    const size_t bytes = slots() * 4;
+    MF_CUDA(cudaMemcpyAsync(S_.pos, pos, bytes, cudaMemcpyHostToDevice, st));
+    MF_CUDA(cudaMemcpyAsync(S_.id, id, bytes, cudaMemcpyHostToDevice, st));
+    MF_CUDA(cudaMemcpyAsync(S_.state, state, bytes, cudaMemcpyHostToDevice, st));
+    MF_CUDA(cudaMemcpyAsync(S_.hp, hp, bytes, cudaMemcpyHostToDevice, st));
+    MF_CUDA(cudaMemcpyAsync(S_.next_rew, next_rew, bytes, cudaMemcpyHostToDevice, st));
+    MF_CUDA(cudaMemcpyAsync(S_.last_rew, last_rew, bytes, cudaMemcpyHostToDevice, st));
+    MF_CUDA(cudaMemcpyAsync(S_.num, num, 8, cudaMemcpyHostToDevice, st));
+    MF_CUDA(cudaMemcpyAsync(S_.dead_ct, dead_ct, 8, cudaMemcpyHostToDevice, st));
+    h_num_[0] = num[0]; h_num_[1] = num[1];
+    rebuild_obs_records(st);
+}
+
 void Engine::rebuild_obs_records(cudaStream_t st) {
     if (!P_.obs_cached) return;
     const int smem = obs_record_layout(P_.W, P_.H, P_.cap).hp10 + 4 * 2 * kViewCells;

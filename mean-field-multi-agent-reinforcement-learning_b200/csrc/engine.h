@@ -73,6 +73,11 @@ public:
     static void mean_action(const int32_t *d_actions, const int32_t *d_num, float *d_out, int rows,
                             int cap, int n_action, cudaStream_t st);
 
+    // E == 1: overwrite the agent records with a host copy (mapped pinned memory; runtime_api.cu rolls back a speculative
+    // clear_dead with it).  Asynchronous on `st`.
+    void restore_state(const int32_t *pos, const int32_t *id, const uint32_t *state, const float *hp, const float *next_rew,
+                       const float *last_rew, const int32_t *num, const int32_t *dead_ct, cudaStream_t st);
+
     // ---- state access ----
     void commit(cudaStream_t st);                // upload a pending placement
     void download_num(cudaStream_t st);          // refresh h_num from the device (syncs)

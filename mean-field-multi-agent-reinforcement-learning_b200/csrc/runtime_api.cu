@@ -58,18 +58,32 @@ struct Game {
     std::vector<int> seq;          // groups in set_action call order since the last step
     bool inject_next = false;
 
-    // Host mirror (pinned).  Every env_* call of the reference ABI is synchronous, so the cost of one environment
-    // is the number of stream synchronisations per step, not kernel time.  The mirror brings it from ~12 to 3:
-    //   * set_action only stages the actions on the host; env_step uploads both groups and runs set_action x2 + step
-    //     in ONE launch (if an observation or a getter is asked for in between, the staged actions are applied first);
-    //   * after step / clear_dead the agents' pos, id, state, hp and reward come back in one batch, and get_reward,
-    //     get_alive, get_pos, get_agent_id, mean_info, global_minimap and render answer from it;
-    //   * the first get_observation after a state change computes and downloads BOTH groups' rows.
+    // Host mirror (pinned, mapped).  Every env_* call of the reference ABI is synchronous, so the cost of one environment
+    // is what sits between a call and its answer, not kernel time:
+    //   * set_action only stages the actions on the host; env_step runs set_action x2 + step in ONE launch that reads
+    //     them straight from the pinned buffer (if an observation or a getter is asked for in between, the staged
+    //     actions are applied first);
+    //   * k_step itself writes the agents' records into the mirror (StepIO::mirror): get_reward, get_alive, get_pos,
+    //     get_agent_id, mean_info, global_minimap and render answer from it, no copy;
+    //   * SPECULATION: the play loop (senario_battle.py:96-168) always continues step -> get_reward / get_alive ->
+    //     clear_dead -> get_observation x2.  env_step therefore also enqueues clear_dead, the observation kernel for both
+    //     groups and one device->host copy per observation buffer BEHIND the step, and returns as soon as the step's
+    //     own results are on the host; the rest runs while the caller is busy with the rewards.  clear_dead then only
+    //     commits what already ran, get_observation waits for an event that has normally fired.  Any other call
+    //     order (an observation before clear_dead, a second step, add_agents ...) ROLLS BACK: the records k_step left
+    //     in the mirror are written back to the device, and the call proceeds as if nothing had been enqueued.
     char *pin = nullptr; int pin_cap = 0;
+    struct Mirror { int32_t *pos, *id; uint32_t *state; float *hp, *rew, *lrew; int32_t *head; } mir[2] = {};
+    int cur = 0;                   // mir[cur] is the one the getters read (the aliases below point into it)
     int32_t *m_pos = nullptr, *m_id = nullptr, *m_actions = nullptr; uint32_t *m_state = nullptr;
     float *m_hp = nullptr, *m_rew = nullptr, *m_view = nullptr, *m_feat = nullptr;
     bool state_fresh = false, obs_fresh = false;
     unsigned pending_mask = 0;     // groups whose staged actions have not reached the device yet
+    cudaEvent_t ev_step = nullptr, ev_spec = nullptr;
+    bool speculate = true;         // MAGENT_SPECULATE=0 switches it off
+    bool spec_pending = false;     // clear_dead + observe are enqueued behind the last step, not asked for yet
+    bool spec_state = false;       // committed: mir[cur ^ 1] holds the records after clear_dead once ev_spec fires
+    bool spec_obs = false;         // committed: m_view / m_feat hold both groups' rows once ev_spec fires
 
     // render trace (RenderGenerator.cc): config.json once, then frames appended to video_<file_ct>.txt
     std::string render_dir;
@@ -81,26 +95,53 @@ struct Game {
     ~Game() {
         cudaFree(d_view); cudaFree(d_feat); cudaFree(d_actions); cudaFree(d_perm); cudaFree(d_done); cudaFree(d_events);
         cudaFreeHost(pin);
+        if (ev_step) cudaEventDestroy(ev_step);
+        if (ev_spec) cudaEventDestroy(ev_spec);
     }
 
-    void invalidate() { state_fresh = false; obs_fresh = false; }
+    void invalidate() { state_fresh = false; obs_fresh = false; spec_state = false; spec_obs = false; }
+
+    void use_mirror(int which) {
+        cur = which;
+        m_pos = mir[cur].pos; m_id = mir[cur].id; m_state = mir[cur].state; m_hp = mir[cur].hp; m_rew = mir[cur].rew;
+    }
+    StepMirror mirror_io(int which) const {
+        const Mirror &m = mir[which];
+        return StepMirror{m.pos, m.id, m.state, m.hp, m.rew, m.lrew, m.head};
+    }
+
+    // something other than clear_dead followed a step: undo the speculative clear_dead (see above)
+    void rollback() {
+        if (!spec_pending) return;
+        MF_CUDA(cudaEventSynchronize(ev_spec));
+        const Mirror &m = mir[cur];                        // the records as the step left them
+        engine().restore_state(m.pos, m.id, m.state, m.hp, m.rew, m.lrew, m.head, m.head + 2, st);
+        MF_CUDA(cudaStreamSynchronize(st));
+        spec_pending = false; obs_fresh = false;
+    }
 
     void ensure_mirror() {
         const int cap = engine().cap(), FS = engine().params().feature_size;
         if (pin_cap >= cap) return;
         std::vector<int32_t> keep(m_actions ? m_actions : nullptr, m_actions ? m_actions + 2 * pin_cap : nullptr);
         const int old_cap = pin_cap;
+        if (st) MF_CUDA(cudaStreamSynchronize(st));
         cudaFreeHost(pin);
         const size_t n = (size_t)2 * cap;
-        MF_CUDA(cudaMallocHost(&pin, n * 4 * 6 + n * (kViewRow + FS) * 4));
+        MF_CUDA(cudaMallocHost(&pin, 2 * (n * 4 * 6 + 64) + n * 4 + n * (kViewRow + FS) * 4));
         char *p = pin;
-        m_pos = (int32_t *)p; p += n * 4; m_id = (int32_t *)p; p += n * 4; m_state = (uint32_t *)p; p += n * 4;
-        m_hp = (float *)p; p += n * 4; m_rew = (float *)p; p += n * 4; m_actions = (int32_t *)p; p += n * 4;
+        for (Mirror &m : mir) {
+            m.pos = (int32_t *)p; p += n * 4; m.id = (int32_t *)p; p += n * 4; m.state = (uint32_t *)p; p += n * 4;
+            m.hp = (float *)p; p += n * 4; m.rew = (float *)p; p += n * 4; m.lrew = (float *)p; p += n * 4;
+            m.head = (int32_t *)p; p += 64;
+        }
+        m_actions = (int32_t *)p; p += n * 4;
         m_view = (float *)p; p += n * kViewRow * 4; m_feat = (float *)p;
         memset(m_actions, 0, n * 4);
         for (int grp = 0; grp < 2 && old_cap > 0; grp++)      // staged actions survive a capacity growth
             memcpy(m_actions + (size_t)grp * cap, keep.data() + (size_t)grp * old_cap, (size_t)old_cap * 4);
         pin_cap = cap;
+        use_mirror(0);
         invalidate();
     }
 
@@ -131,6 +172,12 @@ struct Game {
     void fetch_state() {
         flush_actions();
         if (state_fresh) return;
+        if (spec_state) {                          // the records after clear_dead were written behind the step
+            MF_CUDA(cudaEventSynchronize(ev_spec));
+            use_mirror(cur ^ 1);
+            spec_state = false; state_fresh = true;
+            return;
+        }
         enqueue_state_download();
         MF_CUDA(cudaStreamSynchronize(st));
         state_fresh = true;
@@ -188,6 +235,10 @@ struct Game {
         eng.reset(new Engine(c));
         if (seed_set) eng->set_seed(seed);
         MF_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        MF_CUDA(cudaEventCreateWithFlags(&ev_step, cudaEventDisableTiming));
+        MF_CUDA(cudaEventCreateWithFlags(&ev_spec, cudaEventDisableTiming));
+        const char *sp = getenv("MAGENT_SPECULATE");
+        speculate = !(sp && atoi(sp) == 0);
     }
 
     void ensure_staging() {
@@ -282,7 +333,7 @@ int env_reset(EnvHandle game) {
     g->ensure_engine();
     g->eng->reset();
     g->seq.clear();
-    g->pending_mask = 0; g->invalidate();
+    g->pending_mask = 0; g->invalidate(); g->spec_pending = false;   // (whatever was enqueued is overwritten by the placement)
     g->file_ct++; g->frame_ct = 0;                        // RenderGenerator::next_file (GridWorld.cc:102)
     API_END("env_reset")
 }
@@ -292,10 +343,15 @@ int env_get_observation(EnvHandle game, GroupHandle group, float **buffer) {
     Game *g = G(game);
     Engine &E = g->engine();
     g->type_of(group);
+    g->rollback();                            // an observation BEFORE clear_dead still lists the dead
     g->ensure_staging();
     g->flush_actions();                       // features carry the last action (GridWorld.cc:411-417)
     const int n = E.host_num(0, group), cap = E.cap(), FS = E.params().feature_size;
     if (n == 0) return 0;
+    if (!g->obs_fresh && g->spec_obs) {       // both groups' rows were computed and copied behind the last step
+        MF_CUDA(cudaEventSynchronize(g->ev_spec));
+        g->spec_obs = false; g->obs_fresh = true;
+    }
     if (!g->obs_fresh) {                      // both groups in one launch, one batch of copies, one synchronisation
         const int n0 = E.host_num(0, 0), n1 = E.host_num(0, 1);
         E.observe(g->d_view, g->d_feat, (n0 > 0 ? 1 : 0) | (n1 > 0 ? 2 : 0), g->st);
@@ -320,6 +376,7 @@ int env_set_action(EnvHandle game, GroupHandle group, const int *actions) {
     Game *g = G(game);
     Engine &E = g->engine();
     g->type_of(group);
+    g->rollback();
     g->ensure_staging();
     for (int s : g->seq)
         if (s == group) throw Fatal("set_action called twice for one group before step");
@@ -335,40 +392,55 @@ int env_step(EnvHandle game, int *done) {
     API_BEGIN
     Game *g = G(game);
     Engine &E = g->engine();
+    g->rollback();                            // a second step without clear_dead keeps the dead in the lists
     g->ensure_staging();
+    const int cap = E.cap();
+    const int into = g->cur ^ 1;              // the step's records go to the mirror the getters are not reading
     StepIO io{};
     io.phases = PH_STEP; io.done = g->d_done; io.attack_perm = g->d_perm;
     io.group_seq[0] = g->seq.size() > 0 ? g->seq[0] : -1;
     io.group_seq[1] = g->seq.size() > 1 ? g->seq[1] : -1;
-    if (g->pending_mask) {                    // set_action(g0), set_action(g1) and step in one launch
-        MF_CUDA(cudaMemcpyAsync(g->d_actions, g->m_actions, (size_t)2 * E.cap() * 4, cudaMemcpyHostToDevice, g->st));
-        io.actions = g->d_actions; io.phases |= PH_SETACT; io.setact_mask = (int)g->pending_mask;
+    io.mirror = g->mirror_io(into);
+    if (g->pending_mask) {                    // set_action(g0), set_action(g1) and step in one launch; the kernel reads
+        io.actions = g->m_actions;            // the staged actions from the mapped pinned buffer itself
+        io.phases |= PH_SETACT; io.setact_mask = (int)g->pending_mask;
         g->pending_mask = 0;
     }
     if (g->inject_next) E.set_rng_mode(RNG_INJECT);
     const bool want_events = !g->first_render;            // GridWorld.cc:533,559: recorded once a frame was rendered
     if (want_events) {
-        if (g->ev_cap < E.cap()) {
+        if (g->ev_cap < cap) {
             cudaFree(g->d_events);
-            MF_CUDA(cudaMalloc(&g->d_events, (size_t)(1 + 6 * E.cap()) * 4));
-            g->ev_cap = E.cap();
+            MF_CUDA(cudaMalloc(&g->d_events, (size_t)(1 + 6 * cap) * 4));
+            g->ev_cap = cap;
         }
         io.attack_events = g->d_events;
     }
     E.step(io, g->st);
+    MF_CUDA(cudaEventRecord(g->ev_step, g->st));
+    if (g->inject_next) { E.set_rng_mode(RNG_MINSTD); g->inject_next = false; }
     if (want_events) {
-        const std::vector<int32_t> raw = pull(g->d_events, (size_t)1 + 6 * E.cap(), g->st);
+        const std::vector<int32_t> raw = pull(g->d_events, (size_t)1 + 6 * cap, g->st);
         g->events.clear();
         for (int i = 0; i < raw[0]; i++)
             if (raw[1 + 3 * i] >= 0) g->events.insert(g->events.end(), raw.begin() + 1 + 3 * i, raw.begin() + 4 + 3 * i);
+    } else if (g->speculate) {
+        // what the play loop asks for next, enqueued now: clear_dead (its records into the OTHER mirror), both groups'
+        // observations, one copy per observation buffer
+        StepIO c{};
+        c.phases = PH_CLEAR; c.group_seq[0] = c.group_seq[1] = -1; c.mirror = g->mirror_io(g->cur);
+        E.step(c, g->st);
+        E.observe(g->d_view, g->d_feat, 3, g->st);
+        const int FS = E.params().feature_size;
+        MF_CUDA(cudaMemcpyAsync(g->m_view, g->d_view, (size_t)2 * cap * kViewRow * 4, cudaMemcpyDeviceToHost, g->st));
+        MF_CUDA(cudaMemcpyAsync(g->m_feat, g->d_feat, (size_t)2 * cap * FS * 4, cudaMemcpyDeviceToHost, g->st));
+        MF_CUDA(cudaEventRecord(g->ev_spec, g->st));
+        g->spec_pending = true;
     }
-    if (g->inject_next) { E.set_rng_mode(RNG_MINSTD); g->inject_next = false; }
-    int h_done = 0;
-    MF_CUDA(cudaMemcpyAsync(&h_done, g->d_done, 4, cudaMemcpyDeviceToHost, g->st));
-    g->enqueue_state_download();              // rewards, alive flags, positions: what the caller asks for next
-    MF_CUDA(cudaStreamSynchronize(g->st));
-    g->state_fresh = true; g->obs_fresh = false;
-    *done = h_done;
+    MF_CUDA(cudaEventSynchronize(g->ev_step));            // rewards, alive flags, positions, done: in the mirror now
+    g->use_mirror(into);
+    g->state_fresh = true; g->obs_fresh = false; g->spec_state = false; g->spec_obs = false;
+    *done = g->mir[into].head[4];
     g->seq.clear();
     API_END("env_step")
 }
@@ -624,6 +696,7 @@ int gridworld_add_agents(EnvHandle game, GroupHandle group, int n, const char *m
     (void)dir;   // no turn_mode: every agent faces NORTH (GridWorld.cc:264)
     Game *g = G(game);
     Engine &E = g->engine();
+    g->rollback();
     std::vector<int> xs, ys;
     if (streq(method, "custom")) {
         xs.assign(pos_x, pos_x + n); ys.assign(pos_y, pos_y + n);
@@ -672,6 +745,12 @@ int gridworld_clear_dead(EnvHandle game) {
         int alive = 0;
         for (int i = 0; i < n; i++) alive += !(st[i] & 1u);
         E.set_host_num(0, grp, alive);
+    }
+    if (g->spec_pending) {                    // it already ran behind the step: commit
+        g->spec_pending = false;
+        g->state_fresh = false; g->obs_fresh = false;
+        g->spec_state = true; g->spec_obs = true;
+        return 0;
     }
     io.phases = PH_CLEAR; io.group_seq[0] = io.group_seq[1] = -1;
     E.step(io, g->st);

@@ -193,3 +193,45 @@ def test_two_engine_shapes_interleaved_in_one_process():
     run_lockstep(small_o, small, steps=3, seed=6, stream="fight", check_obs_every=1)
     run_lockstep(big_o, big, steps=3, seed=7, stream="fight", check_obs_every=1)
     run_lockstep(small_o, small, steps=3, seed=8, stream="fight", check_obs_every=1)
+
+
+def test_speculation_rolls_back_when_the_caller_leaves_the_play_loop_order():
+    """env_step enqueues clear_dead + both observations behind the step (runtime_api.cu).  Whatever the caller does
+    next must see the reference's state: a second step without clear_dead, set_action / get_observation / add_agents
+    between step and clear_dead (the dead still listed, GridWorld.cc:696-728 not run yet)."""
+    ora, cu = OracleEngine(40), CudaEngine(40)
+    setup_pair([ora, cu], *generate_map_positions(40))
+    # (a) no observation at all and every 3rd clear_dead skipped: after a skipped one, set_action is the first call
+    st = run_lockstep(ora, cu, steps=90, seed=31, stream="fight", check_obs_every=0, skip_clear_every=3)
+    assert st["deaths"] > 5, st
+    # (b) observation between step and clear_dead on every step
+    rng = np.random.RandomState(5)
+    from scenarios import fight_actions
+    for s in range(30):
+        for g in range(2):
+            a = fight_actions(rng, ora.get_pos(g), 40)
+            ora.set_action(g, a); cu.set_action(g, a)
+        assert ora.step() == cu.step()
+        for g in range(2):
+            va, fa = ora.get_observation(g); vb, fb = cu.get_observation(g)
+            assert_same("view before clear_dead", va, vb, s); assert_same("feature before clear_dead", fa, fb, s)
+            assert_same("reward", ora.get_reward(g), cu.get_reward(g), s)
+            assert_same("alive", ora.get_alive(g), cu.get_alive(g), s)
+        if s % 7 == 3:                      # (c) a late add between step and clear_dead
+            extra = np.array([[2 + s % 5, 2, 0], [3 + s % 5, 37, 0]], np.int32)
+            for eng in (ora, cu):
+                eng.add_agents(s % 2, extra)
+        ora.clear_dead(); cu.clear_dead()
+        for g in range(2):
+            assert ora.get_num(g) == cu.get_num(g)
+            assert_same("id", ora.get_agent_id(g), cu.get_agent_id(g), s)
+            assert_same("pos", ora.get_pos(g), cu.get_pos(g), s)
+    run_lockstep(ora, cu, steps=30, seed=32, stream="fight")
+
+
+def test_speculation_switched_off_gives_the_same_results(monkeypatch):
+    monkeypatch.setenv("MAGENT_SPECULATE", "0")
+    ora, cu = OracleEngine(40), CudaEngine(40)
+    setup_pair([ora, cu], *generate_map_positions(40))
+    st = run_lockstep(ora, cu, steps=120, seed=8, stream="fight", skip_clear_every=5)
+    assert st["deaths"] > 10, st

@@ -1,0 +1,141 @@
+"""INTEGRATION.md promises that the reference's Python binding needs no source change.  Two CPU checks (dev container,
+where /root/reference exists):
+
+  * the UNMODIFIED reference package examples/battle_model/python/magent (its own gridworld.py, c_lib.py, config) and
+    this repo's mirror python/magent drive the SAME engine library through the same action stream and must return
+    identical arrays from every call the play loop makes -- so mirror == reference binding, and with the GPU tests
+    (mirror over the CUDA library == oracle == reference engine) the chain is closed;
+  * every `_LIB.<symbol>(...)` call site of the reference's gridworld.py names a function declared in
+    include/mfmarl_magent.h with the same number of arguments.
+
+The reference package is imported in a child process with only its own directory on sys.path; the one thing done to
+it is at the loader: ctypes.CDLL is pointed at oracle/_ref/libmagent_ref.so instead of <pkg>/../../build/libmagent.so
+(c_lib.py:13-30), which the read-only reference tree cannot hold.
+"""
+import ast
+import os
+import re
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+from conftest import REPO
+from engines import REF_SO, RefEngine, have_ref
+from scenarios import fight_actions, generate_map_positions
+
+REF_PY = "/root/reference/examples/battle_model/python"
+pytestmark = pytest.mark.skipif(not (os.path.isdir(REF_PY) and have_ref()),
+                                reason="reference tree / oracle/_ref not present")
+
+CHILD = textwrap.dedent('''
+    import ctypes, sys, os
+    import numpy as np
+    target, ref_py, stream_npz, out_npz = sys.argv[1:5]
+    _CDLL = ctypes.CDLL
+    class Redirected(_CDLL):                      # c_lib.py:13-30 looks in <pkg>/../../build/
+        def __init__(self, name, *a, **k):
+            if name and os.path.basename(name) == "libmagent.so":
+                name = target
+            super().__init__(name, *a, **k)
+    ctypes.CDLL = Redirected
+    sys.path[:] = [ref_py] + [p for p in sys.path if "site-packages" in p or "lib/python" in p]
+    import magent                                  # the reference's package, unmodified
+    assert os.path.dirname(magent.__file__).startswith(ref_py), magent.__file__
+    data = np.load(stream_npz)
+    env = magent.GridWorld("battle", map_size=40)
+    h = env.get_handles()
+    env.reset()
+    env.add_agents(h[0], method="custom", pos=data["left"])
+    env.add_agents(h[1], method="custom", pos=data["right"])
+    out = {"view_space": np.array(env.get_view_space(h[0])), "feature_space": np.array(env.get_feature_space(h[0])),
+           "action_space": np.array(env.get_action_space(h[0]))}
+    for s in range(int(data["steps"])):
+        for g in range(2):
+            v, f = env.get_observation(h[g])
+            out["view_%d_%d" % (s, g)] = v.copy(); out["feat_%d_%d" % (s, g)] = f.copy()
+            out["id_%d_%d" % (s, g)] = env.get_agent_id(h[g]); out["pos_%d_%d" % (s, g)] = env.get_pos(h[g])
+            out["num_%d_%d" % (s, g)] = np.array(env.get_num(h[g]))
+        for g in range(2):
+            env.set_action(h[g], data["act_%d_%d" % (s, g)])
+        out["done_%d" % s] = np.array(env.step())
+        for g in range(2):
+            out["rew_%d_%d" % (s, g)] = env.get_reward(h[g]); out["alive_%d_%d" % (s, g)] = env.get_alive(h[g])
+        env.clear_dead()
+    np.savez(out_npz, **out)
+''')
+
+
+def test_unmodified_reference_binding_equals_the_mirror(tmp_path):
+    steps = 100
+    left, right = generate_map_positions(40)
+    mirror = RefEngine(40)                         # this repo's python/magent over the reference engine
+    mirror.reset(); mirror.add_agents(0, left); mirror.add_agents(1, right)
+    rng = np.random.RandomState(17)
+    stream, got = {"left": left, "right": right, "steps": np.array(steps)}, {}
+    got["view_space"] = np.array(mirror.env.get_view_space(mirror.h[0]))
+    got["feature_space"] = np.array(mirror.env.get_feature_space(mirror.h[0]))
+    got["action_space"] = np.array(mirror.env.get_action_space(mirror.h[0]))
+    for s in range(steps):
+        for g in range(2):
+            v, f = mirror.get_observation(g)
+            got["view_%d_%d" % (s, g)], got["feat_%d_%d" % (s, g)] = v, f
+            got["id_%d_%d" % (s, g)], got["pos_%d_%d" % (s, g)] = mirror.get_agent_id(g), mirror.get_pos(g)
+            got["num_%d_%d" % (s, g)] = np.array(mirror.get_num(g))
+        for g in range(2):
+            stream["act_%d_%d" % (s, g)] = fight_actions(rng, mirror.get_pos(g), 40)
+            mirror.set_action(g, stream["act_%d_%d" % (s, g)])
+        got["done_%d" % s] = np.array(mirror.step())
+        for g in range(2):
+            got["rew_%d_%d" % (s, g)], got["alive_%d_%d" % (s, g)] = mirror.get_reward(g), mirror.get_alive(g)
+        mirror.clear_dead()
+    assert sum(int((~got["alive_%d_%d" % (s, g)]).sum()) for s in range(steps) for g in range(2)) > 20
+    np.savez(tmp_path / "stream.npz", **stream)
+    child = tmp_path / "child.py"
+    child.write_text(CHILD)
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    env.pop("PYTHONPATH", None)
+    subprocess.run([sys.executable, str(child), REF_SO, REF_PY, str(tmp_path / "stream.npz"), str(tmp_path / "out.npz")],
+                   check=True, env=env, cwd=str(tmp_path))
+    want = np.load(tmp_path / "out.npz")
+    assert sorted(want.files) == sorted(got)
+    for key in want.files:
+        a, b = want[key], np.asarray(got[key])
+        assert a.shape == b.shape and a.dtype == b.dtype, (key, a.shape, b.shape, a.dtype, b.dtype)
+        assert a.tobytes() == b.tobytes(), key
+
+
+def header_prototypes():
+    text = open(os.path.join(REPO, "include", "mfmarl_magent.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\bint\s+(\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        args = [a for a in m.group(2).split(",") if a.strip() and a.strip() != "void"]
+        protos[m.group(1)] = len(args)
+    return protos
+
+
+def test_every_call_site_of_the_reference_binding_is_declared_with_the_same_arity():
+    protos = header_prototypes()
+    tree = ast.parse(open(os.path.join(REF_PY, "magent", "gridworld.py")).read())
+    calls = {}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and \
+                isinstance(node.func.value, ast.Name) and node.func.value.id == "_LIB":
+            calls.setdefault(node.func.attr, set()).add(len(node.args))
+    assert len(calls) >= 15, calls
+    for name, arities in sorted(calls.items()):
+        assert name in protos, "%s is called by the reference binding but not declared in mfmarl_magent.h" % name
+        for n in arities:
+            # gridworld.py:170-176 calls add_reward_rule with 6 of its 7 parameters (auto_value is left to the ABI's
+            # default register content in the reference); everything else passes every parameter
+            assert n == protos[name] or (name == "gridworld_add_reward_rule" and n == protos[name] - 1), \
+                (name, n, protos[name])
+    # ... and the shared library exports each of them
+    import ctypes
+    from engines import CUDA_SO
+    lib = ctypes.CDLL(CUDA_SO)
+    for name in calls:
+        assert hasattr(lib, name), name
