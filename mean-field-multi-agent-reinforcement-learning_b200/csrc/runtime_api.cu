@@ -209,7 +209,10 @@ struct Game {
             if (r.on < 0 || r.on >= (int)nodes.size()) throw Fatal("reward rule refers to an undefined event node");
             const Node &n = nodes[r.on];
             bool ok = n.op == 7 /* OP_ATTACK */ && n.inputs.size() == 2 && r.receivers.size() == 1 &&
-                      r.receivers[0] == n.inputs[0] && !r.terminal && !r.auto_value;
+                      r.receivers[0] == n.inputs[0] && !r.terminal;
+            // (auto_value is not looked at: the reference's binding calls add_reward_rule with 6 of its 7 arguments,
+            //  gridworld.py:719-722, so the flag is whatever the stack held, and the engine only reads it for OP_ALIGN
+            //  nodes, RewardEngine.cc:252)
             if (ok) {
                 const Symbol &a = symbols.at(n.inputs[0]), &b = symbols.at(n.inputs[1]);
                 ok = a.index == -1 && b.index == -1 && a.group != b.group && a.group >= 0 && a.group < 2 && !seen[a.group];

@@ -85,11 +85,11 @@ class GridWorld(Environment):
         buf = np.empty((3,), dtype=np.int32)
         for handle in self.group_handles:
             self._lib.env_get_info(self.game, handle, b"view_space", as_int32_c_array(buf))
-            self.view_space[handle.value] = (int(buf[0]), int(buf[1]), int(buf[2]))
+            self.view_space[handle.value] = (buf[0], buf[1], buf[2])      # numpy int32 scalars, as the reference returns them
             self._lib.env_get_info(self.game, handle, b"feature_space", as_int32_c_array(buf))
-            self.feature_space[handle.value] = (int(buf[0]),)
+            self.feature_space[handle.value] = (buf[0],)
             self._lib.env_get_info(self.game, handle, b"action_space", as_int32_c_array(buf))
-            self.action_space[handle.value] = (int(buf[0]),)
+            self.action_space[handle.value] = (buf[0],)
 
     # ------------------------------------------------------------------ episode set-up
     def reset(self):

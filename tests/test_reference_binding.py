@@ -129,10 +129,14 @@ def test_every_call_site_of_the_reference_binding_is_declared_with_the_same_arit
     for name, arities in sorted(calls.items()):
         assert name in protos, "%s is called by the reference binding but not declared in mfmarl_magent.h" % name
         for n in arities:
-            # gridworld.py:170-176 calls add_reward_rule with 6 of its 7 parameters (auto_value is left to the ABI's
-            # default register content in the reference); everything else passes every parameter
-            assert n == protos[name] or (name == "gridworld_add_reward_rule" and n == protos[name] - 1), \
-                (name, n, protos[name])
+            # two habits of the reference's call sites, both harmless under the C calling convention and both accepted by
+            # the library: the "fill" / "maze" branches of add_agents pass one argument too many (gridworld.py:265-275),
+            # and add_reward_rule is called with 6 of its 7 parameters (:719-722) -- `auto_value` then holds whatever the
+            # stack held, which is why runtime_api.cu ignores it for the attack rules, as RewardEngine.cc:252 does
+            # (the deprecated set_goal also passes one argument too many, :639)
+            ok = n == protos[name] or (name in ("gridworld_add_agents", "gridworld_set_goal") and n == protos[name] + 1) or \
+                (name == "gridworld_add_reward_rule" and n == protos[name] - 1)
+            assert ok, (name, n, protos[name])
     # ... and the shared library exports each of them
     import ctypes
     from engines import CUDA_SO
