@@ -38,6 +38,10 @@ typedef struct mfb_config {
     int obs_tile_agents;   /* agents per observation CTA, 0 = auto: clamp(capacity, 64, 256)         */
     int obs_record;        /* per-env observation record kept by k_step for k_obs: -1 = auto (on for
                               capacity >= 256), 0 = off, 1 = on; same observations either way          */
+    int random_sides;      /* with auto_reset: every env draws per episode (Philox keyed by seed, env, episode)
+                              whether the two armies swap their starting blocks AND ids -- generate_map picks
+                              the left army with random.randint(0, 1) each round (senario_battle.py:14) and
+                              the block added first gets the low ids                                       */
     /* agent type (python/magent/builtin/config/battle.py:16-29) and the attack reward rules (:41-42) */
     float hp, speed, view_radius, attack_radius, damage, step_recover, kill_supply;
     float step_reward, kill_reward, dead_penalty, attack_penalty, attack_bonus[2];
@@ -52,6 +56,12 @@ int mfb_reset(mfb_engine *eng);
 int mfb_add_walls(mfb_engine *eng, int n, const int *xs, const int *ys);             /* host arrays */
 int mfb_add_agents(mfb_engine *eng, int group, int n, const int *xs, const int *ys,  /* host arrays */
                    int *n_added);
+/* A placement of its own for every env: xs / ys are host arrays [n_envs][n].  As in the reference, a position that
+ * is occupied, a wall or out of range is skipped -- per env (GridWorld.cc:180-187) -- and ids are handed out per env
+ * in add order, so the envs may hold different numbers of agents.  n_added (may be NULL) receives [n_envs] counts.
+ * Once used, mfb_add_agents / mfb_add_walls apply to every env's own template; auto_reset re-places each env from
+ * ITS template. */
+int mfb_add_agents_per_env(mfb_engine *eng, int group, int n, const int *xs, const int *ys, int *n_added);
 int mfb_set_seed(mfb_engine *eng, unsigned long seed);
 
 /* sizes: key in {"capacity","n_envs","n_action","view_size","n_channel","feature_size","attack_base"} */
@@ -87,7 +97,8 @@ int mfb_mean_action(const int32_t *d_actions /* [rows][cap] */, const int32_t *d
 /* state read-back into HOST buffers (synchronises `stream`): key in
  *   "num" int32[E][2], "dead_ct" int32[E][2], "pos" int32[E][2][cap][2], "hp" float[E][2][cap],
  *   "id" int32[E][2][cap], "alive" uint8[E][2][cap], "last_action" int32[E][2][cap],
- *   "step_ct" int32[E], "rng" uint32[E], "agent_steps" uint64[E] (agents stepped since creation)   */
+ *   "step_ct" int32[E], "rng" uint32[E], "agent_steps" uint64[E] (agents stepped since creation),
+ *   "side" int32[E] (1 = armies swapped this episode, random_sides), "episode" int32[E]              */
 int mfb_get(mfb_engine *eng, const char *key, void *host_buf, void *stream);
 /* device pointer to the live int32[E][2] agent counts (for masking on the device) */
 int mfb_num_device_ptr(mfb_engine *eng, const int32_t **out);

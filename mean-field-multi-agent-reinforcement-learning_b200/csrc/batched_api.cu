@@ -74,7 +74,7 @@ int mfb_create(const mfb_config *c, mfb_engine **out) {
     ec.n_envs = c->n_envs; ec.width = c->map_width; ec.height = c->map_height; ec.capacity = c->capacity;
     ec.embedding_size = c->embedding_size; ec.rng_mode = c->rng_mode; ec.seed = c->seed;
     ec.env_base = c->env_base; ec.max_steps = c->max_steps; ec.device = c->device;
-    ec.step_threads = c->step_threads; ec.obs_tile_agents = c->obs_tile_agents; ec.obs_cached = c->obs_record;
+    ec.step_threads = c->step_threads; ec.obs_tile_agents = c->obs_tile_agents; ec.obs_cached = c->obs_record; ec.random_sides = c->random_sides;
     ec.type.hp = c->hp; ec.type.speed = c->speed; ec.type.view_radius = c->view_radius;
     ec.type.attack_radius = c->attack_radius; ec.type.damage = c->damage; ec.type.step_recover = c->step_recover;
     ec.type.kill_supply = c->kill_supply; ec.type.step_reward = c->step_reward; ec.type.kill_reward = c->kill_reward;
@@ -100,6 +100,11 @@ int mfb_add_agents(mfb_engine *h, int group, int n, const int *xs, const int *ys
     const int added = E(h).add_agents(group, n, xs, ys);
     if (n_added) *n_added = added;
     MFB_END("mfb_add_agents")
+}
+int mfb_add_agents_per_env(mfb_engine *h, int group, int n, const int *xs, const int *ys, int *n_added) {
+    MFB_BEGIN
+    E(h).add_agents_per_env(group, n, xs, ys, n_added);
+    MFB_END("mfb_add_agents_per_env")
 }
 int mfb_set_seed(mfb_engine *h, unsigned long seed) { MFB_BEGIN E(h).set_seed(seed); MFB_END("mfb_set_seed") }
 
@@ -180,6 +185,8 @@ int mfb_get(mfb_engine *h, const char *key, void *host_buf, void *stream) {
     else if (k == "hp") copy(S.hp, n * 4);
     else if (k == "id") copy(S.id, n * 4);
     else if (k == "step_ct") copy(S.step_ct, ne * 4);
+    else if (k == "side") copy(S.side, ne * 4);
+    else if (k == "episode") copy(S.episode, ne * 4);
     else if (k == "rng") copy(S.rng, ne * 4);
     else if (k == "agent_steps") copy(S.agent_steps, ne * 8);
     else if (k == "pos" || k == "alive" || k == "last_action") {

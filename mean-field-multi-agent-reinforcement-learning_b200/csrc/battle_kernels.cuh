@@ -121,6 +121,28 @@ __device__ __forceinline__ void build_obs_record(const BattleParams &P, const Ba
     }
 }
 
+// Episode start from the placement template of env e (k_place at commit, k_step's auto-reset).  `side` = 1 swaps the
+// armies: group g takes the other block's positions AND ids -- generate_map adds the left block first, so the ids
+// follow the side, not the group (senario_battle.py:14-37).
+__device__ __forceinline__ void place_from_template(const BattleParams &P, const BattleState &S, int e, int side) {
+    const int cap = P.cap, n_action = P.n_move + P.n_attack;
+    const size_t ebase = (size_t)e * 2 * cap;
+    const int32_t *tpos = S.init_pos + (size_t)e * P.tmpl_stride;          // [2][cap] pos, then [2][cap] id
+    const int32_t *tnum = S.init_num + (P.tmpl_stride ? 2 * e : 0);
+    for (int s = threadIdx.x; s < 2 * cap; s += blockDim.x) {
+        const int g = s >= cap, i = s - g * cap, src = (side ? 1 - g : g) * cap + i;
+        const bool live = i < tnum[side ? 1 - g : g];
+        S.pos[ebase + s] = live ? tpos[src] : 0;
+        S.hp[ebase + s] = P.hp;
+        S.id[ebase + s] = live ? tpos[2 * cap + src] : 0;
+        S.state[ebase + s] = make_state(0, OP_NULL, (uint32_t)n_action);   // GridWorld.h:145
+        S.next_rew[ebase + s] = P.step_reward;                             // Agent::init_reward
+        S.last_rew[ebase + s] = 0.0f;
+    }
+    if (threadIdx.x < 2) { S.num[e * 2 + threadIdx.x] = tnum[side ? 1 - threadIdx.x : threadIdx.x]; S.dead_ct[e * 2 + threadIdx.x] = 0; }
+    if (threadIdx.x == 0) { S.step_ct[e] = 0; S.id_counter[e] = tnum[0] + tnum[1]; S.side[e] = side; }
+}
+
 // minstd_rand0 after n steps from state s: s * 16807^n mod (2^31 - 1), square and multiply over a table of
 // 16807^(2^b) -- the reference's sequential chain (GridWorld.cc:510-515 draws one number per attack) without the chain.
 __device__ __forceinline__ uint32_t minstd_jump(uint32_t s, uint32_t n) {
@@ -571,19 +593,15 @@ __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState
     const bool horizon = (phases & PH_STEP) && P.max_steps > 0 && step_before + 1 >= P.max_steps;
     if ((phases & PH_AUTORESET) && (done || horizon)) {
         __syncthreads();
-        for (int s = tid; s < 2 * cap; s += nt) {
-            const int g = s >= cap, i = s - g * cap;
-            if (i < S.init_num[g]) {
-                S.pos[ebase + s] = S.init_pos[s];
-                S.hp[ebase + s] = P.hp;
-                S.id[ebase + s] = S.init_pos[2 * cap + s];
-                S.state[ebase + s] = make_state(0, OP_NULL, (uint32_t)n_action);
-                S.next_rew[ebase + s] = P.step_reward;
-                S.last_rew[ebase + s] = 0.0f;
-            }
+        int side = 0;
+        const int episode = S.episode[e] + 1;
+        __syncthreads();                                  // everybody has read the counter before thread 0 advances it
+        if (P.random_sides) {
+            const uint4 r = philox4x32_10(make_uint4((uint32_t)episode, 0x51DEu, 0u, 0u), make_uint2(P.seed, (uint32_t)(P.env_base + e)));
+            side = (int)(r.x & 1u);
         }
-        if (tid < 2) { S.num[e * 2 + tid] = S.init_num[tid]; S.dead_ct[e * 2 + tid] = 0; }
-        if (tid == 0) { S.step_ct[e] = 0; S.id_counter[e] = S.init_num[0] + S.init_num[1]; }
+        place_from_template(P, S, e, side);
+        if (tid == 0) S.episode[e] = episode;
     } else if (phases & PH_CLEAR) {
         for (int g = 0; g < kGroups; g++) {
             const int ng = g ? n1 : n0;
@@ -1024,21 +1042,8 @@ __global__ void k_mean_action(const int32_t *__restrict__ actions, const int32_t
 // episode (re)initialisation: every env gets the placement template
 // ----------------------------------------------------------------------------------------------
 __global__ void k_place(const __grid_constant__ BattleParams P, const BattleState S) {
-    const int e = blockIdx.x, cap = P.cap;
-    const size_t ebase = (size_t)e * 2 * cap;
-    const int n_action = P.n_move + P.n_attack;
-    for (int s = threadIdx.x; s < 2 * cap; s += blockDim.x) {
-        const int g = s >= cap, i = s - g * cap;
-        const bool live = i < S.init_num[g];
-        S.pos[ebase + s] = live ? S.init_pos[s] : 0;
-        S.hp[ebase + s] = P.hp;
-        S.id[ebase + s] = live ? S.init_pos[2 * cap + s] : 0;
-        S.state[ebase + s] = make_state(0, OP_NULL, (uint32_t)n_action);   // GridWorld.h:145
-        S.next_rew[ebase + s] = P.step_reward;                             // Agent::init_reward
-        S.last_rew[ebase + s] = 0.0f;
-    }
-    if (threadIdx.x < 2) { S.num[e * 2 + threadIdx.x] = S.init_num[threadIdx.x]; S.dead_ct[e * 2 + threadIdx.x] = 0; }
-    if (threadIdx.x == 0) { S.step_ct[e] = 0; S.id_counter[e] = S.init_num[0] + S.init_num[1]; }
+    place_from_template(P, S, blockIdx.x, 0);
+    if (threadIdx.x == 0) S.episode[blockIdx.x] = 0;
 }
 
 }  // namespace mfmarl

@@ -60,6 +60,9 @@ struct BattleParams {
     int wall_stride;        // H*W, or 0 when every env shares one wall map
     int rng_mode;
     int max_steps;          // auto-reset horizon (0 = none)
+    int tmpl_stride;        // 0: one placement template for every env; 4*cap: a template per env (add_agents_per_env)
+    int random_sides;       // auto-reset: each env draws (Philox, keyed by env and episode) whether the two armies swap
+                            // their starting blocks, as generate_map does per round (senario_battle.py:14)
     int obs_cached;         // k_obs starts an item from the per-env observation record (large groups) instead of the agent arrays
     int move_bands;         // 0, or the reference's NUM_SEP_BUFFER when W*H > 99*99 ("large map mode", GridWorld.cc:79-88):
     int band_width;         //   moves run x-band by x-band, then the band-boundary buffer (GridWorld.cc:443-463,662-672)
@@ -84,7 +87,9 @@ struct BattleState {   // device pointers
     unsigned long long *agent_steps;   // [E] running count of agents taken through a step (statistic)
     int32_t *obs_ticket;               // [2] of this launch (ring of kObsTicketRing pairs): next item, CTAs finished (rewound by the last CTA)
     // episode template for auto-reset
-    int32_t *init_pos; int32_t *init_num;   // [2][cap], [2]
+    int32_t *init_pos; int32_t *init_num;   // [T][2][2][cap] (pos, then id), [T][2]; T = 1 or E (BattleParams::tmpl_stride)
+    int32_t *side;                     // [E] 1 = the armies started this episode on swapped sides (random_sides)
+    int32_t *episode;                  // [E] episodes started since the placement (keys the side draw)
 };
 
 // Host mirror of ONE environment's agent records (single-env ABI): mapped pinned memory k_step writes at its end,

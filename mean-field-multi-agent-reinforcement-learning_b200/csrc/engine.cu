@@ -53,6 +53,38 @@ CircleRange::CircleRange(float radius, float inner_radius, int parity) {
         }
 }
 
+void Engine::split_template() {
+    if (!h_env_.empty()) return;
+    h_env_.resize((size_t)P_.E);
+    for (EnvTemplate &t : h_env_) {
+        t.occ.assign(h_occ_.begin(), h_occ_.end());
+        for (int g = 0; g < kGroups; g++) { t.pos[g] = h_tpos_[g]; t.id[g] = h_tid_[g]; }
+        t.id_counter = h_id_counter_;
+    }
+}
+
+void Engine::add_agents_per_env(int group, int n, const int *xs, const int *ys, int *n_added) {
+    if (group < 0 || group >= kGroups) throw Fatal("invalid group handle in add_agents_per_env");
+    if (stepped_) throw Fatal("add_agents_per_env after stepping is not supported (call reset first)");
+    split_template();
+    for (int e = 0; e < P_.E; e++) {   // per env: GridWorld.cc:256-269; Map::add_agent Map.cc:75-97; add_or_error :180-187
+        EnvTemplate &t = h_env_[(size_t)e];
+        int added = 0;
+        for (int i = 0; i < n; i++) {
+            const int x = xs[(size_t)e * n + i], y = ys[(size_t)e * n + i];
+            if (x < 0 || y < 0 || x + 1 >= P_.W || y + 1 >= P_.H) continue;
+            const size_t c = (size_t)y * P_.W + x;
+            if (t.occ[c] != 0) continue;
+            t.occ[c] = 2;
+            t.pos[group].push_back(x | (y << 16));
+            t.id[group].push_back(t.id_counter++);
+            added++;
+        }
+        if (n_added) n_added[e] = added;
+    }
+    placement_dirty_ = true;
+}
+
 // E == 1, device state is newer than the template: pull the full records, patch, push back.
 struct Engine::LateRecords {
     std::vector<int32_t> pos, id; std::vector<float> hp, nr, lr; std::vector<uint32_t> state;
@@ -165,7 +197,12 @@ Engine::Engine(const EngineConfig &cfg) : cfg_(cfg) {
     MF_CUDA(cudaMalloc(&S_.step_ct, E * sizeof(int32_t)));
     MF_CUDA(cudaMalloc(&S_.id_counter, E * sizeof(int32_t)));
     MF_CUDA(cudaMalloc(&S_.walls, (size_t)P_.W * P_.H));
-    MF_CUDA(cudaMalloc(&S_.init_num, 2 * sizeof(int32_t)));
+    MF_CUDA(cudaMalloc(&S_.init_num, E * 2 * sizeof(int32_t)));
+    MF_CUDA(cudaMalloc(&S_.side, E * sizeof(int32_t)));
+    MF_CUDA(cudaMalloc(&S_.episode, E * sizeof(int32_t)));
+    MF_CUDA(cudaMemset(S_.side, 0, E * sizeof(int32_t)));
+    MF_CUDA(cudaMemset(S_.episode, 0, E * sizeof(int32_t)));
+    P_.tmpl_stride = 0; P_.random_sides = cfg.random_sides != 0;
     MF_CUDA(cudaMalloc(&S_.grid_template, grid_template_bytes()));
     {   // minimap cell of a position, as a table: the kernels never divide by the runtime scale
         if ((P_.H - 1) / P_.scale_h * kView + (P_.W - 1) / P_.scale_w > 255) throw Fatal("minimap table overflow");
@@ -196,6 +233,7 @@ Engine::~Engine() {
     free_state();
     cudaFree(S_.num); cudaFree(S_.dead_ct); cudaFree(S_.rng); cudaFree(S_.step_ct);
     cudaFree(S_.id_counter); cudaFree(S_.walls); cudaFree(S_.init_num); cudaFree(S_.agent_steps); cudaFree(S_.obs_ticket); cudaFree(S_.mini_lut); cudaFree(S_.grid_template);
+    cudaFree(S_.side); cudaFree(S_.episode);
 }
 
 size_t Engine::grid_template_bytes() const {
@@ -210,7 +248,7 @@ void Engine::alloc_state(int cap) {
     MF_CUDA(cudaMalloc(&S_.pos, n * 4)); MF_CUDA(cudaMalloc(&S_.hp, n * 4));
     MF_CUDA(cudaMalloc(&S_.id, n * 4)); MF_CUDA(cudaMalloc(&S_.state, n * 4));
     MF_CUDA(cudaMalloc(&S_.next_rew, n * 4)); MF_CUDA(cudaMalloc(&S_.last_rew, n * 4));
-    MF_CUDA(cudaMalloc(&S_.init_pos, (size_t)4 * cap * 4));
+    MF_CUDA(cudaMalloc(&S_.init_pos, (size_t)P_.E * 4 * cap * 4));     // room for a template per env
     S_.obs_record = nullptr;
     if (P_.obs_cached) {
         const size_t bytes = (size_t)P_.E * obs_record_layout(P_.W, P_.H, cap).total;
@@ -249,6 +287,7 @@ void Engine::reset() {   // GridWorld::reset (GridWorld.cc:76-124) + Map::reset 
     h_occ_.assign(h_walls_.begin(), h_walls_.end());
     for (int g = 0; g < kGroups; g++) { h_tpos_[g].clear(); h_tid_[g].clear(); }
     h_id_counter_ = 0;
+    h_env_.clear();
     placement_dirty_ = true;
     stepped_ = false;
     std::fill(h_num_.begin(), h_num_.end(), 0);
@@ -262,7 +301,11 @@ int Engine::add_walls(int n, const int *xs, const int *ys) {   // GridWorld.cc:2
         if (x < 0 || y < 0 || x >= P_.W || y >= P_.H) continue;
         const size_t c = (size_t)y * P_.W + x;
         if (h_occ_[c] == 2) continue;   // an agent stands there: ignored
+        bool taken = false;
+        for (const EnvTemplate &t : h_env_) taken = taken || t.occ[c] == 2;
+        if (taken) continue;            // (per-env placements: an agent of some env stands there)
         h_walls_[c] = 1; h_occ_[c] = 1; added++;
+        for (EnvTemplate &t : h_env_) t.occ[c] = 1;
     }
     placement_dirty_ = true;
     return added;
@@ -273,6 +316,13 @@ int Engine::add_agents(int group, int n, const int *xs, const int *ys) {
     if (stepped_) {
         if (P_.E != 1) throw Fatal("add_agents after stepping is only supported for a single env");
         late_add_sync_down();
+    }
+    if (!h_env_.empty()) {          // per-env templates: the same request goes to every env
+        if (stepped_) throw Fatal("add_agents after stepping is not supported with per-env placements");
+        std::vector<int> rx((size_t)P_.E * n), ry((size_t)P_.E * n), cnt((size_t)P_.E);
+        for (int e = 0; e < P_.E; e++) { std::copy(xs, xs + n, rx.begin() + (size_t)e * n); std::copy(ys, ys + n, ry.begin() + (size_t)e * n); }
+        add_agents_per_env(group, n, rx.data(), ry.data(), cnt.data());
+        return cnt[0];
     }
     int added = 0;
     for (int i = 0; i < n; i++) {   // GridWorld.cc:256-269; Map::add_agent Map.cc:75-97; add_or_error :180-187
@@ -401,21 +451,26 @@ void Engine::grow(int need_cap) {
 
 void Engine::commit(cudaStream_t st) {
     if (!placement_dirty_) return;
-    const int need = (int)std::max(h_tpos_[0].size(), h_tpos_[1].size());
-    grow(need);
+    const bool per_env = !h_env_.empty();
+    size_t need = std::max(h_tpos_[0].size(), h_tpos_[1].size());
+    for (const EnvTemplate &t : h_env_) need = std::max(need, std::max(t.pos[0].size(), t.pos[1].size()));
+    grow((int)need);
     const int cap = P_.cap;
-    std::vector<int32_t> tmpl((size_t)4 * cap, 0);
-    int32_t num[2];
-    for (int g = 0; g < kGroups; g++) {
-        num[g] = (int32_t)h_tpos_[g].size();
-        for (int i = 0; i < num[g]; i++) {
-            tmpl[(size_t)g * cap + i] = h_tpos_[g][i];
-            tmpl[(size_t)2 * cap + (size_t)g * cap + i] = h_tid_[g][i];
+    const size_t T = per_env ? (size_t)P_.E : 1;
+    std::vector<int32_t> tmpl(T * 4 * cap, 0), num(T * 2, 0);
+    for (size_t e = 0; e < T; e++)
+        for (int g = 0; g < kGroups; g++) {
+            const std::vector<int> &pos = per_env ? h_env_[e].pos[g] : h_tpos_[g], &id = per_env ? h_env_[e].id[g] : h_tid_[g];
+            num[e * 2 + g] = (int32_t)pos.size();
+            for (size_t i = 0; i < pos.size(); i++) {
+                tmpl[e * 4 * cap + (size_t)g * cap + i] = pos[i];
+                tmpl[e * 4 * cap + (size_t)2 * cap + (size_t)g * cap + i] = id[i];
+            }
         }
-    }
+    P_.tmpl_stride = per_env ? 4 * cap : 0;
     // pageable sources: these copies are synchronous with respect to the host
     MF_CUDA(cudaMemcpyAsync(S_.init_pos, tmpl.data(), tmpl.size() * 4, cudaMemcpyHostToDevice, st));
-    MF_CUDA(cudaMemcpyAsync(S_.init_num, num, 8, cudaMemcpyHostToDevice, st));
+    MF_CUDA(cudaMemcpyAsync(S_.init_num, num.data(), num.size() * 4, cudaMemcpyHostToDevice, st));
     MF_CUDA(cudaMemcpyAsync(S_.walls, h_walls_.data(), h_walls_.size(), cudaMemcpyHostToDevice, st));
     // the observation kernel's shared-memory grid starts from this image: walls only, 6-cell empty margin
     std::vector<uint16_t> gtmpl(grid_template_bytes() / 2, 0);
@@ -431,7 +486,7 @@ void Engine::commit(cudaStream_t st) {
     // a placement is a per-episode event: wait for it, so that whatever stream the next launch uses (the legacy
     // stream of mfb_query, a non-blocking side stream of the caller) it is ordered after the new state
     MF_CUDA(cudaStreamSynchronize(st));
-    for (int e = 0; e < P_.E; e++) { h_num_[e * 2] = num[0]; h_num_[e * 2 + 1] = num[1]; }
+    for (int e = 0; e < P_.E; e++) { const size_t t = per_env ? (size_t)e : 0; h_num_[e * 2] = num[t * 2]; h_num_[e * 2 + 1] = num[t * 2 + 1]; }
     placement_dirty_ = false;
     stepped_ = false;
 }

@@ -45,6 +45,7 @@ struct EngineConfig {
     int n_envs = 1, width = 40, height = 40, capacity = 64, embedding_size = 10;
     int rng_mode = RNG_MINSTD, max_steps = 0, env_base = 0, device = -1 /* current */;
     int step_threads = 0 /* auto */, obs_tile_agents = 0 /* auto: clamp(cap, 64, 256); 32 with the observation record */;
+    int random_sides = 0 /* auto-reset draws per env and episode whether the armies swap their starting blocks */;
     int obs_cached = -1 /* observation record: -1 auto (capacity >= 256, or MFMARL_OBS_CACHED), 0 off, 1 on */;
     unsigned seed = 0;
     AgentTypeParams type;
@@ -61,7 +62,10 @@ public:
     // ---- episode set-up (host side; takes effect at the next kernel) ----
     void reset();                                              // GridWorld::reset
     int add_walls(int n, const int *xs, const int *ys);        // add_agents(group = -1, "custom")
-    int add_agents(int group, int n, const int *xs, const int *ys);   // add_agents(group, "custom")
+    int add_agents(int group, int n, const int *xs, const int *ys);   // add_agents(group, "custom"), the same in every env
+    // a placement of its own for every env: xs / ys are [E][n]; occupied or out-of-range cells are skipped PER ENV
+    // (GridWorld.cc:180-187), so the envs may end up with different counts; n_added (may be null) receives [E] counts
+    void add_agents_per_env(int group, int n, const int *xs, const int *ys, int *n_added);
     void set_seed(unsigned long seed);                         // set_config("seed")
 
     // ---- kernels ----
@@ -129,6 +133,10 @@ private:
     std::vector<int> h_occ_;                      // [H*W] 0 free, 1 taken (walls + placed agents)
     std::vector<int> h_tpos_[kGroups], h_tid_[kGroups];
     int h_id_counter_ = 0;
+    // per-env placement (after the first add_agents_per_env): the template above replicated, then diverging
+    struct EnvTemplate { std::vector<unsigned char> occ; std::vector<int> pos[kGroups], id[kGroups]; int id_counter = 0; };
+    std::vector<EnvTemplate> h_env_;              // empty = shared template
+    void split_template();                        // shared -> per-env
     bool placement_dirty_ = true;
     bool stepped_ = false;                        // a step has run since the last placement upload
     std::vector<int> h_num_;                      // [E][2] mirror, refreshed by download_num

@@ -25,7 +25,7 @@ def _stream():
 
 class BatchedGridWorld:
     def __init__(self, n_envs, map_size=40, capacity=64, device=None, rng="minstd", seed=0, env_base=0,
-                 max_steps=0, auto_reset=False, step_threads=0, obs_tile_agents=0, obs_record=None, **type_overrides):
+                 max_steps=0, auto_reset=False, step_threads=0, obs_tile_agents=0, obs_record=None, random_sides=False, **type_overrides):
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedGridWorld needs a CUDA device: there is no CPU fallback")
         self.lib = load_library()
@@ -38,6 +38,7 @@ class BatchedGridWorld:
         cfg.step_threads, cfg.obs_tile_agents = step_threads, obs_tile_agents
         if obs_record is not None:          # None = the engine decides (on for capacity >= 256)
             cfg.obs_record = int(obs_record)
+        cfg.random_sides = int(random_sides)
         for key, value in type_overrides.items():
             if not hasattr(cfg, key):
                 raise TypeError("unknown agent-type attribute %r" % key)
@@ -78,6 +79,18 @@ class BatchedGridWorld:
                                       ctypes.byref(added)))
         self._sizes = None
         return added.value
+
+    def add_agents_per_env(self, group, pos):
+        """pos int[E, n, 2 or 3]: every environment gets its OWN placement; cells that are occupied, walls or out of
+        range are skipped per environment (GridWorld.cc:180-187).  Returns the number added in each env, int32[E]."""
+        pos = np.asarray(pos, dtype=np.int32)
+        assert pos.ndim == 3 and pos.shape[0] == self.n_envs, pos.shape
+        xs, ys = np.ascontiguousarray(pos[:, :, 0]), np.ascontiguousarray(pos[:, :, 1])
+        added = np.zeros((self.n_envs,), np.int32)
+        check(self.lib.mfb_add_agents_per_env(self._h, group, pos.shape[1], xs.ctypes.data, ys.ctypes.data,
+                                              added.ctypes.data))
+        self._sizes = None
+        return added
 
     # ------------------------------------------------------------ sizes / buffers
     def query(self, key):
@@ -194,7 +207,8 @@ class BatchedGridWorld:
             "pos": ("i4", lambda E, c: (E, 2, c, 2)), "hp": ("f4", lambda E, c: (E, 2, c)),
             "id": ("i4", lambda E, c: (E, 2, c)), "alive": ("u1", lambda E, c: (E, 2, c)),
             "last_action": ("i4", lambda E, c: (E, 2, c)), "step_ct": ("i4", lambda E, c: (E,)),
-            "rng": ("u4", lambda E, c: (E,)), "agent_steps": ("u8", lambda E, c: (E,))}
+            "rng": ("u4", lambda E, c: (E,)), "agent_steps": ("u8", lambda E, c: (E,)),
+            "side": ("i4", lambda E, c: (E,)), "episode": ("i4", lambda E, c: (E,))}
 
     def get(self, key):
         dtype, shape = self._GET[key]

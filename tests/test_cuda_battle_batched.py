@@ -396,3 +396,102 @@ def test_sampled_envs_of_a_large_engine_match_the_oracle():
         if any(min(o.get_num(0), o.get_num(1)) == 0 for o in oracles.values()):
             break
     assert deaths > 30
+
+
+def per_env_placements(E, map_size, rng):
+    """what generate_map does per round (senario_battle.py:8-37): which army takes the left block is random per env
+    (the block added FIRST gets the low ids); plus per-env noise -- a few duplicated, walled and out-of-range cells
+    that the engine must skip (GridWorld.cc:180-187), so the envs hold different numbers of agents"""
+    left, right = generate_map_positions(map_size)
+    pos = [[], []]
+    for e in range(E):
+        swap = int(rng.randint(2))
+        blocks = [left, right] if not swap else [right, left]           # blocks[g] = where group g starts
+        for g in range(2):
+            p = blocks[g][:, :2].copy()
+            k = rng.randint(0, 6)                                        # overwrite a few entries with bad cells
+            for j in rng.choice(len(p), size=k, replace=False):
+                p[j] = [(0, 7), (map_size - 1, 3), tuple(p[(j + 1) % len(p)]), (-2, 5)][rng.randint(4)]
+            pos[g].append(p)
+    return np.stack(pos[0]), np.stack(pos[1])
+
+
+def test_per_env_placements_match_independent_oracles():
+    """mfb_add_agents_per_env: every env its own armies.  Each env is compared with its own oracle
+    that was given the same positions in the same order."""
+    from mfmarl_b200 import BatchedGridWorld
+    E = 6
+    rng = np.random.RandomState(44)
+    p0, p1 = per_env_placements(E, 40, rng)
+    env = BatchedGridWorld(E, map_size=40, capacity=64)
+    env.reset()
+    oracles = []
+    added0 = env.add_agents_per_env(0, p0)
+    added1 = env.add_agents_per_env(1, p1)
+    for e in range(E):
+        o = OracleEngine(40)
+        o.reset()
+        assert o.add_agents(0, np.c_[p0[e], np.zeros(len(p0[e]), np.int32)]) == added0[e]
+        assert o.add_agents(1, np.c_[p1[e], np.zeros(len(p1[e]), np.int32)]) == added1[e]
+        oracles.append(o)
+    num = env.get_num()
+    assert len({tuple(n) for n in num}) > 1, "the placements were meant to leave different counts: %s" % num
+    for e, o in enumerate(oracles):
+        assert [o.get_num(0), o.get_num(1)] == list(num[e])
+        for g in range(2):
+            assert_same("id", o.get_agent_id(g), env.get("id")[e, g, :num[e, g]], 0)
+    lockstep_batched(env, oracles, steps=40, seed=9, stream="fight", min_deaths=10)
+
+
+def test_shared_and_per_env_adds_mix_and_auto_reset_uses_each_envs_template():
+    from mfmarl_b200 import BatchedGridWorld
+    E = 4
+    left, right = generate_map_positions(40)
+    env = BatchedGridWorld(E, map_size=40, capacity=64, max_steps=3, auto_reset=True)
+    env.reset()
+    env.add_agents(0, left)                                   # shared ...
+    extra = np.array([[[20, 3 + e], [20, 3 + e], [21, 36 - e]] for e in range(E)], np.int32)
+    assert list(env.add_agents_per_env(1, extra)) == [2] * E  # ... then per env (one duplicate skipped)
+    env.add_agents(1, right[:10])                             # ... and shared again: lands in every env's own list
+    pos0, id0, num0 = env.get("pos").copy(), env.get("id").copy(), env.get_num().copy()
+    assert (num0 == [64, 12]).all()
+    for e in range(E):
+        assert pos0[e, 1, 0].tolist() == [20, 3 + e] and pos0[e, 1, 1].tolist() == [21, 36 - e]
+        assert id0[e, 1, :12].tolist() == list(range(64, 76))
+    rng = np.random.RandomState(1)
+    for s in range(3):
+        env.step(torch.from_numpy(rng.randint(0, 13, size=(E, 2, 64)).astype(np.int32)).cuda())
+    assert (env.get("step_ct") == 0).all() and (env.get("episode") == 1).all()
+    assert np.array_equal(env.get("pos"), pos0) and np.array_equal(env.get("id"), id0) and np.array_equal(env.get_num(), num0)
+
+
+def test_random_sides_at_auto_reset():
+    """random_sides: at every auto-reset an env draws whether the armies swap blocks -- positions AND ids, since
+    generate_map adds the left army first (senario_battle.py:14-37).  Keyed by (seed, global env id, episode): the
+    draws do not depend on how the envs are sharded over engines."""
+    from mfmarl_b200 import BatchedGridWorld
+    E = 64
+    left, right = generate_map_positions(40)
+
+    def run(n, base):
+        env = BatchedGridWorld(n, map_size=40, capacity=64, max_steps=2, auto_reset=True, random_sides=True,
+                               rng="philox", seed=11, env_base=base)
+        env.reset(); env.add_agents(0, left); env.add_agents(1, right)
+        sides = []
+        acts = torch.zeros((n, 2, 64), dtype=torch.int32, device="cuda") + 6        # everybody stays put
+        for ep in range(6):
+            env.step(acts); env.step(acts)
+            side, pos, ids = env.get("side"), env.get("pos"), env.get("id")
+            assert (env.get("episode") == ep + 1).all()
+            for e in range(n):
+                a, b = (right, left) if side[e] else (left, right)
+                assert np.array_equal(pos[e, 0, :64], a[:, :2]) and np.array_equal(pos[e, 1, :64], b[:, :2])
+                lo, hi = np.arange(64), np.arange(64, 128)
+                assert np.array_equal(ids[e, 0, :64], hi if side[e] else lo)
+                assert np.array_equal(ids[e, 1, :64], lo if side[e] else hi)
+            sides.append(side.copy())
+        return np.stack(sides)
+
+    full = run(E, 0)
+    assert 0.3 < full.mean() < 0.7 and len({tuple(r) for r in full}) > 1
+    assert np.array_equal(run(16, 32), full[:, 32:48])
