@@ -274,12 +274,14 @@ def repeat_count(ctx, first_region_ms, min_seconds, cap=400):
 
 
 def pick_median(ctx, region_ms, region_work):
-    """Per repeat: time = max over ranks, work = sum over ranks.  The repeat with the median time is the one reported."""
+    """Per repeat: time = max over ranks, work = sum over ranks, throughput = work / time.  The repeat with the median
+    THROUGHPUT is the one reported (the work per region varies a little with the phase of the episodes)."""
     t = ctx.reduce(region_ms, "max")
     w = ctx.reduce(region_work, "sum")
-    order = sorted(range(len(t)), key=lambda i: t[i])
+    order = sorted(range(len(t)), key=lambda i: w[i] / t[i])
     m = order[len(order) // 2]
-    return t[m], w[m], {"repeats": len(t), "min": t[order[0]], "median": t[m], "max": t[order[-1]]}
+    return t[m], w[m], {"repeats": len(t), "min": min(t), "median": sorted(t)[len(t) // 2], "max": max(t),
+                        "reported": t[m]}
 
 
 def measure_battle(ctx, args, workload, K, W, min_seconds, envs_per_gpu=0, pipeline=None, obs_tile=None, extras=True):
