@@ -54,6 +54,14 @@ class ACNet(nn.Module):
         return policy, value.reshape(-1)
 
 
+# tf.layers.dense default names in creation order (ac.py:50-103 ActorCritic, :220-262 MFAC) -> ACNet attributes,
+# for base.load_tf_variables
+TF_AC_LAYERS = [("dense", "view_dense"), ("dense_1", "emb_dense"), ("dense_2", "trunk"), ("dense_3", "policy_head"),
+                ("dense_4", "value_head")]
+TF_MFAC_LAYERS = [("dense", "view_dense"), ("dense_1", "emb_dense"), ("dense_2", "trunk"), ("dense_3", "policy_head"),
+                  ("dense_4", "prob_emb"), ("dense_5", "prob_dense"), ("dense_6", "value_dense"), ("dense_7", "value_head")]
+
+
 def discounted_returns(rewards, bootstrap, gamma):
     """ac.py:144-148: keep = V(last state); for i reversed: keep = keep * gamma + r[i]; r[i] = keep."""
     out = np.array(rewards, dtype=np.float64 if np.asarray(rewards).dtype == np.float64 else np.float32)

@@ -95,6 +95,35 @@ class QNet(nn.Module):
         return self.q_value(F.relu(self.dense_out(x)))
 
 
+def load_tf_variables(net, layers, variables):
+    """Import TensorFlow-layout weights into a torch module: the correspondence that makes these networks the
+    reference's graphs, stated in code (and what a user with a TF checkpoint of the reference needs).
+
+    layers     [(tf_layer_name, torch_attribute)], e.g. TF_QNET_LAYERS
+    variables  {"<tf_layer_name>/kernel": array, "<tf_layer_name>/bias": array} as tf.train.load_checkpoint returns
+               them: conv kernels HWIO over an NHWC input (tf.layers.conv2d, base.py:125-136), dense kernels [in, out]
+               applied as x @ kernel + bias (tf.layers.dense).  A flattened conv output is in (h, w, c) order in both
+               graphs (QNet.forward flattens NHWC), so dense kernels need nothing but the transpose.
+    Layers the module does not have (the mean-action branch without use_mf) are skipped; missing arrays raise."""
+    with torch.no_grad():
+        for tf_name, attr in layers:
+            layer = getattr(net, attr, None)
+            if layer is None:
+                continue
+            kernel = torch.as_tensor(np.asarray(variables[tf_name + "/kernel"]), dtype=torch.float32)
+            bias = torch.as_tensor(np.asarray(variables[tf_name + "/bias"]), dtype=torch.float32)
+            kernel = kernel.permute(3, 2, 0, 1) if kernel.dim() == 4 else kernel.t()      # HWIO -> OIHW; [in, out] -> [out, in]
+            assert tuple(kernel.shape) == tuple(layer.weight.shape), (tf_name, tuple(kernel.shape), tuple(layer.weight.shape))
+            layer.weight.copy_(kernel.contiguous())
+            layer.bias.copy_(bias)
+
+
+# variable scopes of ValueNet._construct_net (base.py:123-183) -> QNet attributes
+TF_QNET_LAYERS = [("Conv1", "conv1"), ("Conv2", "conv2"), ("Dense-Obs", "dense_obs"), ("Dense-Emb", "dense_emb"),
+                  ("Prob-Emb", "prob_emb"), ("Dense-Act-Prob", "dense_act_prob"), ("Dense2", "dense2"),
+                  ("Dense-Out", "dense_out"), ("Q-Value", "q_value")]
+
+
 class ValueNet:
     def __init__(self, env, handle, name, update_every=5, use_mf=False, learning_rate=1e-4, tau=0.005, gamma=0.95,
                  device=None):
