@@ -902,11 +902,14 @@ __global__ void __launch_bounds__(L * (ROWS / RPT), 1) k_ising_persist_f32(const
                 keep_q[j] = a_cur[j] ? pr[j].y : pr[j].x;
                 keep_addr[j] += (uint32_t)a_cur[j] * 4u;
             }
+            // state k+1's halo is asked for HERE: the neighbour sent it before its own interior draws, so it has been in
+            // L2 for a while, and the load's round trip runs under the Philox rounds below instead of in front of the
+            // next sweep (asked for after them it cost ~230 cycles per sweep)
+            if (boundary) hv = ld_halo(mb_in + (par ^ 1u) * MB_PARITY);
             if (k + 1 < A.K) {
                 if (A.u == nullptr) draw_uniforms(A.step0 + (uint32_t)(k + 1));
                 tparam = temperature_param(A.temperatures[k + 1]);
             }
-            if (boundary) hv = ld_halo(mb_in + (par ^ 1u) * MB_PARITY);   // state k+1's halo: in flight until the next iteration looks
         }
         __syncthreads();
         if (tid == 0) {

@@ -41,10 +41,23 @@ def declare_abi(lib):
         "gridworld_define_event_node": [vp, ci, ci, vp, ci],
         "gridworld_add_reward_rule": [vp, ci, vp, vp, ci, ctypes.c_bool, ctypes.c_bool],
     }
+    last_error = getattr(lib, "mfmarl_last_error", None)      # (the reference engine has no such symbol and never fails softly)
+    if last_error is not None:
+        last_error.restype = cp
+
+    def raise_on_error(result, func, args):
+        # The reference aborts the process on a fatal error; this engine does the same unless MAGENT_ERRORS=return
+        # asks for return codes -- then a failure must not pass silently (the reference's binding ignores the codes).
+        if result != 0:
+            text = last_error().decode("utf-8", "replace") if last_error is not None else "error %d" % result
+            raise RuntimeError("%s failed: %s" % (func.__name__, text))
+        return result
+
     for name, argtypes in sig.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = ci
+        fn.errcheck = raise_on_error
     return lib
 
 

@@ -156,7 +156,9 @@ def play_batched(env, n_round, max_steps, models, eps=1.0, train=False, print_ev
         sum_total += r * act_f
         sum_mean += r / num.clamp(min=1).to(torch.float64) * act_f
         steps_run += active.to(torch.int64)
-        final_nums = torch.where(active[:, None], live_num, final_nums)    # after clear_dead, like the last get_num
+        # the reference reads get_num BEFORE the step's clear_dead (senario_battle.py:146): the agents that died in an
+        # environment's last step still count, which is what Runner's `kill` statistic is built on
+        final_nums = torch.where(active[:, None], num, final_nums)
         former = torch.where(active[:, None, None], mean, former)
         active = active & (done == 0)
         step_ct += 1

@@ -39,3 +39,16 @@ def test_missing_library_is_a_hard_error(tmp_path):
     assert r.returncode != 0 and "not found" in r.stderr and "no CPU fallback" in r.stderr
     r = run("import torch, mfmarl_b200; mfmarl_b200.BatchedGridWorld(2)")
     assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.skipif(not os.path.exists(SO), reason="library not built")
+def test_return_codes_are_not_dropped_by_the_binding():
+    """MAGENT_ERRORS=return turns the abort into a return code; the binding must then raise with the engine's message
+    (the reference's binding ignores every code)."""
+    r = run("import magent\n"
+            "try:\n"
+            "    magent.GridWorld('battle', map_size=40)\n"
+            "except RuntimeError as ex:\n"
+            "    print('raised:', ex)\n", MAGENT_ERRORS="return")
+    assert r.returncode == 0, r.stderr[-500:]
+    assert "raised:" in r.stdout and "env_new_game failed" in r.stdout and "no CUDA device" in r.stdout
