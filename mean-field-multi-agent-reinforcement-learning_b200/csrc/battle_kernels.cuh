@@ -703,10 +703,9 @@ __host__ __device__ inline ObsSmem obs_smem_layout(int W, int H, int cap, int ca
     L.record = L.bar = L.cnt = L.tmpl = 0;
     if (cached) {                                                     // the env's observation record, as one bulk copy lands it
         const ObsRecord R = obs_record_layout(W, H, cap);
-        L.record = o; L.code = o + R.grid; L.hp10 = o + R.hp10; L.mini = o + R.mini; o += R.total;
+        L.record = o; L.code = o + R.grid; L.hp10 = o + R.hp10; L.mini = o + R.mini; o += R.total;   // (16-byte pieces)
         L.fxy = o;    o += 4 * (W + H);
         o = (o + 15) & ~15;
-        L.bar = o;    o += 16;                                        // mbarrier the bulk copy completes on
     } else {
         L.hp10 = o;   o += 4 * 2 * cap;                                   // hp / max_hp per agent slot
         L.mini = o;   o += 4 * 2 * kViewCells;
@@ -736,25 +735,6 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-__device__ __forceinline__ void obs_mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void obs_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void obs_mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void bulk_load_g2s(void *sdst, const void *gsrc, uint32_t bytes, uint32_t bar) {
-    const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(sdst);
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(saddr), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
-}
-
 // cell kinds in the CTA-local grid.  Rebuilt per item (CACHED = false) they are relative to the observing group; in the
 // observation record (CACHED = true) they name the group: 2 + group
 enum : uint32_t { KIND_EMPTY = 0, KIND_WALL = 1, KIND_OWN = 2, KIND_OTHER = 3 };
@@ -773,13 +753,7 @@ k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO i
     float *s_fxy = (float *)(smem_raw + L.fxy);
     const bool tmpl_smem = !CACHED && obs_template_in_smem(P.W, P.H);
     const uint4 *s_tmpl = tmpl_smem ? (const uint4 *)(smem_raw + L.tmpl) : (const uint4 *)S.grid_template;
-    const uint32_t rec_bar = (uint32_t)__cvta_generic_to_shared(smem_raw + L.bar);
     const uint32_t rec_bytes = (uint32_t)obs_record_layout(P.W, P.H, P.cap).total;
-    uint32_t rec_phase = 0;
-    if (CACHED && threadIdx.x == 0) {
-        obs_mbar_init(rec_bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // visible to the async proxy
-    }
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = P.W, H = P.H, cap = P.cap;
@@ -837,11 +811,17 @@ k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO i
         const int a_begin = tile * io.tile_agents;
         int n0, n1, ng, a_end;
         if constexpr (CACHED) {
-            // The env's observation record (occupancy grid, hp / 10 per slot, both minimaps -- written by k_step) lands in
-            // shared memory with ONE bulk copy; every warp has finished with the previous item's record (barriers above).
-            if (tid == 0) {
-                obs_mbar_expect_tx(rec_bar, rec_bytes);
-                bulk_load_g2s(smem_raw + L.record, S.obs_record + (size_t)e * rec_bytes, rec_bytes, rec_bar);
+            // The env's observation record (occupancy grid, hp / 10 per slot, both minimaps -- written by k_step) is copied
+            // into shared memory as it is; every warp has finished with the previous item's record (barriers above).
+            // cp.async (LDGSTS), 16 bytes per thread and instruction, NOT a bulk copy: a bulk load is queued in the SM's
+            // TMA unit behind this CTA's (and its neighbour's) 38 KB bulk stores still draining -- ncu showed 24 % of
+            // the samples waiting on that load's mbarrier with 32-agent tiles; the LSU path only pays the L2 latency.
+            {
+                const unsigned char *src = S.obs_record + (size_t)e * rec_bytes;
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_raw + L.record);
+                for (uint32_t c = (uint32_t)tid * 16u; c < rec_bytes; c += kObsThreads * 16u)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + c), "l"(src + c) : "memory");
+                asm volatile("cp.async.commit_group;" ::: "memory");
             }
             n0 = S.num[e * 2]; n1 = S.num[e * 2 + 1];
             int4 my_rec = make_int4(0, 0, 0, 0);                                   // agent a_begin + tid of the tile
@@ -852,9 +832,8 @@ k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO i
             ng = g ? n1 : n0;
             a_end = min(ng, a_begin + io.tile_agents);
             if (tid < a_end - a_begin) s_rec[tid] = my_rec;
-            obs_mbar_wait(rec_bar, rec_phase);            // (also before skipping an empty tile: one copy per phase)
-            rec_phase ^= 1u;
-            if (a_begin >= ng) {                          // nothing to do (uniform across the CTA)
+            asm volatile("cp.async.wait_all;" ::: "memory");   // this thread's pieces have landed; the barrier at the top of
+            if (a_begin >= ng) {                               // the first chunk (or of the next item) publishes everybody's
                 if (tid == 0) s_next = next_ticket;
                 continue;
             }

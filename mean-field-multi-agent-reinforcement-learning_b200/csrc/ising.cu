@@ -29,6 +29,9 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <type_traits>
 
 #include "../../include/mfmarl_batched.h"
 #include "rng.cuh"
@@ -814,9 +817,18 @@ __global__ void __launch_bounds__(L * (ROWS / RPT), 1) k_ising_persist_f32(const
 #pragma unroll
         for (int j = 0; j < RPT; j++) { keep_q[j] = 0.0f; keep_addr[j] = q_site0; }
 
+        // Order inside a sweep.  Only the strip's BOUNDARY row needs the neighbour (its halo word), and only the
+        // boundary row is needed by the neighbour.  It is therefore handled LAST: the interior rows of sweep k are
+        // finished and drawn first, while the halo word of state k -- sent by the neighbour at the end of ITS interior
+        // work of the previous sweep -- travels through L2; it is asked for half-way through the interior work and looked
+        // at only when the boundary row's turn comes, and the boundary row's new word leaves right after.  Between a
+        // send and the moment the neighbour needs the word lies most of a sweep, which is what absorbs the L2 round
+        // trip and the jitter between the 16 strips of a lattice (ncu, boundary row first: 11 % of the samples sat in
+        // the halo poll and 14 % at the barrier behind it).
+        auto is_boundary_row = [&](int j) { return (j == 0 && first_band) || (j == RPT - 1 && last_band); };
         for (int k = 0; k <= A.K; k++) {
             const uint32_t par = (state_no + (uint32_t)k) & 1u, seq = state_no + (uint32_t)k + 1u;
-            const uint32_t cur = par * BUF;
+            const uint32_t cur = par * BUF, nxt = cur ^ BUF;
             __syncthreads();                              // own words of the lattice after sweep k-1 are in buffer `cur`
             if (tid == 0 && k >= 2) {                     // statistics of sweep k-2: all warps added before this barrier
                 const int pk = s_stat[k & 1];
@@ -824,18 +836,32 @@ __global__ void __launch_bounds__(L * (ROWS / RPT), 1) k_ising_persist_f32(const
                 atomicAdd(&A.n_up[(size_t)(k - 2) * A.B + b], pk & 0xFFFF);
                 if (A.reward_sum) atomicAdd(&A.reward_sum[(size_t)(k - 2) * A.B + b], (float)((pk >> 16) - 2 * RPT * NT));
             }
-            // ---- halo word of state k.  It was asked for at the end of the previous iteration, and the neighbour sent it
-            //      early in ITS previous iteration (boundary rows are drawn first), so it is normally already here ----
-            if (boundary)
-                while ((uint32_t)(hv >> 32) != seq) hv = ld_halo(mb_in + par * MB_PARITY);
-            const uint32_t top_word = first_band ? (uint32_t)hv : lds_u32(own_w + cur - WPR * 4u);
-            const uint32_t bot_word = last_band ? (uint32_t)hv : lds_u32(own_w + cur + (uint32_t)RPT * WPR * 4u);
-            // ---- up-neighbour counts of the current lattice ----
+            const bool draw = k < A.K;
+            if (draw && A.u != nullptr) {
+#pragma unroll
+                for (int j = 0; j < RPT; j++)
+                    uu[j] = A.u[((size_t)k * A.B + b) * N + (size_t)(row0 + rb + j) * L + x] * 4294967296.0f;
+            }
+            uint32_t upd = 0xFFFFFFFFu;                                            // bit j: site j updates Q (sweep k-1)
+            if (MASK && k > 0) {
+                const uint8_t *m = A.mask + ((size_t)(k - 1) * A.B + b) * N + (size_t)(row0 + rb) * L + x;
+                upd = 0;
+#pragma unroll
+                for (int j = 0; j < RPT; j++) upd |= (m[j * L] ? 1u : 0u) << j;
+            }
+            // the state-k spins the boundary row's count will need, before the interior rows are redrawn
+            const int a_next_to_boundary = first_band ? a_cur[1] : a_cur[RPT - 2];
+            int packed = 0;
             int ups[RPT];
+            float2 pr[RPT];
+            // ---- interior rows: neighbour counts of state k (own registers + own shared-memory words) ----
             {
+                const uint32_t top_word = first_band ? 0u : lds_u32(own_w + cur - WPR * 4u);
+                const uint32_t bot_word = last_band ? 0u : lds_u32(own_w + cur + (uint32_t)RPT * WPR * 4u);
                 const int v_top = (int)((top_word >> lane) & 1u), v_bot = (int)((bot_word >> lane) & 1u);
 #pragma unroll
                 for (int j = 0; j < RPT; j++) {
+                    if (is_boundary_row(j)) continue;
                     const int up = j == 0 ? v_top : a_cur[j - 1];
                     const int dn = j == RPT - 1 ? v_bot : a_cur[j + 1];
                     const uint32_t Wl = lds_u32(own_l + cur + (uint32_t)j * WPR * 4u), Wr = lds_u32(own_r + cur + (uint32_t)j * WPR * 4u);
@@ -843,69 +869,84 @@ __global__ void __launch_bounds__(L * (ROWS / RPT), 1) k_ising_persist_f32(const
                     ups[j] = up + dn + (int)((lf >> lane) & 1u) + (int)((rt >> lane) & 1u);
                 }
             }
-            // ---- finish sweep k-1: reward on the new lattice, Q update in shared memory, statistics ----
+            // ---- interior rows: finish sweep k-1 (reward on state k, Q update in shared memory, statistics) ----
             if (k > 0) {
-                int packed = 0;
-                uint32_t upd = 0xFFFFFFFFu;
-                if (MASK) {
-                    const uint8_t *m = A.mask + ((size_t)(k - 1) * A.B + b) * N + (size_t)(row0 + rb) * L + x;
-                    upd = 0;
 #pragma unroll
-                    for (int j = 0; j < RPT; j++) upd |= (m[j * L] ? 1u : 0u) << j;
+                for (int j = 0; j < RPT; j++) {
+                    if (is_boundary_row(j)) continue;
+                    const int d = ups[j] - 2;
+                    const int ri = a_cur[j] ? d : -d;                                  // (2a-1)(ups-2) = Ising.py:101-111
+                    if (!MASK || ((upd >> j) & 1u)) sts_f32(keep_addr[j], keep_q[j] + A.lr * ((float)ri - keep_q[j]));
+                    packed += a_cur[j] + ((ri + 2) << 16);
+                }
+            }
+            // the halo word of state k: asked for now, looked at after the interior draws
+            if (boundary && (uint32_t)(hv >> 32) != seq) hv = ld_halo(mb_in + par * MB_PARITY);
+            // ---- interior rows: draw sweep k (staged: all Q-pair loads, all decisions, all ballots) ----
+            if (draw) {
+#pragma unroll
+                for (int j = 0; j < RPT; j++) {
+                    if (is_boundary_row(j)) continue;
+                    keep_addr[j] = q_site0 + (uint32_t)ups[j] * PLANE + (uint32_t)j * (L * 8u);
+                    pr[j] = lds_f32x2(keep_addr[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < RPT; j++)
+                    if (!is_boundary_row(j)) a_cur[j] = draw_action_scaled(uu[j], pr[j].x, pr[j].y, tparam);
+#pragma unroll
+                for (int j = 0; j < RPT; j++)
+                    if (!is_boundary_row(j)) w_cur[j] = __ballot_sync(0xFFFFFFFFu, a_cur[j] != 0);
+                if (lane == 0) {
+#pragma unroll
+                    for (int j = 0; j < RPT; j++)
+                        if (!is_boundary_row(j)) sts_u32(own_w + nxt + (uint32_t)j * WPR * 4u, w_cur[j]);
                 }
 #pragma unroll
                 for (int j = 0; j < RPT; j++) {
-                    const int d = ups[j] - 2;
-                    const int ri = a_cur[j] ? d : -d;                                  // (2a-1)(ups-2) = Ising.py:101-111
-                    const float reward = (float)ri;
-                    if (!MASK || ((upd >> j) & 1u)) sts_f32(keep_addr[j], keep_q[j] + A.lr * (reward - keep_q[j]));
-                    packed += a_cur[j] + ((ri + 2) << 16);
+                    if (is_boundary_row(j)) continue;
+                    keep_q[j] = a_cur[j] ? pr[j].y : pr[j].x;
+                    keep_addr[j] += (uint32_t)a_cur[j] * 4u;
                 }
+            }
+            // ---- the boundary row: halo word of state k, count, finish, draw, and its new word straight to the neighbour ----
+            if (boundary) {
+                while ((uint32_t)(hv >> 32) != seq) hv = ld_halo(mb_in + par * MB_PARITY);
+                const int v_halo = (int)(((uint32_t)hv >> lane) & 1u);
+                auto boundary_row = [&](auto jc) {
+                    constexpr int j = decltype(jc)::value;
+                    const int up = j == 0 ? v_halo : a_next_to_boundary, dn = j == 0 ? a_next_to_boundary : v_halo;
+                    const uint32_t Wl = lds_u32(own_l + cur + (uint32_t)j * WPR * 4u), Wr = lds_u32(own_r + cur + (uint32_t)j * WPR * 4u);
+                    const uint32_t lf = __funnelshift_l(Wl, w_cur[j], 1), rt = __funnelshift_r(w_cur[j], Wr, 1);
+                    const int u = up + dn + (int)((lf >> lane) & 1u) + (int)((rt >> lane) & 1u);
+                    if (k > 0) {
+                        const int d = u - 2;
+                        const int ri = a_cur[j] ? d : -d;
+                        if (!MASK || ((upd >> j) & 1u)) sts_f32(keep_addr[j], keep_q[j] + A.lr * ((float)ri - keep_q[j]));
+                        packed += a_cur[j] + ((ri + 2) << 16);
+                    }
+                    if (draw) {
+                        keep_addr[j] = q_site0 + (uint32_t)u * PLANE + (uint32_t)j * (L * 8u);
+                        const float2 q = lds_f32x2(keep_addr[j]);
+                        a_cur[j] = draw_action_scaled(uu[j], q.x, q.y, tparam);
+                        w_cur[j] = __ballot_sync(0xFFFFFFFFu, a_cur[j] != 0);
+                        if (lane == 0) {
+                            st_halo(mb_out + (par ^ 1u) * MB_PARITY, w_cur[j], seq + 1u);
+                            sts_u32(own_w + nxt + (uint32_t)j * WPR * 4u, w_cur[j]);
+                        }
+                        keep_q[j] = a_cur[j] ? q.y : q.x;
+                        keep_addr[j] += (uint32_t)a_cur[j] * 4u;
+                    }
+                };
+                if (first_band) boundary_row(std::integral_constant<int, 0>{});
+                else boundary_row(std::integral_constant<int, RPT - 1>{});
+            }
+            if (k > 0) {
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) packed += __shfl_xor_sync(0xFFFFFFFFu, packed, o);
                 if (lane == 0) atomicAdd(&s_stat[(k - 1) & 1], packed);
             }
-            if (k == A.K) break;
-            // ---- draw sweep k.  The strip's boundary row goes FIRST and straight into the neighbour's mailbox, so that
-            //      the L2 round trip of the halo runs under the other rows' draws; the next halo is asked for right away ----
-            if (A.u != nullptr) {
-#pragma unroll
-                for (int j = 0; j < RPT; j++)
-                    uu[j] = A.u[((size_t)k * A.B + b) * N + (size_t)(row0 + rb + j) * L + x] * 4294967296.0f;
-            }
-            const uint32_t nxt = cur ^ BUF;
-            float2 pr[RPT];
-#pragma unroll
-            for (int j = 0; j < RPT; j++) {
-                keep_addr[j] = q_site0 + (uint32_t)ups[j] * PLANE + (uint32_t)j * (L * 8u);
-                pr[j] = lds_f32x2(keep_addr[j]);
-            }
-            if (boundary) {
-                if (first_band) { a_cur[0] = draw_action_scaled(uu[0], pr[0].x, pr[0].y, tparam); w_cur[0] = __ballot_sync(0xFFFFFFFFu, a_cur[0] != 0); }
-                else { a_cur[RPT - 1] = draw_action_scaled(uu[RPT - 1], pr[RPT - 1].x, pr[RPT - 1].y, tparam); w_cur[RPT - 1] = __ballot_sync(0xFFFFFFFFu, a_cur[RPT - 1] != 0); }
-                if (lane == 0) st_halo(mb_out + (par ^ 1u) * MB_PARITY, first_band ? w_cur[0] : w_cur[RPT - 1], seq + 1u);
-            }
-#pragma unroll
-            for (int j = 0; j < RPT; j++)
-                if (!((j == 0 && first_band) || (j == RPT - 1 && last_band)))
-                    a_cur[j] = draw_action_scaled(uu[j], pr[j].x, pr[j].y, tparam);
-#pragma unroll
-            for (int j = 0; j < RPT; j++)
-                if (!((j == 0 && first_band) || (j == RPT - 1 && last_band)))
-                    w_cur[j] = __ballot_sync(0xFFFFFFFFu, a_cur[j] != 0);
-            if (lane == 0) {
-#pragma unroll
-                for (int j = 0; j < RPT; j++) sts_u32(own_w + nxt + (uint32_t)j * WPR * 4u, w_cur[j]);
-            }
-#pragma unroll
-            for (int j = 0; j < RPT; j++) {
-                keep_q[j] = a_cur[j] ? pr[j].y : pr[j].x;
-                keep_addr[j] += (uint32_t)a_cur[j] * 4u;
-            }
-            // state k+1's halo is asked for HERE: the neighbour sent it before its own interior draws, so it has been in
-            // L2 for a while, and the load's round trip runs under the Philox rounds below instead of in front of the
-            // next sweep (asked for after them it cost ~230 cycles per sweep)
-            if (boundary) hv = ld_halo(mb_in + (par ^ 1u) * MB_PARITY);
+            if (!draw) break;
+            // ---- the next sweep's Philox draws and temperature (independent of the lattice) ----
             if (k + 1 < A.K) {
                 if (A.u == nullptr) draw_uniforms(A.step0 + (uint32_t)(k + 1));
                 tparam = temperature_param(A.temperatures[k + 1]);
@@ -991,9 +1032,23 @@ static bool launch_ising_persistent(const IsingRunArgs<float> &A, cudaStream_t s
     MF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (int)threads, smem));
     const int n_slots = std::min(A.B, per_sm * n_sm / C);           // lattices in flight: 9 of 16 strips on 148 SMs
     if (n_slots < 1) return false;
-    unsigned long long *halo = nullptr;                              // mailboxes [slot][rank][parity][top|bottom][wpr]
+    // mailboxes [slot][rank][parity][top|bottom][wpr]: one buffer per (device, stream), kept for the life of the process
+    // (launches on one stream are ordered, so they can share it; a stream-ordered allocation per launch made the
+    // host-synchronised loop of bench.py's e2e leg jitter by hundreds of milliseconds)
     const size_t halo_bytes = (size_t)n_slots * C * 2 * 2 * wpr * sizeof(unsigned long long);
-    MF_CUDA(cudaMallocAsync(&halo, halo_bytes, st));
+    unsigned long long *halo = nullptr;
+    {
+        static std::mutex mu;
+        static std::map<std::pair<int, cudaStream_t>, std::pair<unsigned long long *, size_t>> pool;
+        std::lock_guard<std::mutex> lock(mu);
+        auto &slot = pool[std::make_pair(dev, st)];
+        if (slot.second < halo_bytes) {
+            if (slot.first) { MF_CUDA(cudaStreamSynchronize(st)); cudaFree(slot.first); }
+            MF_CUDA(cudaMalloc(&slot.first, halo_bytes));
+            slot.second = halo_bytes;
+        }
+        halo = slot.first;
+    }
     MF_CUDA(cudaMemsetAsync(halo, 0, halo_bytes, st));              // sequence numbers start at 1
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(n_slots * C)); cfg.blockDim = dim3(threads);
@@ -1002,9 +1057,7 @@ static bool launch_ising_persistent(const IsingRunArgs<float> &A, cudaStream_t s
     attr[0].id = cudaLaunchAttributeCooperative;                    // the strips of a lattice wait for each other: the
     attr[0].val.cooperative = 1;                                    // whole grid must be resident at once
     cfg.attrs = attr; cfg.numAttrs = 1;
-    const cudaError_t err = cudaLaunchKernelEx(&cfg, kern, A, n_slots, halo);
-    cudaFreeAsync(halo, st);
-    MF_CUDA(err);
+    MF_CUDA(cudaLaunchKernelEx(&cfg, kern, A, n_slots, halo));
     return true;
 }
 

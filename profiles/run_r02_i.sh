@@ -1,0 +1,16 @@
+#!/bin/bash
+# round 2, call I: Ising persistent kernel v4 (boundary row last), policy-forward probe
+set -x
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_cuda_ising.py tests/test_ising_env.py -m gpu -x -q > gpurun_out/pytest_ising.log 2>&1; echo "pytest ising rc=$?" >> gpurun_out/pytest_ising.log
+tail -3 gpurun_out/pytest_ising.log
+timeout 300 python bench.py --workload c5 --no-cpu > gpurun_out/bench_c5.json 2> gpurun_out/bench_c5.err; echo "c5 rc=$?"
+MFMARL_ISING_RPT=4 timeout 300 python bench.py --workload c5 --no-cpu > gpurun_out/bench_c5_rpt4.json 2> gpurun_out/bench_c5_rpt4.err
+for f in c5 c5_rpt4; do python - <<PY
+import json
+d=json.loads(open("gpurun_out/bench_$f.json").read().strip().splitlines()[-1])
+print("$f", "%.4g"%d["value"], "ms/step %.4f"%d["ms_per_step"], d.get("region_ms"), "frac", d["roofline"]["frac"], "e2e %.4g"%d["e2e"]["value"])
+PY
+done
+timeout 600 python profiles/policy_forward_probe.py 65536 > gpurun_out/policy_forward_probe.txt 2>&1; echo "probe rc=$?"
+cat gpurun_out/policy_forward_probe.txt | head -40
