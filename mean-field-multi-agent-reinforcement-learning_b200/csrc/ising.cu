@@ -754,6 +754,7 @@ __global__ void __launch_bounds__(L * (ROWS / RPT), 1) k_ising_persist_f32(const
     float *s_q = (float *)s_raw;                                                    // [5][STRIP][2]
     uint32_t *s_bits = (uint32_t *)(s_raw + (size_t)5 * STRIP * 8);                 // [2][HR][WPR]
     int *s_stat = (int *)(s_bits + 2 * HR * WPR);                                   // [2] packed statistics per sweep parity
+    float *s_tparam = (float *)(s_stat + 4);                                        // [K] log2(e) / T_k, computed once per launch
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int x = tid % L, band = tid / L, w = x >> 5;
@@ -774,6 +775,7 @@ __global__ void __launch_bounds__(L * (ROWS / RPT), 1) k_ising_persist_f32(const
         halo + (((size_t)slot * C + (first_band ? up_rank : dn_rank)) * 2 * 2 + (first_band ? 1 : 0)) * WPR + w;
     const bool boundary = first_band || last_band;
 
+    for (int i = threadIdx.x; i < A.K; i += NT) s_tparam[i] = temperature_param(A.temperatures[i]);
     uint32_t state_no = 0;                                      // lattice states published so far by this slot
     for (int b = slot; b < A.B; b += n_slots, state_no += (uint32_t)A.K + 1u) {
         const size_t lbase = (size_t)b * N;
@@ -812,7 +814,6 @@ __global__ void __launch_bounds__(L * (ROWS / RPT), 1) k_ising_persist_f32(const
             }
         };
         if (A.u == nullptr) draw_uniforms(A.step0);
-        float tparam = temperature_param(A.temperatures[0]);
         float keep_q[RPT]; uint32_t keep_addr[RPT];
 #pragma unroll
         for (int j = 0; j < RPT; j++) { keep_q[j] = 0.0f; keep_addr[j] = q_site0; }
@@ -837,6 +838,7 @@ __global__ void __launch_bounds__(L * (ROWS / RPT), 1) k_ising_persist_f32(const
                 if (A.reward_sum) atomicAdd(&A.reward_sum[(size_t)(k - 2) * A.B + b], (float)((pk >> 16) - 2 * RPT * NT));
             }
             const bool draw = k < A.K;
+            const float tparam = s_tparam[draw ? k : 0];      // (written before the first barrier of the first lattice)
             if (draw && A.u != nullptr) {
 #pragma unroll
                 for (int j = 0; j < RPT; j++)
@@ -941,16 +943,12 @@ __global__ void __launch_bounds__(L * (ROWS / RPT), 1) k_ising_persist_f32(const
                 else boundary_row(std::integral_constant<int, RPT - 1>{});
             }
             if (k > 0) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) packed += __shfl_xor_sync(0xFFFFFFFFu, packed, o);
+                packed = __reduce_add_sync(0xFFFFFFFFu, packed);           // one REDUX instead of a five-step shuffle tree
                 if (lane == 0) atomicAdd(&s_stat[(k - 1) & 1], packed);
             }
             if (!draw) break;
             // ---- the next sweep's Philox draws and temperature (independent of the lattice) ----
-            if (k + 1 < A.K) {
-                if (A.u == nullptr) draw_uniforms(A.step0 + (uint32_t)(k + 1));
-                tparam = temperature_param(A.temperatures[k + 1]);
-            }
+            if (k + 1 < A.K && A.u == nullptr) draw_uniforms(A.step0 + (uint32_t)(k + 1));
         }
         __syncthreads();
         if (tid == 0) {
@@ -1024,7 +1022,21 @@ static bool launch_ising_persistent(const IsingRunArgs<float> &A, cudaStream_t s
 #undef MF_PICK
     if (!kern) return false;
     const int C = A.L / A.rows_per, wpr = A.L / 32;
-    const size_t smem = resident_smem_bytes<float>(A.L, A.rows_per);
+    constexpr int kMaxSweeps = 4096;                                 // per launch: the temperature table lives in shared memory
+    if (A.K > kMaxSweeps) {
+        for (int k0 = 0; k0 < A.K; k0 += kMaxSweeps) {
+            IsingRunArgs<float> part = A;
+            part.K = std::min(kMaxSweeps, A.K - k0);
+            part.temperatures = A.temperatures + k0; part.step0 = A.step0 + (uint32_t)k0;
+            if (A.u) part.u = A.u + (size_t)k0 * A.B * A.L * A.L;
+            if (A.mask) part.mask = A.mask + (size_t)k0 * A.B * A.L * A.L;
+            part.n_up = A.n_up + (size_t)k0 * A.B;
+            if (A.reward_sum) part.reward_sum = A.reward_sum + (size_t)k0 * A.B;
+            if (!launch_ising_persistent(part, st)) return false;
+        }
+        return true;
+    }
+    const size_t smem = resident_smem_bytes<float>(A.L, A.rows_per) + (size_t)A.K * sizeof(float);
     MF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, n_sm = 0, per_sm = 0;
     MF_CUDA(cudaGetDevice(&dev));
