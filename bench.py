@@ -305,7 +305,8 @@ def measure_battle(ctx, args, workload, K, W, min_seconds, envs_per_gpu=0, pipel
     for h in range(P):
         env = BatchedGridWorld(Eh, map_size=wl["map_size"], capacity=cap, device=dev, rng="philox", seed=0,
                                env_base=rank * E + h * Eh, max_steps=wl["max_steps"], auto_reset=True,
-                               obs_tile_agents=tile, step_threads=args.step_threads)
+                               obs_tile_agents=tile, step_threads=args.step_threads,
+                               concurrent_step_envs=Eh if P > 1 else 0)   # the sibling engine's k_step overlaps this k_obs
         env.reset(); env.add_agents(0, left); env.add_agents(1, right)
         envs.append(env)
     streams = [torch.cuda.current_stream()] if P == 1 else [torch.cuda.Stream(device=dev) for _ in range(P)]
@@ -795,13 +796,14 @@ def run_play(args):
     elif args.policy_precision == "bf16":
         for m in models:
             m.act_autocast = torch.bfloat16
-    play_batched(env, 0, max(3, args.warmup), models, eps=1.0, train=False, left_group=0)
+    obs_dtype = torch.bfloat16 if args.policy_precision == "bf16rows" else None   # the engine emits the policy's input format
+    play_batched(env, 0, max(3, args.warmup), models, eps=1.0, train=False, left_group=0, obs_dtype=obs_dtype)
     torch.cuda.synchronize()
     a0 = int(env.get("agent_steps").sum())
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(dev.index or 0) as clocks:
         t0.record()
-        play_batched(env, 1, K, models, eps=1.0, train=False, left_group=0)
+        play_batched(env, 1, K, models, eps=1.0, train=False, left_group=0, obs_dtype=obs_dtype)
         t1.record()
         torch.cuda.synchronize()
     ms = t0.elapsed_time(t1)
@@ -872,7 +874,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=60000, help="timed steps per CPU-baseline worker")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--algo", default="mfq", choices=["mfq", "il", "mfac", "ac"], help="--workload play: the learner")
-    ap.add_argument("--policy-precision", default="fp32", choices=["fp32", "tf32", "bf16"],
+    ap.add_argument("--policy-precision", default="fp32", choices=["fp32", "tf32", "bf16", "bf16rows"],
                     help="--workload play: precision of the rollout forward pass (training is always fp32)")
     ap.add_argument("--obs-to-host-steps", type=int, default=5,
                     help="extra e2e variant: steps timed with the observations copied to the host too (0 = skip)")

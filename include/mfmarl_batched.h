@@ -38,6 +38,9 @@ typedef struct mfb_config {
     int obs_tile_agents;   /* agents per observation CTA, 0 = auto: clamp(capacity, 64, 256)         */
     int obs_record;        /* per-env observation record kept by k_step for k_obs: -1 = auto (on for
                               capacity >= 256), 0 = off, 1 = on; same observations either way          */
+    int concurrent_step_envs; /* pipelined use: envs of a sibling engine whose mfb_step runs on another stream while
+                              this engine's mfb_observe streams; the observation kernel then leaves SM slots free
+                              where a step CTA does not fit beside it (0 = not pipelined)                     */
     int random_sides;      /* with auto_reset: every env draws per episode (Philox keyed by seed, env, episode)
                               whether the two armies swap their starting blocks AND ids -- generate_map picks
                               the left army with random.randint(0, 1) each round (senario_battle.py:14) and
@@ -76,6 +79,13 @@ int mfb_observe(mfb_engine *eng, float *d_view, float *d_feature, int group_mask
  * skips that group. */
 int mfb_observe_groups(mfb_engine *eng, float *d_view0, float *d_feature0, float *d_view1, float *d_feature1,
                        void *stream);
+
+/* K1 with bf16 rows in the layout a bf16 channels-last policy network consumes directly:
+ *   d_viewG  __nv_bfloat16[E][cap][13][13][8]: the 7 channels of mfb_observe_groups rounded to nearest-even bf16,
+ *            channel 7 = 0 (a cell is one 16-byte vector); d_featureG stays float[E][cap][feature_size].
+ * Same values as casting the fp32 observation (tests compare bit for bit); 2840 instead of 4868 bytes per agent. */
+int mfb_observe_groups_bf16(mfb_engine *eng, void *d_view0, float *d_feature0, void *d_view1, float *d_feature1,
+                            void *stream);
 
 /* K2, fused set_action(g0), set_action(g1), step, get_reward, get_alive, mean action, clear_dead.
  *   d_actions      int32[E][2][cap]       in

@@ -75,6 +75,7 @@ int mfb_create(const mfb_config *c, mfb_engine **out) {
     ec.embedding_size = c->embedding_size; ec.rng_mode = c->rng_mode; ec.seed = c->seed;
     ec.env_base = c->env_base; ec.max_steps = c->max_steps; ec.device = c->device;
     ec.step_threads = c->step_threads; ec.obs_tile_agents = c->obs_tile_agents; ec.obs_cached = c->obs_record; ec.random_sides = c->random_sides;
+    ec.concurrent_step_envs = c->concurrent_step_envs;
     ec.type.hp = c->hp; ec.type.speed = c->speed; ec.type.view_radius = c->view_radius;
     ec.type.attack_radius = c->attack_radius; ec.type.damage = c->damage; ec.type.step_recover = c->step_recover;
     ec.type.kill_supply = c->kill_supply; ec.type.step_reward = c->step_reward; ec.type.kill_reward = c->kill_reward;
@@ -137,6 +138,15 @@ int mfb_observe_groups(mfb_engine *h, float *d_view0, float *d_feature0, float *
     const int mask = (d_view0 ? 1 : 0) | (d_view1 ? 2 : 0);
     E(h).observe_groups(v, f, E(h).params().cap, mask, (cudaStream_t)stream);
     MFB_END("mfb_observe_groups")
+}
+
+int mfb_observe_groups_bf16(mfb_engine *h, void *d_view0, float *d_feature0, void *d_view1, float *d_feature1,
+                            void *stream) {
+    MFB_BEGIN
+    float *v[kGroups] = {(float *)d_view0, (float *)d_view1}, *f[kGroups] = {d_feature0, d_feature1};
+    const int mask = (d_view0 ? 1 : 0) | (d_view1 ? 2 : 0);
+    E(h).observe_groups(v, f, E(h).params().cap, mask, (cudaStream_t)stream, true);
+    MFB_END("mfb_observe_groups_bf16")
 }
 
 int mfb_step(mfb_engine *h, const int32_t *d_actions, const int32_t *d_attack_perm, float *d_reward,

@@ -687,6 +687,9 @@ constexpr int kObsChunk = MF_OBS_CHUNK;                        // agents per bul
 constexpr int kObsThreads = 32 * kObsChunk, kObsWarps = kObsThreads / 32;
 constexpr int kObsCtasPerSm = 16 / kObsChunk;                  // resident CTAs per SM the kernel is tuned for
 constexpr int kObsStageBytes = kObsChunk * kViewRow * 4;       // 37 856, a multiple of 16
+// bf16 rows (mfb_observe_groups_bf16): [169 cells][8 channels] bf16 -- channel 7 is padding, so a cell is one 16-byte
+// vector and a row (2704 B) is what a bf16 channels-last convolution reads without a cast or a padding pass
+constexpr int kViewRowBf16Bytes = kViewCells * 16;
 constexpr int kObsPasses = (kViewCells + 31) / 32;             // 6
 static_assert(kObsChunk == kObsWarps, "one warp composes one row of a chunk");
 
@@ -695,10 +698,11 @@ constexpr int kObsMaxTile = kObsThreads;   // agents per CTA tile, upper bound (
 // The pristine wall template is kept in shared memory when two CTAs per SM still fit with it (40x40: +5.4 KB);
 // larger maps copy it from global memory (L2) per item instead.
 __host__ __device__ inline bool obs_template_in_smem(int W, int H) { return (W + 2 * kPad) * (H + 2 * kPad) * 2 <= 8 * 1024; }
-__host__ __device__ inline ObsSmem obs_smem_layout(int W, int H, int cap, int cached) {
+__host__ __device__ inline ObsSmem obs_smem_layout(int W, int H, int cap, int cached, int bf16 = 0) {
     ObsSmem L; int o = 0;
-    L.stage0 = o; o += kObsStageBytes;
-    L.stage1 = o; o += kObsStageBytes;
+    const int stage_bytes = bf16 ? kObsChunk * kViewRowBf16Bytes : kObsStageBytes;
+    L.stage0 = o; o += stage_bytes;
+    L.stage1 = o; o += stage_bytes;
     L.rec = o;    o += 16 * kObsMaxTile;                              // (pos, id, state, last_rew) of the tile's agents
     L.record = L.bar = L.cnt = L.tmpl = 0;
     if (cached) {                                                     // the env's observation record, as one bulk copy lands it
@@ -739,11 +743,19 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 // observation record (CACHED = true) they name the group: 2 + group
 enum : uint32_t { KIND_EMPTY = 0, KIND_WALL = 1, KIND_OWN = 2, KIND_OTHER = 3 };
 
-template <bool CACHED>
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {     // round to nearest even, like torch's .to(bfloat16)
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
+template <bool CACHED, bool BF16>
 __global__ void __launch_bounds__(kObsThreads, kObsCtasPerSm)
 k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO io) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const ObsSmem L = obs_smem_layout(P.W, P.H, P.cap, CACHED);
+    const ObsSmem L = obs_smem_layout(P.W, P.H, P.cap, CACHED, BF16);
+    constexpr int kRowBytes = BF16 ? kViewRowBf16Bytes : kViewRow * 4;
+    constexpr int kStageBytes = kObsChunk * kRowBytes;
     float *const s_stage0 = (float *)(smem_raw + L.stage0), *const s_stage1 = (float *)(smem_raw + L.stage1);
     int4 *s_rec = (int4 *)(smem_raw + L.rec);
     float *s_hp10 = (float *)(smem_raw + L.hp10);
@@ -774,7 +786,7 @@ k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO i
     }
     // cells outside the view disc never carry occupancy: their five occupancy channels are zeroed once here and
     // never written again (the minimap channels of all 169 cells are refreshed per item below)
-    for (int i = tid; i < 2 * kObsStageBytes / 16; i += kObsThreads) ((uint4 *)s_stage0)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < 2 * kStageBytes / 16; i += kObsThreads) ((uint4 *)s_stage0)[i] = make_uint4(0u, 0u, 0u, 0u);
     if (tmpl_smem)
         for (int c = tid; c < (pcells * 2 + 15) / 16; c += kObsThreads)   // padded grid with the walls, built at commit
             ((uint4 *)(smem_raw + L.tmpl))[c] = ((const uint4 *)S.grid_template)[c];
@@ -903,7 +915,7 @@ k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO i
 
         // ---- stream the tile: compose, bulk-store ----
         // (selects, not io.view[g]: a dynamic index into a kernel parameter would spill the struct to local memory)
-        float *vout = (g ? io.view[1] : io.view[0]) + (size_t)e * io.env_stride * kViewRow;
+        float *vout = (float *)((unsigned char *)(g ? io.view[1] : io.view[0]) + (size_t)e * io.env_stride * kRowBytes);
         float *fout = (g ? io.feature[1] : io.feature[0]) + (size_t)e * io.env_stride * FS;
         int self_prev1 = -1, self_prev2 = -1;   // self-marker cell of the row in the other / this buffer
         int stale = 2;                          // staging buffers whose minimap channels belong to another item
@@ -923,7 +935,8 @@ k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO i
                 const int id = rec.y;
                 const uint32_t st = (uint32_t)rec.z;
                 const float last_rew = __int_as_float(rec.w);
-                float *row = (buf ? s_stage1 : s_stage0) + warp * kViewRow;
+                unsigned char *const row_b = (unsigned char *)(buf ? s_stage1 : s_stage0) + warp * kRowBytes;
+                float *const row = (float *)row_b;
                 // window top-left corner (ax - 6, ay - 6) in padded coordinates is simply (ax, ay)
                 const uint16_t *win = s_code + ay * PW + ax;
                 // staged (all grid look-ups, then all hp look-ups, then the stores): a store of one pass would otherwise
@@ -933,6 +946,38 @@ k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO i
                 for (int it = 0; it < kDiscPasses; it++) code[it] = (uint32_t)win[off[it]];      // idle lanes read offset 0
 #pragma unroll
                 for (int it = 0; it < kDiscPasses; it++) hpv[it] = s_hp10[code[it] & 0x3FFFu];
+                self_new = lut[W + ay] + lut[ax];
+                if constexpr (BF16) {
+                    // one 16-byte vector per cell: {wall, own, own hp, own minimap | other, other hp, other minimap, 0} in bf16
+                    if (stale > 0) {                    // new item: cells outside the disc only ever hold the two minimaps
+#pragma unroll
+                        for (int it = 0; it < kObsPasses; it++) {
+                            const int c = it * 32 + lane;
+                            if (c < kViewCells)
+                                *(uint4 *)(row_b + c * 16) = make_uint4(0u, pack_bf16x2(0.0f, mini_own[c]), 0u, pack_bf16x2(mini_oth[c], 0.0f));
+                        }
+                    } else if (lane == 0 && self_prev2 >= 0) {      // the row's previous self marker (it may sit outside the disc)
+                        *(uint4 *)(row_b + self_prev2 * 16) = make_uint4(0u, pack_bf16x2(0.0f, mini_own[self_prev2]), 0u,
+                                                                          pack_bf16x2(mini_oth[self_prev2], 0.0f));
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int it = 0; it < kDiscPasses; it++) {
+                        if (cell7[it] >= 0) {
+                            const uint32_t k = code[it] >> 14;
+                            const int c = cell7[it] / kChan;
+                            const float own = k == kind_own ? 1.0f : 0.0f, oth = k == kind_oth ? 1.0f : 0.0f;
+                            *(uint4 *)(row_b + c * 16) = make_uint4(
+                                pack_bf16x2(k == KIND_WALL ? 1.0f : 0.0f, own), pack_bf16x2(k == kind_own ? hpv[it] : 0.0f, mini_own[c]),
+                                pack_bf16x2(oth, k == kind_oth ? hpv[it] : 0.0f), pack_bf16x2(mini_oth[c], 0.0f));
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) {                    // self marker in BOTH minimap channels (GridWorld.cc:396-408)
+                        ((uint16_t *)(row_b + self_new * 16))[3] = (uint16_t)(pack_bf16x2(mini_own[self_new] + 1.0f, 0.0f) & 0xFFFFu);
+                        ((uint16_t *)(row_b + self_new * 16))[6] = (uint16_t)(pack_bf16x2(mini_oth[self_new] + 1.0f, 0.0f) & 0xFFFFu);
+                    }
+                } else {
 #pragma unroll
                 for (int it = 0; it < kDiscPasses; it++) {
                     if (cell7[it] >= 0) {               // only the last pass has idle lanes
@@ -953,7 +998,6 @@ k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO i
                     }
                 }
                 // self marker in BOTH minimap channels (GridWorld.cc:396-408): move it
-                self_new = lut[W + ay] + lut[ax];
                 __syncwarp();
                 if (lane == 0) {
                     if (stale <= 0 && self_prev2 >= 0) {
@@ -962,6 +1006,7 @@ k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO i
                     }
                     row[self_new * kChan + 3] = mini_own[self_new] + 1.0f;
                     row[self_new * kChan + 6] = mini_oth[self_new] + 1.0f;
+                }
                 }
                 // features (GridWorld.cc:411-421): id bits LSB first, one-hot last action, last reward, x/W, y/H
                 const float fx = s_fxy[ax], fy = s_fxy[W + ay];
@@ -982,8 +1027,8 @@ k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO i
             if (tid == 0) {
                 // rows are 4732 B (= 12 mod 16): a ragged tail is rounded up to 16 B; the <= 12 spill bytes land
                 // in the next, unused row of the same [cap] block (cap is a multiple of 4, see engine.cu)
-                const uint32_t bytes = ((uint32_t)cn * kViewRow * 4 + 15u) & ~15u;
-                bulk_store_s2g(vout + (size_t)c0 * kViewRow, buf ? s_stage1 : s_stage0, bytes);
+                const uint32_t bytes = ((uint32_t)cn * kRowBytes + 15u) & ~15u;     // (bf16 rows are 16-byte multiples)
+                bulk_store_s2g((unsigned char *)vout + (size_t)c0 * kRowBytes, buf ? s_stage1 : s_stage0, bytes);
                 bulk_commit();
             }
         }

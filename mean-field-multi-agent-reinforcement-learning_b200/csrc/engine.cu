@@ -224,6 +224,7 @@ Engine::Engine(const EngineConfig &cfg) : cfg_(cfg) {
 #ifdef MF_PROFILE_BUILD
     { const char *dbg = getenv("MFMARL_OBS_DEBUG"); obs_debug_ = dbg ? atoi(dbg) : 0; }
 #endif
+    { const char *lim = getenv("MFMARL_OBS_GRID"); obs_grid_limit_ = lim ? atoi(lim) : 0; }
     set_seed(cfg.seed);   // seed 0 -> minstd state 1, as GridWorld.cc:31 random_engine.seed(0)
     alloc_state(std::max(4, round_up(cfg.capacity, 4)));
     reset();
@@ -507,7 +508,7 @@ void Engine::observe(float *d_view, float *d_feature, int group_mask, cudaStream
 }
 
 void Engine::observe_groups(float *const d_view[kGroups], float *const d_feature[kGroups], int env_stride,
-                            int group_mask, cudaStream_t st) {
+                            int group_mask, cudaStream_t st, bool bf16) {
     commit(st);
     if (group_mask < 1 || group_mask > 3) throw Fatal("observe: bad group mask");
     ObsIO io;
@@ -518,21 +519,37 @@ void Engine::observe_groups(float *const d_view[kGroups], float *const d_feature
     }
     io.env_stride = env_stride; io.group_mask = group_mask;
     io.debug = obs_debug_;
-    const ObsSmem L = obs_smem_layout(P_.W, P_.H, P_.cap, P_.obs_cached);
-    void (*kern)(const BattleParams, const BattleState, const ObsIO) = P_.obs_cached ? k_obs<true> : k_obs<false>;
+    const ObsSmem L = obs_smem_layout(P_.W, P_.H, P_.cap, P_.obs_cached, bf16);
+    void (*kern)(const BattleParams, const BattleState, const ObsIO) =
+        P_.obs_cached ? (bf16 ? k_obs<true, true> : k_obs<true, false>) : (bf16 ? k_obs<false, true> : k_obs<false, false>);
     raise_dynamic_smem((const void *)kern, L.total, device_);
-    if (obs_attr_ != L.total) {
-        MF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&obs_ctas_per_sm_, kern, kObsThreads, L.total));
-        obs_attr_ = L.total;
+    int &ctas_per_sm = obs_ctas_per_sm_[bf16 ? 1 : 0];
+    if (obs_attr_[bf16 ? 1 : 0] != L.total) {
+        MF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kObsThreads, L.total));
+        obs_attr_[bf16 ? 1 : 0] = L.total;
     }
-    // persistent CTAs (two per SM, shared-memory bound) take (env, group, tile) work items from a ticket counter
-    const size_t ctas = (size_t)std::max(1, obs_ctas_per_sm_) * n_sm_;
+    // persistent CTAs (as many per SM as the shared memory allows) take (env, group, tile) work items from a ticket counter
+    size_t ctas = (size_t)std::max(1, ctas_per_sm) * n_sm_;
+    // Pipelined use (two engines on two streams): the sibling's k_step runs while this k_obs streams.  Where a k_step CTA
+    // does not fit beside a full complement of k_obs CTAs (512 v 512: 73 KB next to 2 x 103 KB), it would wait for a
+    // k_obs CTA to EXIT -- and persistent CTAs all exit at the end.  Leaving one k_obs slot free per expected k_step CTA
+    // lets the two kernels really overlap: C4 on two streams 1.07e9 -> 1.16e9 agent-steps/s (profiles/r02).
+    if (cfg_.concurrent_step_envs > 0) {
+        const int step_smem = step_smem_layout(P_.W, P_.H, P_.cap, P_.obs_cached).total + 1024;
+        const int sm_smem = 227 * 1024, obs_smem = L.total + 1024;
+        const int fit_beside_full = (sm_smem - ctas_per_sm * obs_smem) / step_smem;
+        if (fit_beside_full < 1 && ctas_per_sm > 1) {
+            const int per_freed_slot = std::max(1, (sm_smem - (ctas_per_sm - 1) * obs_smem) / step_smem);
+            const size_t reserve = ((size_t)cfg_.concurrent_step_envs + per_freed_slot - 1) / per_freed_slot;
+            ctas = ctas > reserve + (size_t)n_sm_ ? ctas - reserve : (size_t)n_sm_;
+        }
+    }
     // tile: a larger tile amortises the per-item grid rebuild over more agents (it matters when groups are large),
     // but the items must stay numerous enough to balance over the CTAs: measured at cap 512 x 128 envs, 128-agent
     // tiles (1024 items) beat 256 (512 items for 296 CTAs) and 64
     int want_tile = cfg_.obs_tile_agents;
     if (want_tile <= 0 && P_.obs_cached) {
-        // an item starts with one bulk copy of the env's record, so tiles can be small: many items per CTA, and the
+        // an item starts with one copy of the env's record, so tiles can be small: many items per CTA, and the
         // last wave is short
         want_tile = 32;
     } else if (want_tile <= 0) {
@@ -545,7 +562,8 @@ void Engine::observe_groups(float *const d_view[kGroups], float *const d_feature
     io.tile_agents = std::min(kObsMaxTile, std::max(kObsChunk, round_up(want_tile, kObsChunk)));
     io.tiles_per_group = (P_.cap + io.tile_agents - 1) / io.tile_agents;
     const size_t items = (size_t)P_.E * (group_mask == 3 ? 2 : 1) * io.tiles_per_group;
-    const unsigned grid = (unsigned)std::min<size_t>(items, ctas);
+    unsigned grid = (unsigned)std::min<size_t>(items, ctas);
+    if (obs_grid_limit_ > 0) grid = std::min(grid, (unsigned)obs_grid_limit_);   // experiment knob (MFMARL_OBS_GRID)
     // every launch takes its own ticket pair from a small ring, so observe launches of one engine may overlap on
     // different streams (the last CTA of a launch rewinds its pair)
     BattleState S = S_;

@@ -45,6 +45,8 @@ struct EngineConfig {
     int n_envs = 1, width = 40, height = 40, capacity = 64, embedding_size = 10;
     int rng_mode = RNG_MINSTD, max_steps = 0, env_base = 0, device = -1 /* current */;
     int step_threads = 0 /* auto */, obs_tile_agents = 0 /* auto: clamp(cap, 64, 256); 32 with the observation record */;
+    int concurrent_step_envs = 0 /* envs of a sibling engine whose k_step runs (on another stream) while this engine's
+                                    k_obs streams: k_obs then leaves SM slots free for it where the two do not fit together */;
     int random_sides = 0 /* auto-reset draws per env and episode whether the armies swap their starting blocks */;
     int obs_cached = -1 /* observation record: -1 auto (capacity >= 256, or MFMARL_OBS_CACHED), 0 off, 1 on */;
     unsigned seed = 0;
@@ -71,8 +73,10 @@ public:
     // ---- kernels ----
     void observe(float *d_view, float *d_feature, int group_mask, cudaStream_t st);
     // per-group output blocks [E][cap][...] (env_stride = cap) or any layout with `env_stride` rows between envs
+    // bf16 = true: d_view[g] are __nv_bfloat16 [E][cap][13][13][8] blocks (channel 7 = 0), the rows a bf16 channels-last
+    // policy reads without a cast or a padding pass; features stay fp32
     void observe_groups(float *const d_view[kGroups], float *const d_feature[kGroups], int env_stride, int group_mask,
-                        cudaStream_t st);
+                        cudaStream_t st, bool bf16 = false);
     void step(const StepIO &io, cudaStream_t st);
     static void mean_action(const int32_t *d_actions, const int32_t *d_num, float *d_out, int rows,
                             int cap, int n_action, cudaStream_t st);
@@ -123,9 +127,10 @@ private:
     CircleRange view_, attack_, move_;
     int device_ = 0;
     int n_sm_ = 148;
-    int obs_attr_ = -1;                    // shared-memory size the occupancy below was queried for
+    int obs_attr_[2] = {-1, -1};           // shared-memory size the occupancy below was queried for (fp32 rows, bf16 rows)
     unsigned obs_launches_ = 0;            // k_obs launches so far (picks the ticket pair)
-    int obs_ctas_per_sm_ = 2;              // resident k_obs CTAs per SM at that size (occupancy query)
+    int obs_ctas_per_sm_[2] = {2, 2};      // resident k_obs CTAs per SM at that size (occupancy query)
+    int obs_grid_limit_ = 0;               // MFMARL_OBS_GRID: cap on k_obs CTAs (leaves SM slots to a concurrent k_step)
     int obs_debug_ = 0;                    // MFMARL_OBS_DEBUG at construction (profiling experiments only)
 
     // host-side placement template (what add_agents has built since the last reset)

@@ -43,6 +43,21 @@ class ACNet(nn.Module):
         _, h = self._features(view, feature)
         return torch.softmax(self.policy_head(h / 0.1), dim=1).clamp(1e-10, 1.0 - 1e-10)
 
+    def bf16_rollout_copy(self, view_space):
+        """bf16 twin for the engine's bf16 observation rows ([N, 13, 13, 8], channel 7 = 0): the first dense layer gets
+        zero weights for the extra channel (see base.bf16_rollout_copy)."""
+        import copy
+        from .base import _pad_last_input_channel
+        twin = copy.deepcopy(self)
+        h, w, c = view_space
+        if c % 8:
+            dense = nn.Linear(h * w * (c + 1), self.view_dense.out_features).to(self.view_dense.weight.device)
+            with torch.no_grad():
+                dense.weight.copy_(_pad_last_input_channel(self.view_dense.weight, h, w, c))
+                dense.bias.copy_(self.view_dense.bias)
+            twin.view_dense = dense
+        return twin.to(torch.bfloat16).eval()
+
     def forward(self, view, feature, prob=None):
         both, h = self._features(view, feature)
         policy = torch.softmax(self.policy_head(h / 0.1), dim=1).clamp(1e-10, 1.0 - 1e-10)
@@ -130,6 +145,11 @@ class _ActorCriticBase:
     def act(self, **kwargs):
         """multinomial(log policy) (ac.py:43-48, 70): numpy int32 for numpy inputs, a device tensor otherwise."""
         view, feature = kwargs['state'][0], kwargs['state'][1]
+        if isinstance(view, torch.Tensor) and view.dtype == torch.bfloat16:       # the engine's bf16 rows [N, 13, 13, 8]
+            if getattr(self, "_rollout16", None) is None or self._rollout16_stale:
+                self._rollout16, self._rollout16_stale = self.net.bf16_rollout_copy(self.view_space), False
+            policy = self._rollout16.policy(view, feature.to(torch.bfloat16)).float()
+            return torch.multinomial(policy, 1, generator=self.generator).reshape(-1).to(torch.int32)
         v, f = as_tensor(view, self.device), as_tensor(feature, self.device)
         if self.act_autocast is not None and v.is_cuda:
             with torch.autocast("cuda", dtype=self.act_autocast):
@@ -166,6 +186,7 @@ class _ActorCriticBase:
         if self.grad_sync:
             sync_gradients(self.net.parameters())
         self.optimizer.step()
+        self._rollout16_stale = True
         return (float(pg_loss.detach()), float(vf_loss.detach()), float(neg_entropy.detach()),
                 float(value.detach().mean()))
 
@@ -215,6 +236,7 @@ class _ActorCriticBase:
         self.net.load_state_dict(blob["net"])
         self.optimizer.load_state_dict(blob["optimizer"])
         print("[*] Loaded model from {}".format(path))
+        self._rollout16_stale = True
 
 
 class ActorCritic(_ActorCriticBase):

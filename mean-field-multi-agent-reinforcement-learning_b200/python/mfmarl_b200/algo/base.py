@@ -124,6 +124,31 @@ TF_QNET_LAYERS = [("Conv1", "conv1"), ("Conv2", "conv2"), ("Dense-Obs", "dense_o
                   ("Dense-Out", "dense_out"), ("Q-Value", "q_value")]
 
 
+def _pad_last_input_channel(weight, h, w, c):
+    """dense weight [out, h*w*c] over a flattened (h, w, c) view -> [out, h*w*(c+1)] with zeros for the extra channel"""
+    out = weight.new_zeros((weight.shape[0], h * w, c + 1))
+    out[:, :, :c] = weight.reshape(weight.shape[0], h * w, c)
+    return out.reshape(weight.shape[0], -1)
+
+
+def bf16_rollout_copy(net):
+    """A bf16, channels-last copy of a QNet for the ROLLOUT forward on the engine's bf16 observation rows
+    (BatchedGridWorld.observe_groups(dtype=torch.bfloat16): [N, 13, 13, 8], channel 7 = 0): conv1 takes the eighth
+    channel with zero weights, so no cast and no padding pass stand between k_obs and the tensor cores.  Training
+    always uses the fp32 network; refresh the copy after the weights change."""
+    import copy
+    twin = copy.deepcopy(net)
+    c_in = net.conv1.in_channels
+    if c_in % 8:
+        conv1 = nn.Conv2d(c_in + 1, net.conv1.out_channels, net.conv1.kernel_size)
+        with torch.no_grad():
+            conv1.weight.zero_()
+            conv1.weight[:, :c_in] = net.conv1.weight
+            conv1.bias.copy_(net.conv1.bias)
+        twin.conv1 = conv1.to(net.conv1.weight.device)
+    return twin.to(torch.bfloat16).to(memory_format=torch.channels_last).eval()
+
+
 class ValueNet:
     def __init__(self, env, handle, name, update_every=5, use_mf=False, learning_rate=1e-4, tau=0.005, gamma=0.95,
                  device=None):
@@ -141,6 +166,7 @@ class ValueNet:
         self.eval_net = QNet(self.view_space, self.feature_space, self.num_actions, use_mf).to(self.device)
         self.target_net = QNet(self.view_space, self.feature_space, self.num_actions, use_mf).to(self.device)
         self.optimizer = torch.optim.Adam(self.eval_net.parameters(), lr=learning_rate)
+        self._rollout16, self._rollout16_stale = None, True     # bf16 twin of eval_net for bf16 observation rows
 
     # -- the reference exposes the variable list for the self-play soft copy (base.py:185-190, tools.py:566-569)
     @property
@@ -180,6 +206,18 @@ class ValueNet:
         for numpy inputs, a device tensor for device inputs."""
         view, feature = kwargs["state"][0], kwargs["state"][1]
         self.temperature = kwargs.get("eps", self.temperature)
+        if isinstance(view, torch.Tensor) and view.dtype == torch.bfloat16:
+            # the engine's bf16 rows ([N, 13, 13, 8]): straight into the bf16 channels-last twin
+            if self._rollout16 is None or self._rollout16_stale:
+                self._rollout16, self._rollout16_stale = bf16_rollout_copy(self.eval_net), False
+            prob = kwargs.get("prob")
+            p = None
+            if self.use_mf:
+                p = prob.to(torch.bfloat16)
+                if p.shape[0] == 1 and view.shape[0] != 1:
+                    p = p.expand(view.shape[0], -1)
+            q = self._rollout16(view, feature.to(torch.bfloat16), p)
+            return q.argmax(dim=1).to(torch.int32)
         v, f, p = self._inputs(view, feature, kwargs.get("prob"))
         if self.use_mf and not isinstance(kwargs["prob"], torch.Tensor):
             assert len(kwargs["prob"]) == len(view)
@@ -204,6 +242,7 @@ class ValueNet:
         if self.grad_sync:
             sync_gradients(self.eval_net.parameters())
         self.optimizer.step()
+        self._rollout16_stale = True
         return float(loss.detach()), {"Eval-Q": round(float(e_q.detach().mean()), 6),
                                       "Target-Q": round(float(target_q.mean()), 6)}
 
@@ -221,4 +260,5 @@ class ValueNet:
         self.eval_net.load_state_dict(blob["eval"])
         self.target_net.load_state_dict(blob["target"])
         self.optimizer.load_state_dict(blob["optimizer"])
+        self._rollout16_stale = True
         print("[*] Loaded model from {}".format(path))

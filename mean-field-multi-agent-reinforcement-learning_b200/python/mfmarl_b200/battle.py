@@ -25,7 +25,7 @@ def _stream():
 
 class BatchedGridWorld:
     def __init__(self, n_envs, map_size=40, capacity=64, device=None, rng="minstd", seed=0, env_base=0,
-                 max_steps=0, auto_reset=False, step_threads=0, obs_tile_agents=0, obs_record=None, random_sides=False, **type_overrides):
+                 max_steps=0, auto_reset=False, step_threads=0, obs_tile_agents=0, obs_record=None, random_sides=False, concurrent_step_envs=0, **type_overrides):
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedGridWorld needs a CUDA device: there is no CPU fallback")
         self.lib = load_library()
@@ -39,6 +39,7 @@ class BatchedGridWorld:
         if obs_record is not None:          # None = the engine decides (on for capacity >= 256)
             cfg.obs_record = int(obs_record)
         cfg.random_sides = int(random_sides)
+        cfg.concurrent_step_envs = int(concurrent_step_envs)   # pipelined use: a sibling engine's step() overlaps this observe()
         for key, value in type_overrides.items():
             if not hasattr(cfg, key):
                 raise TypeError("unknown agent-type attribute %r" % key)
@@ -130,22 +131,29 @@ class BatchedGridWorld:
             check(self.lib.mfb_observe(self._h, _ptr(view), _ptr(feat), group_mask, _stream()))
         return view, feat
 
-    def observe_groups(self, groups=(0, 1)):
+    def observe_groups(self, groups=(0, 1), dtype=torch.float32):
         """Per-group observation blocks, each contiguous: -> [(view_g float32[E, cap, 13, 13, 7], feature_g
         float32[E, cap, 34]) for g in (0, 1)] (None for a group not asked for).  This is the layout a per-group
-        policy network consumes in place (`view_g.view(E * cap, 13, 13, 7)` is free)."""
+        policy network consumes in place (`view_g.view(E * cap, 13, 13, 7)` is free).
+
+        dtype=torch.bfloat16: view_g is bfloat16[E, cap, 13, 13, 8] -- the same seven channels rounded to bf16 plus a
+        zero eighth, i.e. exactly what a bf16 channels-last convolution wants (no cast, no padding pass, 42 % fewer
+        bytes); features stay float32."""
         s = self.sizes
         E, cap, v = self.n_envs, s["capacity"], s["view_size"]
+        bf16 = dtype == torch.bfloat16
+        assert bf16 or dtype == torch.float32
         out, ptrs = [], []
         for g in (0, 1):
             if g in groups:
-                view = self._buf("view_g%d" % g, (E, cap, v, v, s["n_channel"]), torch.float32)
+                view = self._buf("view%s_g%d" % ("16" if bf16 else "", g), (E, cap, v, v, 8 if bf16 else s["n_channel"]), dtype)
                 feat = self._buf("feat_g%d" % g, (E, cap, s["feature_size"]), torch.float32)
                 out.append((view, feat)); ptrs += [_ptr(view), _ptr(feat)]
             else:
                 out.append(None); ptrs += [None, None]
         with torch.cuda.device(self.device):
-            check(self.lib.mfb_observe_groups(self._h, *ptrs, _stream()))
+            fn = self.lib.mfb_observe_groups_bf16 if bf16 else self.lib.mfb_observe_groups
+            check(fn(self._h, *ptrs, _stream()))
         return out
 
     def device_state(self, key):

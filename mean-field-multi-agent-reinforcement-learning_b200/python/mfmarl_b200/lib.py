@@ -12,7 +12,8 @@ class MfbConfig(ctypes.Structure):
         ("capacity", ctypes.c_int), ("embedding_size", ctypes.c_int), ("rng_mode", ctypes.c_int),
         ("seed", ctypes.c_uint), ("env_base", ctypes.c_int), ("max_steps", ctypes.c_int),
         ("auto_reset", ctypes.c_int), ("device", ctypes.c_int), ("step_threads", ctypes.c_int),
-        ("obs_tile_agents", ctypes.c_int), ("obs_record", ctypes.c_int), ("random_sides", ctypes.c_int),
+        ("obs_tile_agents", ctypes.c_int), ("obs_record", ctypes.c_int), ("concurrent_step_envs", ctypes.c_int),
+        ("random_sides", ctypes.c_int),
         ("hp", ctypes.c_float), ("speed", ctypes.c_float), ("view_radius", ctypes.c_float),
         ("attack_radius", ctypes.c_float), ("damage", ctypes.c_float), ("step_recover", ctypes.c_float),
         ("kill_supply", ctypes.c_float), ("step_reward", ctypes.c_float), ("kill_reward", ctypes.c_float),
@@ -46,6 +47,7 @@ def load_library(path=None):
         "mfb_query": [vp, cp, ctypes.POINTER(ci)],
         "mfb_observe": [vp, vp, vp, ci, vp],
         "mfb_observe_groups": [vp, vp, vp, vp, vp, vp],
+        "mfb_observe_groups_bf16": [vp, vp, vp, vp, vp, vp],
         "mfb_state_device_ptr": [vp, cp, ctypes.POINTER(vp)],
         "mfb_step": [vp, vp, vp, vp, vp, vp, vp, ci, vp],
         "mfb_clear_dead": [vp, vp],

@@ -101,7 +101,7 @@ def battle(env, n_round, map_size, max_steps, handles, models, print_every, eps=
 # batched, device-resident form
 # ----------------------------------------------------------------------------------------------------------
 def play_batched(env, n_round, max_steps, models, eps=1.0, train=False, print_every=0, left_group=None,
-                 positions=None):
+                 positions=None, obs_dtype=None):
     """E episodes in lockstep on a `BatchedGridWorld` (one per environment), everything on the device.
 
     Per environment this is the loop of `play`: observe both groups -> models[g].act on the group's rows (with the
@@ -109,6 +109,10 @@ def play_batched(env, n_round, max_steps, models, eps=1.0, train=False, print_ev
     clear_dead in one launch) -> statistics.  An environment stops contributing once it is done; the round ends when
     all are done or after max_steps.  With train=True the main model's transitions (group 0 rows of the active
     environments) go to its device replay buffer via `flush_buffer_batched`, and `train()` runs once at the end.
+
+    obs_dtype=torch.bfloat16: the policies act on the engine's bf16 NHWC-8 observation rows (no cast, no padding pass,
+    bf16 tensor cores; see algo.base.bf16_rollout_copy); the fp32 rows are still produced for the replay buffer when
+    train=True.
 
     Returns (max_nums [E, 2], nums [E, 2], mean_rewards [E, 2], total_rewards [E, 2]) as numpy arrays.
     """
@@ -135,12 +139,16 @@ def play_batched(env, n_round, max_steps, models, eps=1.0, train=False, print_ev
     actions = torch.zeros((E, 2, cap), dtype=torch.int32, device=dev)
     step_ct = 0
     while step_ct < max_steps and bool(active.any()):
-        obs = env.observe_groups()                         # per group: view [E, cap, 13, 13, 7], feature [E, cap, 34]
+        if obs_dtype is not None and obs_dtype != torch.float32:
+            act_obs = env.observe_groups(dtype=obs_dtype)  # bf16 [E, cap, 13, 13, 8] rows for the policies
+            obs = env.observe_groups(groups=(0,)) if train else act_obs
+        else:
+            obs = act_obs = env.observe_groups()           # per group: view [E, cap, 13, 13, 7], feature [E, cap, 34]
         num.copy_(live_num)
         ids = live_id.clone()                              # rows of this step, before clear_dead compacts them
         valid = (slot[None, None, :] < num[:, :, None]) & active[:, None, None]          # [E, 2, cap]
         for g in range(2):
-            view, feat = obs[g]
+            view, feat = act_obs[g]
             prob = former[:, g, None, :].expand(E, cap, n_action).reshape(E * cap, n_action)
             a = models[g].act(state=[view.view((E * cap,) + tuple(view.shape[2:])), feat.view(E * cap, -1)],
                               prob=prob, eps=eps)

@@ -174,3 +174,35 @@ def test_runner_trains_one_round_and_saves(algo, tmp_path):
     tools.soft_copy(models[1].vars, models[0].vars, 0.01)
     for a, b, c in zip(models[1].vars, l, r):
         np.testing.assert_allclose(a.detach().numpy(), (0.99 * b + 0.01 * c).numpy(), rtol=1e-6, atol=1e-8)
+
+
+@pytest.mark.parametrize("algo", ["mfq", "il", "mfac", "ac"])
+def test_bf16_rollout_twins_take_the_engines_bf16_rows(algo):
+    """The bf16 twins (base.bf16_rollout_copy, ACNet.bf16_rollout_copy) consume [N, 13, 13, 8] bf16 rows -- the seven
+    observation channels plus a zero eighth -- and compute what the fp32 network computes, to bf16 accuracy: the extra
+    channel has zero weights, so it is the same function."""
+    from mfmarl_b200.algo import spawn_ai
+    torch.manual_seed(3)
+    m = spawn_ai(algo, FakeEnv(), 0, algo + "-x", 400, device="cpu")
+    view, feat, prob = _batch(64, 4)
+    view8 = np.zeros((64, 13, 13, 8), np.float32)
+    view8[..., :7] = view
+    v16, f32, p32 = torch.from_numpy(view8).to(torch.bfloat16), torch.from_numpy(feat), torch.from_numpy(prob)
+    if algo in ("mfq", "il"):
+        from mfmarl_b200.algo.base import bf16_rollout_copy
+        twin = bf16_rollout_copy(m.eval_net)
+        with torch.no_grad():
+            want = m.eval_net(torch.from_numpy(view), f32, p32 if algo == "mfq" else None)
+            got = twin(v16, f32.to(torch.bfloat16), p32.to(torch.bfloat16) if algo == "mfq" else None).float()
+        assert got.shape == want.shape and float((got - want).abs().max()) < 0.05 * max(1.0, float(want.abs().max()))
+        acts = m.act(state=[v16, f32], prob=p32, eps=1.0)
+        assert acts.dtype == torch.int32 and tuple(acts.shape) == (64,)
+        assert float((acts == got.argmax(1).to(torch.int32)).float().mean()) == 1.0
+    else:
+        twin = m.net.bf16_rollout_copy(m.view_space)
+        with torch.no_grad():
+            want = m.net.policy(torch.from_numpy(view), f32)
+            got = twin.policy(v16, f32.to(torch.bfloat16)).float()
+        assert float((got - want).abs().max()) < 0.1
+        acts = m.act(state=[v16, f32], prob=p32)
+        assert acts.dtype == torch.int32 and int(acts.min()) >= 0 and int(acts.max()) < 21

@@ -495,3 +495,51 @@ def test_random_sides_at_auto_reset():
     full = run(E, 0)
     assert 0.3 < full.mean() < 0.7 and len({tuple(r) for r in full}) > 1
     assert np.array_equal(run(16, 32), full[:, 32:48])
+
+
+@pytest.mark.parametrize("map_size,cap,E", [(40, 64, 5), (80, 512, 2)])
+def test_bf16_observation_rows_are_the_fp32_rows_rounded(map_size, cap, E):
+    """mfb_observe_groups_bf16: [E, cap, 13, 13, 8] bf16 rows = the fp32 observation rounded to nearest-even bf16 with a
+    zero eighth channel -- bit for bit, mid-fight (dead agents gone, hp fractions, minimap fractions, self markers), for
+    both set-up modes of k_obs (rebuild at cap 64, observation record at cap 512)."""
+    pos = generate_map_positions(40) if map_size == 40 else c4_positions()
+    env, oracles = make(E, map_size=map_size, cap=cap, pos=pos)
+    lockstep_batched(env, oracles, steps=12, seed=3, stream="fight", check_obs_every=0)
+    for rnd in range(3):
+        num = env.get_num()
+        f32 = env.observe_groups()
+        b16 = env.observe_groups(dtype=torch.bfloat16)
+        for g in range(2):
+            view32, feat32 = f32[g]
+            view16, feat16 = b16[g]
+            assert view16.dtype == torch.bfloat16 and tuple(view16.shape) == (E, cap, 13, 13, 8)
+            for e in range(E):
+                n = int(num[e, g])
+                want = torch.zeros((n, 13, 13, 8), dtype=torch.bfloat16, device=view32.device)
+                want[..., :7] = view32[e, :n].to(torch.bfloat16)
+                assert torch.equal(view16[e, :n].view(torch.int16), want.view(torch.int16)), (rnd, g, e)
+                assert torch.equal(feat16[e, :n], feat32[e, :n])
+                ov, _ = oracles[e].get_observation(g)              # and the fp32 rows are the oracle's
+                assert np.array_equal(ov.view(np.uint32), view32[e, :n].cpu().numpy().view(np.uint32))
+        lockstep_batched(env, oracles, steps=4, seed=10 + rnd, stream="fight", check_obs_every=0)
+
+
+def test_observe_leaves_slots_for_a_pipelined_sibling_and_gives_the_same_rows():
+    """concurrent_step_envs only changes how many persistent k_obs CTAs are launched (room for the sibling engine's
+    k_step on another stream); the observations are the same."""
+    from mfmarl_b200 import BatchedGridWorld
+    left, right = c4_positions()
+    envs = []
+    for reserve in (0, 4):
+        env = BatchedGridWorld(4, map_size=80, capacity=512, concurrent_step_envs=reserve)
+        env.reset(); env.add_agents(0, left); env.add_agents(1, right)
+        envs.append(env)
+    rng = np.random.RandomState(2)
+    for s in range(3):
+        acts = torch.from_numpy(rng.randint(0, 21, size=(4, 2, 512)).astype(np.int32)).cuda()
+        views = []
+        for env in envs:
+            v, f = env.observe()
+            views.append((v.clone(), f.clone()))
+            env.step(acts)
+        assert torch.equal(views[0][0], views[1][0]) and torch.equal(views[0][1], views[1][1])
