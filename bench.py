@@ -559,11 +559,11 @@ def measure_grad_allreduce(ctx, iters=20):
 def run_ours(args):
     ctx = Ctx()
     main = measure_battle(ctx, args, args.workload, args.steps, args.warmup, MIN_REGION_SECONDS,
-                          envs_per_gpu=args.envs, obs_tile=args.obs_tile or (128 if args.workload == "c4" else 0))
+                          envs_per_gpu=args.envs, obs_tile=args.obs_tile)
     also = {}
     if args.workload == "c3" and not args.no_also:
         # the other two named shapes under the same clock (BASELINE configs[3] and [4]): shorter legs, same rules
-        c4 = measure_battle(ctx, args, "c4", 200, max(3, min(args.warmup, 10)), 0.25, pipeline=2, obs_tile=128, extras=False)
+        c4 = measure_battle(ctx, args, "c4", 200, max(3, min(args.warmup, 10)), 0.25, pipeline=2, obs_tile=0, extras=False)
         c5 = measure_ising(ctx, args, min(max(args.steps, 100), 200), max(3, args.warmup), 0.25)
         if ctx.rank == 0:
             keep = ("metric", "value", "unit", "ms_per_step", "scaling", "config", "region_ms", "roofline", "e2e",

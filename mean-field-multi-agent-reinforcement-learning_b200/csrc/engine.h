@@ -44,7 +44,7 @@ struct AgentTypeParams {   // the attributes of AgentType.h:21-45 that reach the
 struct EngineConfig {
     int n_envs = 1, width = 40, height = 40, capacity = 64, embedding_size = 10;
     int rng_mode = RNG_MINSTD, max_steps = 0, env_base = 0, device = -1 /* current */;
-    int step_threads = 0 /* auto */, obs_tile_agents = 0 /* auto: clamp(cap, 64, 256); 32 with the observation record */;
+    int step_threads = 0 /* auto */, obs_tile_agents = 0 /* auto: clamp(cap, 64, 256); 64 with the observation record */;
     int concurrent_step_envs = 0 /* envs of a sibling engine whose k_step runs (on another stream) while this engine's
                                     k_obs streams: k_obs then leaves SM slots free for it where the two do not fit together */;
     int random_sides = 0 /* auto-reset draws per env and episode whether the armies swap their starting blocks */;
