@@ -35,4 +35,34 @@ cu.env.set_render_dir(tmp)
 for s in range(4):
     for g in range(2): cu.set_action(g, fight_actions(rng, cu.get_pos(g), 40))
     cu.step(); cu.env.render(); cu.clear_dead()
+# round 2: bf16 rows, observation record forced on at cap 64, per-env placement + random sides, large-map band order,
+# the Ising environment step, the persistent Ising kernel (default for 256 / 128) with and without act groups
+from scenarios import block_positions
+for cached in (0, 1):
+    env = BatchedGridWorld(3, map_size=40, capacity=64, rng="philox", auto_reset=True, max_steps=3, obs_record=cached,
+                           random_sides=True, concurrent_step_envs=3)
+    env.reset()
+    env.add_agents_per_env(0, np.stack([left[:, :2] + [0, e % 2] for e in range(3)]))
+    env.add_agents(1, right)
+    for s in range(5):
+        env.observe_groups(dtype=torch.bfloat16); env.observe()
+        env.step(torch.from_numpy(rng.randint(0, 21, size=(3, 2, 64)).astype(np.int32)).cuda())
+big = CudaEngine(104); big.reset()
+big.add_agents(0, block_positions(20, 30, 20, 10, stride=1)); big.add_agents(1, block_positions(54, 30, 20, 10, stride=1))
+for s in range(4):
+    for g in range(2): big.get_observation(g)
+    for g in range(2): big.set_action(g, fight_actions(rng, big.get_pos(g), 104))
+    big.step(); big.get_observation(0); big.clear_dead()          # (an observation before clear_dead: the rollback path)
+os.environ.pop("MFMARL_ISING_RPT", None)
+for L in (128, 256):
+    m = IsingMFQ(3, L)
+    m.run([0.8] * 4, resident=True)
+    masks = (torch.rand((4, 3, L * L), device="cuda") < 0.5).to(torch.uint8).contiguous()
+    m.run([0.8] * 4, resident=True, update_mask=masks)
+import ctypes
+from mfmarl_b200.lib import load_library
+lib = load_library(); lib.mfi_env_step.argtypes = [ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 6
+sp = torch.randint(0, 2, (2, 33 * 33), dtype=torch.int8, device="cuda"); ac = torch.randint(-1, 2, (2, 33 * 33), dtype=torch.int32, device="cuda")
+ob = torch.zeros((2, 33 * 33, 4), dtype=torch.uint8, device="cuda"); rw = torch.zeros((2, 33 * 33), device="cuda"); nu = torch.zeros((2,), dtype=torch.int32, device="cuda")
+lib.mfi_env_step(2, 33, sp.data_ptr(), ac.data_ptr(), ob.data_ptr(), rw.data_ptr(), nu.data_ptr(), None)
 torch.cuda.synchronize(); print("sanitize case done")
