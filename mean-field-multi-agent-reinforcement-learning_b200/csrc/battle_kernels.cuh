@@ -190,8 +190,7 @@ __host__ __device__ inline StepSmem step_smem_layout(int W, int H, int cap, int 
     return L;
 }
 
-enum { MISC_WARP = 0, MISC_N = 32, MISC_DEAD = 34, MISC_NA = 36, MISC_NM = 37, MISC_DONE = 38, MISC_RESET = 39,
-       MISC_FLAG = 40, MISC_NENT = 41, MISC_HIST = 64 };
+enum { MISC_WARP = 0, MISC_N = 32, MISC_DEAD = 34, MISC_FLAG = 40, MISC_HIST = 64 };   // ints in s_misc
 
 // mover results while the move phase runs
 enum : int { MV_FAIL = 0, MV_OK = 1, MV_WAIT = 2 };
@@ -693,7 +692,7 @@ constexpr int kViewRowBf16Bytes = kViewCells * 16;
 constexpr int kObsPasses = (kViewCells + 31) / 32;             // 6
 static_assert(kObsChunk == kObsWarps, "one warp composes one row of a chunk");
 
-struct ObsSmem { int stage0, stage1, rec, hp10, mini, cnt, code, fxy, tmpl, record, bar, total; };
+struct ObsSmem { int stage0, stage1, rec, hp10, mini, cnt, code, fxy, tmpl, record, total; };
 constexpr int kObsMaxTile = kObsThreads;   // agents per CTA tile, upper bound (one record per thread)
 // The pristine wall template is kept in shared memory when two CTAs per SM still fit with it (40x40: +5.4 KB);
 // larger maps copy it from global memory (L2) per item instead.
@@ -704,7 +703,7 @@ __host__ __device__ inline ObsSmem obs_smem_layout(int W, int H, int cap, int ca
     L.stage0 = o; o += stage_bytes;
     L.stage1 = o; o += stage_bytes;
     L.rec = o;    o += 16 * kObsMaxTile;                              // (pos, id, state, last_rew) of the tile's agents
-    L.record = L.bar = L.cnt = L.tmpl = 0;
+    L.record = L.cnt = L.tmpl = 0;
     if (cached) {                                                     // the env's observation record, as one bulk copy lands it
         const ObsRecord R = obs_record_layout(W, H, cap);
         L.record = o; L.code = o + R.grid; L.hp10 = o + R.hp10; L.mini = o + R.mini; o += R.total;   // (16-byte pieces)
