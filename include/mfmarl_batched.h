@@ -154,10 +154,13 @@ int mfi_step(int dtype, int n_lattices, int side, int8_t *d_spins, void *d_q, do
              const void *d_uniforms, const uint8_t *d_update_mask, unsigned seed, unsigned lattice_base,
              unsigned step, int32_t *d_n_up, void *d_reward_sum, void *d_mse, void *stream);
 
-/* K6r: `n_sweeps` sweeps in ONE launch with the Q table resident in shared memory (a lattice is split over a
- * thread-block cluster of mfi_resident_cluster_size() CTAs; 1 for side <= 64, 16 for side 256 in fp32).
- * Same semantics and the same Philox keys as n_sweeps calls of mfi_step with step = step0 .. step0+n_sweeps-1
- * (bit-identical results).  HBM traffic: the Q table is read and written once per launch.
+/* K6r / K6p: `n_sweeps` sweeps in ONE launch with the Q table resident in shared memory.  A lattice is split into
+ * mfi_resident_cluster_size() strips of rows, one CTA each (1 for side <= 64, 4 for 128, 16 for 256 in fp32).  For the
+ * fp32 shapes 128 and 256 the strips are ordinary CTAs of a persistent, cooperatively launched grid that fills the
+ * GPU (144 of 148 SMs at side 256) and exchange their halo rows through L2 (K6p); other shapes use a thread-block
+ * cluster per lattice (K6r; MFMARL_ISING_PERSIST=0 forces it).  Either way: same semantics and the same Philox keys as
+ * n_sweeps calls of mfi_step with step = step0 .. step0+n_sweeps-1 (bit-identical results); the Q table is read and
+ * written once per launch.
  *   d_temperatures  T    [n_sweeps]                          in (the schedule of main_MFQ_Ising.py:108-112)
  *   d_uniforms      T    [n_sweeps][n_lattices][side*side]   or NULL (test hook)
  *   d_update_mask   uint8[n_sweeps][n_lattices][side*side]   or NULL: the act group of every sweep (act_rate < 1)

@@ -25,6 +25,9 @@ def battle_parser(description, training):
     if training:
         ap.add_argument("--envs", type=int, default=0,
                         help="lock-stepped environments on the GPU per round (0 = one environment via magent)")
+        ap.add_argument("--rollout_bf16", action="store_true",
+                        help="with --envs: the policies act on bf16 observation rows emitted by the engine (bf16 twins of "
+                             "the networks; training stays fp32 on the fp32 rows)")
     return ap
 
 

@@ -30,8 +30,8 @@ class BatchedEnvAdapter:
     """What Runner / spawn_ai ask of `env` (space queries) on top of a BatchedGridWorld, plus a `play` handle that
     reduces the per-environment statistics of play_batched to the scalars Runner logs (means over environments)."""
 
-    def __init__(self, benv):
-        self.benv = benv
+    def __init__(self, benv, rollout_bf16=False):
+        self.benv, self.rollout_bf16 = benv, rollout_bf16
 
     def get_view_space(self, handle):
         s = self.benv.sizes
@@ -45,11 +45,13 @@ class BatchedEnvAdapter:
 
     def play(self, env, n_round, map_size, max_steps, handles, models, print_every, eps=1.0, render=False, train=False):
         import numpy as np
+        import torch
         from mfmarl_b200.senario_battle import play_batched
         print("\n\n[*] ROUND #{0}, EPS: {1:.2f} ENVS: {2}".format(n_round, eps, self.benv.n_envs))
         # every rank places the armies the same way round (the draw of senario_battle.py:14 comes from the round number)
         max_nums, nums, mean_r, total_r = play_batched(self.benv, n_round, max_steps, models, eps=eps, train=train,
-                                                       print_every=print_every, left_group=n_round % 2)
+                                                       print_every=print_every, left_group=n_round % 2,
+                                                       obs_dtype=torch.bfloat16 if self.rollout_bf16 else None)
         stats = np.stack([max_nums.mean(axis=0), nums.mean(axis=0), mean_r.mean(axis=0), total_r.mean(axis=0)])
         stats = all_ranks_mean(stats, self.benv.device)     # one decision (self-play update, win count) on every rank
         return tuple(list(row) for row in stats)
@@ -101,7 +103,7 @@ def main(argv=None):
         cap = max(64, int(args.map_size * args.map_size * 0.04))
         benv = BatchedGridWorld(args.envs, map_size=args.map_size, capacity=cap, device=args.device, rng="philox",
                                 env_base=rank * args.envs)
-        env = BatchedEnvAdapter(benv)
+        env = BatchedEnvAdapter(benv, rollout_bf16=args.rollout_bf16)
         handles, play = [0, 1], env.play
     else:
         import magent
