@@ -131,6 +131,14 @@ def test_every_learner_trains_a_batched_round_on_the_gpu(algo):
     assert any(not torch.equal(a, b) for a, b in zip(before, models[0].vars))
     for p in models[0].vars:
         assert torch.isfinite(p).all()
+    # the same round with the policies acting on the engine's bf16 observation rows (bf16 twins, refreshed after the
+    # update above); the replay still receives the fp32 rows
+    before = [p.detach().clone() for p in models[0].vars]
+    max_nums, nums, mean_r, total_r = play_batched(env, 1, steps, models, eps=1.0, train=True, left_group=1,
+                                                   obs_dtype=torch.bfloat16)
+    assert (max_nums == 64).all() and np.isfinite(mean_r).all() and np.isfinite(total_r).all()
+    assert any(not torch.equal(a, b) for a, b in zip(before, models[0].vars))
+    assert models[0]._rollout16 is not None and models[0]._rollout16_stale
 
 
 def test_train_battle_and_battle_scripts_end_to_end(tmp_path):
