@@ -365,6 +365,25 @@ def measure_battle(ctx, args, workload, K, W, min_seconds, envs_per_gpu=0, pipel
     obs_ms = sum(e[0].elapsed_time(e[1]) for evh in ev for e in evh) / (K * P)     # per k_obs launch
     step_ms = sum(e[1].elapsed_time(e[2]) for evh in ev for e in evh) / (K * P)    # per k_step launch
 
+    # ---- the same region on FRESH episodes (armies at full strength), as round 1 measured it: reset, W warm-up steps,
+    #      K timed steps, five times.  The regions above run on into the steady state of the 400-step episodes, where
+    #      uniform random actions have killed ~8 % of the agents and the per-step fixed costs weigh a little more. ----
+    fresh = None
+    if extras:
+        f_ms, f_work = [], []
+        for _ in range(5):
+            for env in envs:
+                env.reset(); env.add_agents(0, left); env.add_agents(1, right)
+            for k in range(W):
+                for h, env in enumerate(envs):
+                    one_step(h, env, k)
+            m, w_, _e = timed_region(False)
+            f_ms.append(m); f_work.append(w_)
+        fm, fw, fregions = pick_median(ctx, f_ms, f_work)
+        fresh = {"value": fw / (fm * 1e-3), "unit": "agent-steps/s", "ms_per_step": fm / K, "region_ms": fregions,
+                 "agents_per_step": fw / K,
+                 "note": "steps %d..%d of fresh episodes (all %d agents of an env alive), the phase round 1 reported" % (W, W + K, 2 * cap)}
+
     # ---- attribution: with P > 1 the two kernels of different engines overlap, so the event pairs above contain
     #      the time a kernel shared the GPU with the other one.  A short extra run with the launches back to back on
     #      ONE stream gives each kernel's duration alone (what the ncu launch list also shows). ----
@@ -490,6 +509,8 @@ def measure_battle(ctx, args, workload, K, W, min_seconds, envs_per_gpu=0, pipel
                    "timed_region": "exactly %d steps, repeated %d times (>= %.2f s of device time); the repeat with the "
                                    "median time is reported" % (K, regions["repeats"], min_seconds)},
         "region_ms": regions,
+        "agents_per_step": agent_steps_all / K,
+        "fresh_episodes": fresh,
         "gpu_launches": 2 * K * P,
         "kernels_ms": {"k_obs": obs_ms, "k_step": step_ms,
                        "note": "event pairs on the launching streams inside the first timed region" +
