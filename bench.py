@@ -339,6 +339,7 @@ def measure_battle(ctx, args, workload, K, W, min_seconds, envs_per_gpu=0, pipel
         ev = [[[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)] for _ in range(P)] if with_events else None
         t0 = torch.cuda.Event(enable_timing=True)
         t1 = [torch.cuda.Event(enable_timing=True) for _ in range(P)]
+        ctx.barrier()                              # (everything launched so far has run: the counter below is exact)
         a0 = agent_steps_total()
         ctx.barrier()
         t0.record()
@@ -423,6 +424,7 @@ def measure_battle(ctx, args, workload, K, W, min_seconds, envs_per_gpu=0, pipel
     checksum = [0.0]
 
     def e2e_region():
+        ctx.barrier()
         a0 = agent_steps_total()
         ctx.barrier()
         e0 = torch.cuda.Event(enable_timing=True)
