@@ -543,3 +543,59 @@ def test_observe_leaves_slots_for_a_pipelined_sibling_and_gives_the_same_rows():
             views.append((v.clone(), f.clone()))
             env.step(acts)
         assert torch.equal(views[0][0], views[1][0]) and torch.equal(views[0][1], views[1][1])
+
+
+@pytest.mark.parametrize("map_size,cap", [(40, 64), (80, 512)])
+def test_convoys_and_focused_fire_resolve_like_the_ordered_loops(map_size, cap):
+    """Worst cases for k_step's parallel formulations: packed blocks (stride 1) in which EVERYBODY makes the same move,
+    so that almost every mover's target is held by another mover whose own fate decides (long chains for the pointer
+    jumping, first-come-first-served ties on every freed cell), alternating with steps in which everybody attacks the
+    same way (many attacks per victim, attackers that are victims: the entangled path), and a few random steps."""
+    from scenarios import block_positions
+    n_side = int(np.sqrt(cap))
+    rows = cap // n_side
+    left = block_positions(2, 3, n_side, rows, stride=1)
+    right = block_positions(2 + n_side, 3, n_side, rows, stride=1)        # the two armies touch
+    env, oracles = make(2, map_size=map_size, cap=cap, pos=(left, right))
+    E = 2
+    rng = np.random.RandomState(map_size)
+    plan = [7, 7, 10, 5, 16, 17, 2, 8, 4, 14, 19, 7, 11, 1, 16, 6, 12, 0]        # moves (0-12) and attacks (13-20), see SURVEY 8
+    deaths = 0
+    for s in range(3 * len(plan)):
+        num = env.get_num()
+        pos = env.get("pos")
+        actions = np.zeros((E, 2, cap), np.int32)
+        for e, o in enumerate(oracles):
+            for g in range(2):
+                n = num[e, g]
+                assert o.get_num(g) == n
+                assert_same("pos", o.get_pos(g), pos[e, g, :n], s)
+                a = np.full(n, plan[s % len(plan)], np.int32)
+                if s % 5 == 4:
+                    a = uniform_actions(rng, n)
+                elif e == 1:                       # env 1: the two groups do different things
+                    a[:] = plan[(s + 3 * g) % len(plan)]
+                actions[e, g, :n] = a
+                o.set_action(g, a)
+        reward, alive, done, mean = env.step(torch.from_numpy(actions).cuda())
+        reward, alive = reward.cpu().numpy(), alive.cpu().numpy()
+        for e, o in enumerate(oracles):
+            o.step()
+            for g in range(2):
+                n = num[e, g]
+                assert_same("reward", o.get_reward(g), reward[e, g, :n], s)
+                al = o.get_alive(g)
+                assert_same("alive", al, alive[e, g, :n].astype(bool), s)
+                deaths += int((~al).sum())
+            o.clear_dead()
+        if s % 6 == 0:
+            view, feat = env.observe()
+            view = view.cpu().numpy()
+            num2 = env.get_num()
+            for e, o in enumerate(oracles):
+                for g in range(2):
+                    v, f = o.get_observation(g)
+                    assert_same("view", v, view[e, g, :num2[e, g]], s)
+        if (env.get_num() == 0).any():
+            break
+    assert deaths > 0, deaths
