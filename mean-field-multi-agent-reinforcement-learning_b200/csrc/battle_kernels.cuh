@@ -299,6 +299,8 @@ __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState
             // the draws, all at once: Philox is counter based; the reference's minstd_rand0 chain is jumped ahead
             // (state after i+1 steps = state * 16807^(i+1))
             const uint32_t rs0 = P.rng_mode == RNG_MINSTD ? S.rng[e] : 0u;
+            uint32_t rs_end = 0;                       // the engine's state after the last draw (held by the thread that made it)
+            bool made_last_draw = false;
             for (int i = tid; i < nA; i += nt) {
                 if (P.rng_mode == RNG_PHILOX) {
                     const uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)step_before, 0u, 0u),
@@ -307,11 +309,12 @@ __global__ void k_step(const __grid_constant__ BattleParams P, const BattleState
                 } else {
                     const uint32_t rs = minstd_jump(rs0, (uint32_t)(i + 1));
                     s_aux[i] = (int)rs % (i + 1);
-                    if (i == nA - 1) S.rng[e] = rs;
+                    if (i == nA - 1) { rs_end = rs; made_last_draw = true; }
                 }
                 s_scr0[i] = -1;
             }
             __syncthreads();
+            if (made_last_draw) S.rng[e] = rs_end;     // (after the barrier: every thread has read the old state by now)
             // No swap is executed.  Position i still holds element i when step i runs, so the content of position q
             // after all steps < t is: element i* if i* is the LAST step in (q, t) that swapped into q (j_i* = q);
             // otherwise what position j_q held after the steps < q (step q itself moved it in).  Every final position
@@ -749,7 +752,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {     // rou
 }
 
 template <bool CACHED, bool BF16>
-__global__ void __launch_bounds__(kObsThreads, kObsCtasPerSm)
+__global__ void __launch_bounds__(kObsThreads, BF16 ? kObsCtasPerSm + 1 : kObsCtasPerSm)   // bf16 rows: smaller staging, 3 CTAs fit
 k_obs(const __grid_constant__ BattleParams P, const BattleState S, const ObsIO io) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const ObsSmem L = obs_smem_layout(P.W, P.H, P.cap, CACHED, BF16);
