@@ -967,6 +967,266 @@ __global__ void __launch_bounds__(L * (ROWS / RPT), 1) k_ising_persist_f32(const
     }
 }
 
+// ---- K6s: K6p with the per-site integer work done for a thread's RPT rows AT ONCE (SWAR) -------------------------
+// ncu on K6p v5: 69 thread instructions per site-step, 9 % of them branches, 8 ballots + 16 word loads + 16 funnel
+// shifts per thread per sweep only to count neighbours.  Here a thread keeps its RPT <= 8 spins as ONE word of 4-bit
+// fields (field i = slot i), so
+//   * the left / right neighbours of all its rows arrive with two warp shuffles (lanes 0 and 31 take the word the
+//     neighbouring warp's edge lane left in shared memory),
+//   * up / down are the word shifted by one field,
+//   * the neighbour counts of all rows are three SWAR additions (a field never exceeds 4),
+//   * the per-sweep statistics are a popcount and two horizontal field sums,
+//   * the reward as a float is (2^23 + count) reinterpreted, minus (2^23 + 2): no integer-to-float conversion,
+//   * only the two rows other threads' columns look at from above / below are still published as ballot words.
+// Shape: exactly two bands per strip (ROWS == 2 RPT).  The lower band holds its rows in REVERSE order (slot i = local
+// row ROWS-1-i, in registers and in the shared-memory Q strip), which makes the two bands mirror images: slot 0 is
+// always the strip's boundary row (the one that needs the halo word and feeds the neighbouring strip), slot RPT-1
+// always the row facing the other band, and the neighbour sum is symmetric in up / down -- one code path, no
+// per-row "is this the boundary row" branches.  The sweep loop is peeled (first sweep: nothing to finish; after the
+// last: nothing to draw).  Same Philox keys, same float operations in the same order as K6 / K6r / K6p: same bits.
+template <int I0, int I1, class F> __device__ __forceinline__ void static_for(F &&f) {
+    if constexpr (I0 < I1) { f(std::integral_constant<int, I0>{}); static_for<I0 + 1, I1>(f); }
+}
+template <uint32_t OFF> __device__ __forceinline__ float2 lds_f32x2_at(uint32_t a) {
+    float2 v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(v.x), "=f"(v.y) : "r"(a), "n"(OFF) : "memory"); return v;
+}
+template <uint32_t OFF> __device__ __forceinline__ void sts_f32_at(uint32_t a, float v) {
+    asm volatile("st.shared.f32 [%0+%1], %2;" :: "r"(a), "n"(OFF), "f"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t field_sum(uint32_t x) {            // sum of the eight 4-bit fields (each <= 15)
+    return (((x & 0x0F0F0F0Fu) + ((x >> 4) & 0x0F0F0F0Fu)) * 0x01010101u) >> 24;
+}
+
+template <int L, int RPT, bool MASK>
+__global__ void __launch_bounds__(2 * L, 1) k_ising_persist_swar_f32(const IsingRunArgs<float> A, const int n_slots,
+                                                                     unsigned long long *const halo) {
+    static_assert(L % 32 == 0 && RPT % kIsingRB == 0 && RPT <= 8 && L % (2 * RPT) == 0, "shape");
+    static_assert(((uint64_t)0x4B000000u * ((uint64_t)2 * RPT * L * 8)) % (1ull << 32) == 0, "plane stride must clear the float exponent bits");
+    constexpr int ROWS = 2 * RPT, N = L * L, WPR = L / 32, STRIP = ROWS * L, NT = 2 * L, C = L / ROWS;
+    constexpr int NPH = RPT / kIsingRB;
+    constexpr uint32_t PLANE = (uint32_t)STRIP * 8u;            // bytes between the Q planes of consecutive s
+    constexpr uint32_t ROWB = (uint32_t)L * 8u;                 // bytes between consecutive rows of a plane
+    constexpr uint32_t TOP = 4u * (RPT - 1);                    // bit position of the last slot's field
+    constexpr uint32_t FIELDS = RPT == 8 ? 0xFFFFFFFFu : ((1u << (4 * RPT)) - 1u);
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const int slot = blockIdx.x / C, rank = blockIdx.x % C, row0 = rank * ROWS;
+    float *s_q = (float *)s_raw;                                                    // [5][ROWS (lower band reversed)][L][2]
+    uint32_t *s_inner = (uint32_t *)(s_raw + (size_t)5 * STRIP * 8);                // [2 parity][2 band][WPR]: slot RPT-1 ballots
+    uint32_t *s_edge = s_inner + 2 * 2 * WPR;                                       // [2 parity][2 band][WPR][2]: lane 0 / 31 field words
+    int *s_stat = (int *)(s_edge + 2 * 2 * WPR * 2);                                // [2] packed statistics per sweep parity
+    float *s_tparam = (float *)(s_stat + 4);                                        // [K]
+    constexpr uint32_t INNER_BUF = 2u * WPR * 4u, EDGE_BUF = 2u * WPR * 2u * 4u;
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int x = tid % L, band = tid / L, w = x >> 5;
+    const bool upper = band == 0;
+    const int wl = w == 0 ? WPR - 1 : w - 1, wr = w == WPR - 1 ? 0 : w + 1;
+    const int up_rank = (rank + C - 1) % C, dn_rank = (rank + 1) % C;
+    auto local_row = [&](int i) { return upper ? i : ROWS - 1 - i; };               // slot -> row of the strip
+    const uint32_t q_site0 = smem_addr(s_q) + (uint32_t)(band * RPT * L + x) * 8u;  // Q pair of (s = 0, slot 0, column x)
+    const uint32_t inner_out = smem_addr(s_inner) + (uint32_t)(band * WPR + w) * 4u;
+    const uint32_t inner_in = smem_addr(s_inner) + (uint32_t)((band ^ 1) * WPR + w) * 4u;
+    const uint32_t edge_out = smem_addr(s_edge) + (uint32_t)(((band * WPR + w) * 2 + (lane == 31 ? 1 : 0))) * 4u;
+    const uint32_t edge_in = smem_addr(s_edge) +
+        (uint32_t)(lane == 0 ? (band * WPR + wl) * 2 + 1 : lane == 31 ? (band * WPR + wr) * 2 : (band * WPR + w) * 2) * 4u;
+    const bool edge_lane = lane == 0 || lane == 31;
+    // halo mailboxes in L2 as in K6p: [slot][rank][parity][top | bottom][WPR]
+    constexpr size_t MB_PARITY = 2 * WPR;
+    const unsigned long long *const mb_in = halo + (((size_t)slot * C + rank) * 2 * 2 + (upper ? 0 : 1)) * WPR + w;
+    unsigned long long *const mb_out = halo + (((size_t)slot * C + (upper ? up_rank : dn_rank)) * 2 * 2 + (upper ? 1 : 0)) * WPR + w;
+
+    for (int i = threadIdx.x; i < A.K; i += NT) s_tparam[i] = temperature_param(A.temperatures[i]);
+    uint32_t state_no = 0;
+    for (int b = slot; b < A.B; b += n_slots, state_no += (uint32_t)A.K + 1u) {
+        const size_t lbase = (size_t)b * N;
+        __syncthreads();                                        // the previous lattice's Q strip has been stored
+        if (tid < 2) s_stat[tid] = 0;
+        for (int sp = 0; sp < 5; sp++) {
+            const float4 *s4 = (const float4 *)(A.Q + (lbase * 5 + (size_t)sp * N + (size_t)row0 * L) * 2);
+            float4 *d4 = (float4 *)(s_q + (size_t)sp * STRIP * 2);
+#pragma unroll 4
+            for (int i = tid; i < STRIP / 2; i += NT) {
+                const int sr = i / (L / 2), c4 = i % (L / 2);
+                d4[i] = s4[(sr < RPT ? sr : ROWS - 1 - sr + RPT) * (L / 2) + c4];
+            }
+        }
+        uint32_t own = 0;                                       // this thread's spins of the current state, 4 bits per slot
+        float sgn[RPT];                                         // the same spins as sigma = +-1
+        unsigned long long hv = 0;
+        {
+            const uint32_t par = state_no & 1u, seq = state_no + 1u;
+            int a0 = 0, aN = 0;
+#pragma unroll
+            for (int i = 0; i < RPT; i++) {
+                const int a = (int)A.spins[lbase + (size_t)(row0 + local_row(i)) * L + x] != 0;
+                own |= (uint32_t)a << (4 * i);
+                sgn[i] = a ? 1.0f : -1.0f;
+                if (i == 0) a0 = a;
+                if (i == RPT - 1) aN = a;
+            }
+            const uint32_t w0 = __ballot_sync(0xFFFFFFFFu, a0 != 0), wN = __ballot_sync(0xFFFFFFFFu, aN != 0);
+            if (lane == 0) {
+                sts_u32(inner_out + par * INNER_BUF, wN);
+                st_halo(mb_out + par * MB_PARITY, w0, seq);
+            }
+            if (edge_lane) sts_u32(edge_out + par * EDGE_BUF, own);
+            hv = ld_halo(mb_in + par * MB_PARITY);
+        }
+        const uint2 key = make_uint2(A.seed, A.lattice_base + (uint32_t)b);
+        const uint32_t gband = (uint32_t)((row0 + band * RPT) >> 2);
+        float uu[RPT];                                          // uniforms * 2^32, by slot
+        auto draw_uniforms = [&](uint32_t step) {
+            uint4 rnd[NPH];
+#pragma unroll
+            for (int h = 0; h < NPH; h++) rnd[h] = philox4x32_10(make_uint4((uint32_t)x, gband + (uint32_t)h, step, 0u), key);
+            if (upper) {                                        // component c of call h belongs to row 4h + c of the band
+#pragma unroll
+                for (int h = 0; h < NPH; h++) {
+                    uu[4 * h + 0] = __uint2float_rz(rnd[h].x); uu[4 * h + 1] = __uint2float_rz(rnd[h].y);
+                    uu[4 * h + 2] = __uint2float_rz(rnd[h].z); uu[4 * h + 3] = __uint2float_rz(rnd[h].w);
+                }
+            } else {                                            // ... which is slot RPT-1 - (4h + c) of the lower band
+#pragma unroll
+                for (int h = 0; h < NPH; h++) {
+                    uu[RPT - 1 - (4 * h + 0)] = __uint2float_rz(rnd[h].x); uu[RPT - 1 - (4 * h + 1)] = __uint2float_rz(rnd[h].y);
+                    uu[RPT - 1 - (4 * h + 2)] = __uint2float_rz(rnd[h].z); uu[RPT - 1 - (4 * h + 3)] = __uint2float_rz(rnd[h].w);
+                }
+            }
+        };
+        if (A.u == nullptr) draw_uniforms(A.step0);
+        float keep_q[RPT]; uint32_t keep_addr[RPT];
+#pragma unroll
+        for (int i = 0; i < RPT; i++) { keep_q[i] = 0.0f; keep_addr[i] = q_site0; }
+
+        // one pass of the loop: finish sweep k-1 on state k (FIN), draw sweep k (DRAW).  Interior slots first, the
+        // boundary slot 0 last (its halo word travels through L2 meanwhile), as in K6p.
+        auto sweep = [&](auto fin_c, auto draw_c, const int k) {
+            constexpr bool FIN = decltype(fin_c)::value, DRAW = decltype(draw_c)::value;
+            const uint32_t par = (state_no + (uint32_t)k) & 1u, seq = state_no + (uint32_t)k + 1u;
+            __syncthreads();                              // the words of state k are in the buffers of parity `par`
+            if (tid == 0 && k >= 2) {                     // statistics of sweep k-2: all warps added before this barrier
+                const int pk = s_stat[k & 1];
+                s_stat[k & 1] = 0;
+                atomicAdd(&A.n_up[(size_t)(k - 2) * A.B + b], pk & 0xFFFF);
+                if (A.reward_sum) atomicAdd(&A.reward_sum[(size_t)(k - 2) * A.B + b], (float)((pk >> 16) - 2 * RPT * NT));
+            }
+            float tparam = 0.0f;
+            if (DRAW) {
+                tparam = s_tparam[k];
+                if (A.u != nullptr) {
+#pragma unroll
+                    for (int i = 0; i < RPT; i++)
+                        uu[i] = A.u[((size_t)k * A.B + b) * N + (size_t)(row0 + local_row(i)) * L + x] * 4294967296.0f;
+                }
+            }
+            uint32_t upd = 0xFFFFFFFFu;                                            // bit i: slot i updates Q (sweep k-1)
+            if (MASK && FIN) {
+                const uint8_t *m = A.mask + ((size_t)(k - 1) * A.B + b) * N + (size_t)row0 * L + x;
+                upd = 0;
+#pragma unroll
+                for (int i = 0; i < RPT; i++) upd |= (m[local_row(i) * L] ? 1u : 0u) << i;
+            }
+            // neighbour counts of state k for all slots at once (the boundary slot still lacks its halo neighbour)
+            uint32_t left = __shfl_up_sync(0xFFFFFFFFu, own, 1), right = __shfl_down_sync(0xFFFFFFFFu, own, 1);
+            const uint32_t e = lds_u32(edge_in + par * EDGE_BUF);
+            const uint32_t inner = lds_u32(inner_in + par * INNER_BUF);
+            if (lane == 0) left = e;
+            if (lane == 31) right = e;
+            uint32_t cnt = (own << 4) + (own >> 4) + left + right + (((inner >> lane) & 1u) << TOP);
+            uint32_t nxt_own = 0;
+            // the halo word of state k: asked for now, looked at after the interior slots
+            if ((uint32_t)(hv >> 32) != seq) hv = ld_halo(mb_in + par * MB_PARITY);
+
+            uint32_t qaddr[RPT];
+            auto finish = [&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                // g = 2^23 + ups as float bits.  g - (2^23 + 2) = (float)(ups - 2) exactly, and g * PLANE = ups * PLANE
+                // modulo 2^32 (0x4B000000 * PLANE is a multiple of 2^32): one word serves the reward and the address.
+                const uint32_t g = ((cnt >> (4 * i)) & 15u) | 0x4B000000u;
+                if constexpr (FIN) {
+                    const float t = __fmaf_rn(__uint_as_float(g) - 8388610.0f, sgn[i], -keep_q[i]);   // (2a-1)(ups-2) - q: one rounding
+                    if (!MASK || ((upd >> i) & 1u)) sts_f32_at<(uint32_t)i * ROWB>(keep_addr[i], keep_q[i] + A.lr * t);
+                }
+                asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(qaddr[i]) : "r"(g), "n"(PLANE), "r"(q_site0));
+            };
+            auto decide = [&](auto ic, const float2 q) {
+                constexpr int i = decltype(ic)::value;
+                const int a = draw_action_scaled(uu[i], q.x, q.y, tparam);
+                keep_q[i] = a ? q.y : q.x;
+                keep_addr[i] = qaddr[i] + (a ? 4u : 0u);                               // (+ i * ROWB in the store instruction)
+                sgn[i] = a ? 1.0f : -1.0f;
+                nxt_own |= a ? (1u << (4 * i)) : 0u;
+                return a;
+            };
+            // ---- interior slots 1 .. RPT-1 (staged: all finishes, all Q-pair loads, all decisions) ----
+            float2 pr[RPT];
+            int a_top = 0;
+            static_for<1, RPT>([&](auto ic) { finish(ic); });
+            if (DRAW) {
+                static_for<1, RPT>([&](auto ic) {
+                    constexpr int i = decltype(ic)::value;
+                    pr[i] = lds_f32x2_at<(uint32_t)i * ROWB>(qaddr[i]);
+                });
+                static_for<1, RPT>([&](auto ic) {
+                    constexpr int i = decltype(ic)::value;
+                    const int a = decide(ic, pr[i]);
+                    if (i == RPT - 1) a_top = a;
+                });
+            }
+            if (DRAW) {
+                const uint32_t wN = __ballot_sync(0xFFFFFFFFu, a_top != 0);         // slot RPT-1: the row the other band looks at
+                if (lane == 0) sts_u32(inner_out + (par ^ 1u) * INNER_BUF, wN);
+            }
+            // ---- the boundary slot 0: halo word of state k, count, finish, draw, its new word straight to the neighbour ----
+            while ((uint32_t)(hv >> 32) != seq) hv = ld_halo(mb_in + par * MB_PARITY);
+            cnt += ((uint32_t)hv >> lane) & 1u;
+            finish(std::integral_constant<int, 0>{});
+            if (DRAW) {
+                const float2 q = lds_f32x2_at<0>(qaddr[0]);
+                const int a = decide(std::integral_constant<int, 0>{}, q);
+                const uint32_t w0 = __ballot_sync(0xFFFFFFFFu, a != 0);
+                if (lane == 0) st_halo(mb_out + (par ^ 1u) * MB_PARITY, w0, seq + 1u);
+            }
+            if (FIN) {                                    // statistics of sweep k-1 from the complete counts of state k
+                const uint32_t n_up = (uint32_t)__popc(own);
+                const uint32_t s_all = field_sum(cnt & FIELDS), s_up = field_sum(cnt & (own * 15u));
+                // sum_i (2a-1)(ups-2) + 2 RPT  (>= 0), packed above the up count
+                int packed = (int)(n_up + ((2u * s_up - s_all - 4u * n_up + 4u * RPT) << 16));
+                packed = __reduce_add_sync(0xFFFFFFFFu, packed);
+                if (lane == 0) atomicAdd(&s_stat[(k - 1) & 1], packed);
+            }
+            if (DRAW) {
+                own = nxt_own;
+                if (edge_lane) sts_u32(edge_out + (par ^ 1u) * EDGE_BUF, own);
+            }
+        };
+        sweep(std::false_type{}, std::true_type{}, 0);
+        for (int k = 1; k < A.K; k++) {
+            if (A.u == nullptr) draw_uniforms(A.step0 + (uint32_t)k);
+            sweep(std::true_type{}, std::true_type{}, k);
+        }
+        sweep(std::true_type{}, std::false_type{}, A.K);
+        __syncthreads();
+        if (tid == 0) {
+            const int kk = A.K - 1, pk = s_stat[kk & 1];
+            atomicAdd(&A.n_up[(size_t)kk * A.B + b], pk & 0xFFFF);
+            if (A.reward_sum) atomicAdd(&A.reward_sum[(size_t)kk * A.B + b], (float)((pk >> 16) - 2 * RPT * NT));
+        }
+        for (int sp = 0; sp < 5; sp++) {
+            float4 *d4 = (float4 *)(A.Q + (lbase * 5 + (size_t)sp * N + (size_t)row0 * L) * 2);
+            const float4 *s4 = (const float4 *)(s_q + (size_t)sp * STRIP * 2);
+#pragma unroll 4
+            for (int i = tid; i < STRIP / 2; i += NT) {
+                const int sr = i / (L / 2), c4 = i % (L / 2);
+                d4[(sr < RPT ? sr : ROWS - 1 - sr + RPT) * (L / 2) + c4] = s4[i];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < RPT; i++)
+            A.spins[lbase + (size_t)(row0 + local_row(i)) * L + x] = (int8_t)((own >> (4 * i)) & 1u);
+    }
+}
+
 template <typename T>
 static size_t resident_smem_bytes(int L, int rows) {
     const int wpr = (L + 31) >> 5;
@@ -1020,6 +1280,11 @@ static bool launch_ising_persistent(const IsingRunArgs<float> &A, cudaStream_t s
     }
     MF_PICK(256, 16) MF_PICK(128, 32)
 #undef MF_PICK
+    // K6s (SWAR neighbour counts) where the strip is exactly two bands of 8 rows; MFMARL_ISING_PERSIST=1 keeps K6p
+    if (!(env && atoi(env) == 1) && rpt == 8 && A.L == 256 && A.rows_per == 16) {
+        kern = A.mask ? k_ising_persist_swar_f32<256, 8, true> : k_ising_persist_swar_f32<256, 8, false>;
+        threads = 512;
+    }
     if (!kern) return false;
     const int C = A.L / A.rows_per, wpr = A.L / 32;
     constexpr int kMaxSweeps = 4096;                                 // per launch: the temperature table lives in shared memory
