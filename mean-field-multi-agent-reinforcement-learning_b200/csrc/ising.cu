@@ -993,6 +993,13 @@ template <uint32_t OFF> __device__ __forceinline__ float2 lds_f32x2_at(uint32_t 
 template <uint32_t OFF> __device__ __forceinline__ void sts_f32_at(uint32_t a, float v) {
     asm volatile("st.shared.f32 [%0+%1], %2;" :: "r"(a), "n"(OFF), "f"(v) : "memory");
 }
+// 8-byte shared-memory messages {word, sequence number}: data and flag in one single-copy-atomic access
+__device__ __forceinline__ void sts_msg(uint32_t a, uint32_t word, uint32_t seq) {
+    asm volatile("st.relaxed.cta.shared.u64 [%0], %1;" :: "r"(a), "l"(((unsigned long long)seq << 32) | word) : "memory");
+}
+__device__ __forceinline__ unsigned long long lds_msg(uint32_t a) {
+    unsigned long long v; asm volatile("ld.relaxed.cta.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory"); return v;
+}
 __device__ __forceinline__ uint32_t field_sum(uint32_t x) {            // sum of the eight 4-bit fields (each <= 15)
     return (((x & 0x0F0F0F0Fu) + ((x >> 4) & 0x0F0F0F0Fu)) * 0x01010101u) >> 24;
 }
@@ -1002,7 +1009,7 @@ __global__ void __launch_bounds__(2 * L, 1) k_ising_persist_swar_f32(const Ising
                                                                      unsigned long long *const halo) {
     static_assert(L % 32 == 0 && RPT % kIsingRB == 0 && RPT <= 8 && L % (2 * RPT) == 0, "shape");
     static_assert(((uint64_t)0x4B000000u * ((uint64_t)2 * RPT * L * 8)) % (1ull << 32) == 0, "plane stride must clear the float exponent bits");
-    constexpr int ROWS = 2 * RPT, N = L * L, WPR = L / 32, STRIP = ROWS * L, NT = 2 * L, C = L / ROWS;
+    constexpr int ROWS = 2 * RPT, N = L * L, WPR = L / 32, STRIP = ROWS * L, NT = 2 * L, C = L / ROWS, NW = NT / 32;
     constexpr int NPH = RPT / kIsingRB;
     constexpr uint32_t PLANE = (uint32_t)STRIP * 8u;            // bytes between the Q planes of consecutive s
     constexpr uint32_t ROWB = (uint32_t)L * 8u;                 // bytes between consecutive rows of a plane
@@ -1011,45 +1018,37 @@ __global__ void __launch_bounds__(2 * L, 1) k_ising_persist_swar_f32(const Ising
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int slot = blockIdx.x / C, rank = blockIdx.x % C, row0 = rank * ROWS;
     float *s_q = (float *)s_raw;                                                    // [5][ROWS (lower band reversed)][L][2]
-    uint32_t *s_inner = (uint32_t *)(s_raw + (size_t)5 * STRIP * 8);                // [2 parity][2 band][WPR]: slot RPT-1 ballots
-    uint32_t *s_edge = s_inner + 2 * 2 * WPR;                                       // [2 parity][2 band][WPR][2]: lane 0 / 31 field words
-    int *s_stat = (int *)(s_edge + 2 * 2 * WPR * 2);                                // [2] packed statistics per sweep parity
-    float *s_tparam = (float *)(s_stat + 4);                                        // [K]
-    constexpr uint32_t INNER_BUF = 2u * WPR * 4u, EDGE_BUF = 2u * WPR * 2u * 4u;
+    unsigned long long *s_inner = (unsigned long long *)(s_raw + (size_t)5 * STRIP * 8);   // [2 parity][2 band][WPR] {ballot of slot RPT-1, seq}
+    unsigned long long *s_edge = s_inner + 2 * 2 * WPR;                             // [2 parity][2 band][WPR][2] {field word of lane 0 / 31, seq}
+    int *s_wstat = (int *)(s_edge + 2 * 2 * WPR * 2);                               // [NW][32] packed statistics of up to 32 sweeps per warp
+    float *s_tparam = (float *)(s_wstat + NW * 32);                                 // [K]
+    constexpr uint32_t INNER_BUF = 2u * WPR * 8u, EDGE_BUF = 2u * WPR * 2u * 8u;
 
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int x = tid % L, band = tid / L, w = x >> 5;
     const bool upper = band == 0;
     const int wl = w == 0 ? WPR - 1 : w - 1, wr = w == WPR - 1 ? 0 : w + 1;
     const int up_rank = (rank + C - 1) % C, dn_rank = (rank + 1) % C;
-    auto local_row = [&](int i) { return upper ? i : ROWS - 1 - i; };               // slot -> row of the strip
     const uint32_t q_site0 = smem_addr(s_q) + (uint32_t)(band * RPT * L + x) * 8u;  // Q pair of (s = 0, slot 0, column x)
-    const uint32_t inner_out = smem_addr(s_inner) + (uint32_t)(band * WPR + w) * 4u;
-    const uint32_t inner_in = smem_addr(s_inner) + (uint32_t)((band ^ 1) * WPR + w) * 4u;
-    const uint32_t edge_out = smem_addr(s_edge) + (uint32_t)(((band * WPR + w) * 2 + (lane == 31 ? 1 : 0))) * 4u;
+    const uint32_t inner_out = smem_addr(s_inner) + (uint32_t)(band * WPR + w) * 8u;
+    const uint32_t inner_in = smem_addr(s_inner) + (uint32_t)((band ^ 1) * WPR + w) * 8u;
+    const uint32_t edge_out = smem_addr(s_edge) + (uint32_t)(((band * WPR + w) * 2 + (lane == 31 ? 1 : 0))) * 8u;
     const uint32_t edge_in = smem_addr(s_edge) +
-        (uint32_t)(lane == 0 ? (band * WPR + wl) * 2 + 1 : lane == 31 ? (band * WPR + wr) * 2 : (band * WPR + w) * 2) * 4u;
+        (uint32_t)(lane == 0 ? (band * WPR + wl) * 2 + 1 : lane == 31 ? (band * WPR + wr) * 2 : (band * WPR + w) * 2) * 8u;
     const bool edge_lane = lane == 0 || lane == 31;
     // halo mailboxes in L2 as in K6p: [slot][rank][parity][top | bottom][WPR]
     constexpr size_t MB_PARITY = 2 * WPR;
     const unsigned long long *const mb_in = halo + (((size_t)slot * C + rank) * 2 * 2 + (upper ? 0 : 1)) * WPR + w;
     unsigned long long *const mb_out = halo + (((size_t)slot * C + (upper ? up_rank : dn_rank)) * 2 * 2 + (upper ? 1 : 0)) * WPR + w;
 
-    for (int i = threadIdx.x; i < A.K; i += NT) s_tparam[i] = temperature_param(A.temperatures[i]);
-    uint32_t state_no = 0;
-    for (int b = slot; b < A.B; b += n_slots, state_no += (uint32_t)A.K + 1u) {
+    for (int i = tid; i < A.K; i += NT) s_tparam[i] = temperature_param(A.temperatures[i]);
+    for (int i = tid; i < 2 * 2 * WPR * 3; i += NT) s_inner[i] = 0ull;              // (s_inner and s_edge are contiguous) sequence numbers start at 1
+
+    // everything a lattice needs, for the upper band (slot i = row i of the strip) or the lower one (slot i = row ROWS-1-i)
+    auto run_lattice = [&](auto upper_c, const int b, const uint32_t state_no) {
+        constexpr bool UPPER = decltype(upper_c)::value;
+        auto local_row = [](int i) { return UPPER ? i : ROWS - 1 - i; };
         const size_t lbase = (size_t)b * N;
-        __syncthreads();                                        // the previous lattice's Q strip has been stored
-        if (tid < 2) s_stat[tid] = 0;
-        for (int sp = 0; sp < 5; sp++) {
-            const float4 *s4 = (const float4 *)(A.Q + (lbase * 5 + (size_t)sp * N + (size_t)row0 * L) * 2);
-            float4 *d4 = (float4 *)(s_q + (size_t)sp * STRIP * 2);
-#pragma unroll 4
-            for (int i = tid; i < STRIP / 2; i += NT) {
-                const int sr = i / (L / 2), c4 = i % (L / 2);
-                d4[i] = s4[(sr < RPT ? sr : ROWS - 1 - sr + RPT) * (L / 2) + c4];
-            }
-        }
         uint32_t own = 0;                                       // this thread's spins of the current state, 4 bits per slot
         float sgn[RPT];                                         // the same spins as sigma = +-1
         unsigned long long hv = 0;
@@ -1066,50 +1065,39 @@ __global__ void __launch_bounds__(2 * L, 1) k_ising_persist_swar_f32(const Ising
             }
             const uint32_t w0 = __ballot_sync(0xFFFFFFFFu, a0 != 0), wN = __ballot_sync(0xFFFFFFFFu, aN != 0);
             if (lane == 0) {
-                sts_u32(inner_out + par * INNER_BUF, wN);
+                sts_msg(inner_out + par * INNER_BUF, wN, seq);
                 st_halo(mb_out + par * MB_PARITY, w0, seq);
             }
-            if (edge_lane) sts_u32(edge_out + par * EDGE_BUF, own);
+            if (edge_lane) sts_msg(edge_out + par * EDGE_BUF, own, seq);
             hv = ld_halo(mb_in + par * MB_PARITY);
         }
         const uint2 key = make_uint2(A.seed, A.lattice_base + (uint32_t)b);
         const uint32_t gband = (uint32_t)((row0 + band * RPT) >> 2);
         float uu[RPT];                                          // uniforms * 2^32, by slot
         auto draw_uniforms = [&](uint32_t step) {
-            uint4 rnd[NPH];
 #pragma unroll
-            for (int h = 0; h < NPH; h++) rnd[h] = philox4x32_10(make_uint4((uint32_t)x, gband + (uint32_t)h, step, 0u), key);
-            if (upper) {                                        // component c of call h belongs to row 4h + c of the band
-#pragma unroll
-                for (int h = 0; h < NPH; h++) {
-                    uu[4 * h + 0] = __uint2float_rz(rnd[h].x); uu[4 * h + 1] = __uint2float_rz(rnd[h].y);
-                    uu[4 * h + 2] = __uint2float_rz(rnd[h].z); uu[4 * h + 3] = __uint2float_rz(rnd[h].w);
-                }
-            } else {                                            // ... which is slot RPT-1 - (4h + c) of the lower band
-#pragma unroll
-                for (int h = 0; h < NPH; h++) {
-                    uu[RPT - 1 - (4 * h + 0)] = __uint2float_rz(rnd[h].x); uu[RPT - 1 - (4 * h + 1)] = __uint2float_rz(rnd[h].y);
-                    uu[RPT - 1 - (4 * h + 2)] = __uint2float_rz(rnd[h].z); uu[RPT - 1 - (4 * h + 3)] = __uint2float_rz(rnd[h].w);
-                }
+            for (int h = 0; h < NPH; h++) {                     // component c of call h belongs to row 4h + c of the band
+                const uint4 rnd = philox4x32_10(make_uint4((uint32_t)x, gband + (uint32_t)h, step, 0u), key);
+                uu[UPPER ? 4 * h + 0 : RPT - 1 - (4 * h + 0)] = __uint2float_rz(rnd.x);
+                uu[UPPER ? 4 * h + 1 : RPT - 1 - (4 * h + 1)] = __uint2float_rz(rnd.y);
+                uu[UPPER ? 4 * h + 2 : RPT - 1 - (4 * h + 2)] = __uint2float_rz(rnd.z);
+                uu[UPPER ? 4 * h + 3 : RPT - 1 - (4 * h + 3)] = __uint2float_rz(rnd.w);
             }
         };
         if (A.u == nullptr) draw_uniforms(A.step0);
         float keep_q[RPT]; uint32_t keep_addr[RPT];
 #pragma unroll
         for (int i = 0; i < RPT; i++) { keep_q[i] = 0.0f; keep_addr[i] = q_site0; }
+        int acc = 0;                                            // lane l: packed statistics of the sweep with (sweep & 31) == l
 
-        // one pass of the loop: finish sweep k-1 on state k (FIN), draw sweep k (DRAW).  Interior slots first, the
-        // boundary slot 0 last (its halo word travels through L2 meanwhile), as in K6p.
+        // One pass: finish sweep k-1 on state k (FIN), draw sweep k (DRAW).  No CTA barrier: a warp waits only for the
+        // three messages it reads -- the edge words of its left / right neighbour warps and the other band's ballot --
+        // each an 8-byte {word, sequence number} in shared memory, double-buffered by state parity like the halo
+        // mailboxes (a warp can be at most one state ahead of a warp it exchanges messages with).  Interior slots
+        // first, the boundary slot 0 last (its halo word travels through L2 meanwhile), as in K6p.
         auto sweep = [&](auto fin_c, auto draw_c, const int k) {
             constexpr bool FIN = decltype(fin_c)::value, DRAW = decltype(draw_c)::value;
             const uint32_t par = (state_no + (uint32_t)k) & 1u, seq = state_no + (uint32_t)k + 1u;
-            __syncthreads();                              // the words of state k are in the buffers of parity `par`
-            if (tid == 0 && k >= 2) {                     // statistics of sweep k-2: all warps added before this barrier
-                const int pk = s_stat[k & 1];
-                s_stat[k & 1] = 0;
-                atomicAdd(&A.n_up[(size_t)(k - 2) * A.B + b], pk & 0xFFFF);
-                if (A.reward_sum) atomicAdd(&A.reward_sum[(size_t)(k - 2) * A.B + b], (float)((pk >> 16) - 2 * RPT * NT));
-            }
             float tparam = 0.0f;
             if (DRAW) {
                 tparam = s_tparam[k];
@@ -1128,11 +1116,16 @@ __global__ void __launch_bounds__(2 * L, 1) k_ising_persist_swar_f32(const Ising
             }
             // neighbour counts of state k for all slots at once (the boundary slot still lacks its halo neighbour)
             uint32_t left = __shfl_up_sync(0xFFFFFFFFu, own, 1), right = __shfl_down_sync(0xFFFFFFFFu, own, 1);
-            const uint32_t e = lds_u32(edge_in + par * EDGE_BUF);
-            const uint32_t inner = lds_u32(inner_in + par * INNER_BUF);
-            if (lane == 0) left = e;
-            if (lane == 31) right = e;
-            uint32_t cnt = (own << 4) + (own >> 4) + left + right + (((inner >> lane) & 1u) << TOP);
+            unsigned long long e, inner;
+            for (;;) {
+                e = lds_msg(edge_in + par * EDGE_BUF);
+                inner = lds_msg(inner_in + par * INNER_BUF);
+                const bool ok = (uint32_t)(inner >> 32) == seq && (!edge_lane || (uint32_t)(e >> 32) == seq);
+                if (__all_sync(0xFFFFFFFFu, ok)) break;
+            }
+            if (lane == 0) left = (uint32_t)e;
+            if (lane == 31) right = (uint32_t)e;
+            uint32_t cnt = (own << 4) + (own >> 4) + left + right + ((((uint32_t)inner >> lane) & 1u) << TOP);
             uint32_t nxt_own = 0;
             // the halo word of state k: asked for now, looked at after the interior slots
             if ((uint32_t)(hv >> 32) != seq) hv = ld_halo(mb_in + par * MB_PARITY);
@@ -1172,10 +1165,8 @@ __global__ void __launch_bounds__(2 * L, 1) k_ising_persist_swar_f32(const Ising
                     const int a = decide(ic, pr[i]);
                     if (i == RPT - 1) a_top = a;
                 });
-            }
-            if (DRAW) {
                 const uint32_t wN = __ballot_sync(0xFFFFFFFFu, a_top != 0);         // slot RPT-1: the row the other band looks at
-                if (lane == 0) sts_u32(inner_out + (par ^ 1u) * INNER_BUF, wN);
+                if (lane == 0) sts_msg(inner_out + (par ^ 1u) * INNER_BUF, wN, seq + 1u);
             }
             // ---- the boundary slot 0: halo word of state k, count, finish, draw, its new word straight to the neighbour ----
             while ((uint32_t)(hv >> 32) != seq) hv = ld_halo(mb_in + par * MB_PARITY);
@@ -1186,6 +1177,7 @@ __global__ void __launch_bounds__(2 * L, 1) k_ising_persist_swar_f32(const Ising
                 const int a = decide(std::integral_constant<int, 0>{}, q);
                 const uint32_t w0 = __ballot_sync(0xFFFFFFFFu, a != 0);
                 if (lane == 0) st_halo(mb_out + (par ^ 1u) * MB_PARITY, w0, seq + 1u);
+                if (edge_lane) sts_msg(edge_out + (par ^ 1u) * EDGE_BUF, nxt_own, seq + 1u);
             }
             if (FIN) {                                    // statistics of sweep k-1 from the complete counts of state k
                 const uint32_t n_up = (uint32_t)__popc(own);
@@ -1193,25 +1185,52 @@ __global__ void __launch_bounds__(2 * L, 1) k_ising_persist_swar_f32(const Ising
                 // sum_i (2a-1)(ups-2) + 2 RPT  (>= 0), packed above the up count
                 int packed = (int)(n_up + ((2u * s_up - s_all - 4u * n_up + 4u * RPT) << 16));
                 packed = __reduce_add_sync(0xFFFFFFFFu, packed);
-                if (lane == 0) atomicAdd(&s_stat[(k - 1) & 1], packed);
+                if (lane == ((k - 1) & 31)) acc = packed;
+                // every 32 sweeps and after the last one: the warps' sums meet in shared memory, warp 0 adds them up
+                if ((k & 31) == 0 || !DRAW) {
+                    s_wstat[warp * 32 + lane] = acc;
+                    acc = 0;
+                    __syncthreads();
+                    const int ks = ((k - 1) & ~31) + lane;
+                    if (warp == 0 && ks < k) {
+                        int pk = 0;
+#pragma unroll
+                        for (int ww = 0; ww < NW; ww++) pk += s_wstat[ww * 32 + lane];
+                        atomicAdd(&A.n_up[(size_t)ks * A.B + b], pk & 0xFFFF);
+                        if (A.reward_sum) atomicAdd(&A.reward_sum[(size_t)ks * A.B + b], (float)((pk >> 16) - 2 * RPT * NT));
+                    }
+                    __syncthreads();
+                }
             }
-            if (DRAW) {
-                own = nxt_own;
-                if (edge_lane) sts_u32(edge_out + (par ^ 1u) * EDGE_BUF, own);
-            }
+            if (DRAW) own = nxt_own;
         };
         sweep(std::false_type{}, std::true_type{}, 0);
         for (int k = 1; k < A.K; k++) {
             if (A.u == nullptr) draw_uniforms(A.step0 + (uint32_t)k);
             sweep(std::true_type{}, std::true_type{}, k);
         }
-        sweep(std::true_type{}, std::false_type{}, A.K);
-        __syncthreads();
-        if (tid == 0) {
-            const int kk = A.K - 1, pk = s_stat[kk & 1];
-            atomicAdd(&A.n_up[(size_t)kk * A.B + b], pk & 0xFFFF);
-            if (A.reward_sum) atomicAdd(&A.reward_sum[(size_t)kk * A.B + b], (float)((pk >> 16) - 2 * RPT * NT));
+        sweep(std::true_type{}, std::false_type{}, A.K);        // (ends with a barrier: every warp's Q updates are in shared memory)
+#pragma unroll
+        for (int i = 0; i < RPT; i++)
+            A.spins[lbase + (size_t)(row0 + local_row(i)) * L + x] = (int8_t)((own >> (4 * i)) & 1u);
+    };
+
+    uint32_t state_no = 0;                                      // lattice states published so far by this slot
+    for (int b = slot; b < A.B; b += n_slots, state_no += (uint32_t)A.K + 1u) {
+        const size_t lbase = (size_t)b * N;
+        __syncthreads();                                        // the previous lattice's Q strip has been stored (first pass: the tables are set)
+        for (int sp = 0; sp < 5; sp++) {
+            const float4 *s4 = (const float4 *)(A.Q + (lbase * 5 + (size_t)sp * N + (size_t)row0 * L) * 2);
+            float4 *d4 = (float4 *)(s_q + (size_t)sp * STRIP * 2);
+#pragma unroll 4
+            for (int i = tid; i < STRIP / 2; i += NT) {
+                const int sr = i / (L / 2), c4 = i % (L / 2);
+                d4[i] = s4[(sr < RPT ? sr : ROWS - 1 - sr + RPT) * (L / 2) + c4];
+            }
         }
+        __syncthreads();                                        // the strip is complete before anybody draws from it
+        if (upper) run_lattice(std::true_type{}, b, state_no);
+        else run_lattice(std::false_type{}, b, state_no);
         for (int sp = 0; sp < 5; sp++) {
             float4 *d4 = (float4 *)(A.Q + (lbase * 5 + (size_t)sp * N + (size_t)row0 * L) * 2);
             const float4 *s4 = (const float4 *)(s_q + (size_t)sp * STRIP * 2);
@@ -1221,9 +1240,6 @@ __global__ void __launch_bounds__(2 * L, 1) k_ising_persist_swar_f32(const Ising
                 d4[(sr < RPT ? sr : ROWS - 1 - sr + RPT) * (L / 2) + c4] = s4[i];
             }
         }
-#pragma unroll
-        for (int i = 0; i < RPT; i++)
-            A.spins[lbase + (size_t)(row0 + local_row(i)) * L + x] = (int8_t)((own >> (4 * i)) & 1u);
     }
 }
 
@@ -1281,9 +1297,10 @@ static bool launch_ising_persistent(const IsingRunArgs<float> &A, cudaStream_t s
     MF_PICK(256, 16) MF_PICK(128, 32)
 #undef MF_PICK
     // K6s (SWAR neighbour counts) where the strip is exactly two bands of 8 rows; MFMARL_ISING_PERSIST=1 keeps K6p
+    bool swar = false;
     if (!(env && atoi(env) == 1) && rpt == 8 && A.L == 256 && A.rows_per == 16) {
         kern = A.mask ? k_ising_persist_swar_f32<256, 8, true> : k_ising_persist_swar_f32<256, 8, false>;
-        threads = 512;
+        threads = 512; swar = true;
     }
     if (!kern) return false;
     const int C = A.L / A.rows_per, wpr = A.L / 32;
@@ -1301,7 +1318,9 @@ static bool launch_ising_persistent(const IsingRunArgs<float> &A, cudaStream_t s
         }
         return true;
     }
-    const size_t smem = resident_smem_bytes<float>(A.L, A.rows_per) + (size_t)A.K * sizeof(float);
+    // K6p: bit buffers + statistics; K6s: message slots [2][2][wpr] x (1 + 2) of 8 bytes + [warps][32] statistics
+    const size_t smem = (swar ? (size_t)5 * A.rows_per * A.L * 8 + (size_t)2 * 2 * wpr * 3 * 8 + (size_t)(threads / 32) * 32 * 4
+                              : resident_smem_bytes<float>(A.L, A.rows_per)) + (size_t)A.K * sizeof(float);
     MF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, n_sm = 0, per_sm = 0;
     MF_CUDA(cudaGetDevice(&dev));

@@ -52,13 +52,25 @@ def test_fp64_trajectory_matches_oracle_exactly(L, T):
         Q[...] = new_Q
 
 
+def _select_kernel(monkeypatch, variant):
+    """variant: "0" generic resident kernel, "4"/"8" the shape-specialised fp32 kernels with 4 / 8 rows per thread
+    (at 256 x 256 the default "8" is K6s, the persistent kernel with SWAR neighbour counts); a "p" prefix keeps the
+    previous persistent kernel K6p (MFMARL_ISING_PERSIST=1), a "c" prefix the cluster kernel K6r (=0)."""
+    if not variant:
+        return
+    if variant[0] in "pc":
+        monkeypatch.setenv("MFMARL_ISING_PERSIST", "1" if variant[0] == "p" else "0")
+        variant = variant[1:]
+    monkeypatch.setenv("MFMARL_ISING_RPT", variant)
+
+
 def _neighbourhood(mask):
     """sites whose reward (hence Q update) can see a site of `mask`: the site itself and its 4 torus neighbours"""
     return mask | np.roll(mask, 1, -2) | np.roll(mask, -1, -2) | np.roll(mask, 1, -1) | np.roll(mask, -1, -1)
 
 
 @pytest.mark.parametrize("L,B,mode", [(20, 2, "stream"), (256, 2, "stream"), (256, 2, "0"), (256, 2, "4"), (256, 2, "8"),
-                                        (64, 3, "8"), (128, 2, "8")])
+                                        (256, 2, "p8"), (256, 2, "c8"), (64, 3, "8"), (128, 2, "8")])
 def test_fp32_every_sweep_from_the_oracle_state(L, B, mode, monkeypatch, capsys):
     """Production precision, production kernels (BASELINE config 5 shape, main_MFQ_Ising.py:55-67,105-134): 20 sweeps,
     each started from the oracle's state and driven by the same injected uniforms.  The fp32 decision
@@ -68,7 +80,7 @@ def test_fp32_every_sweep_from_the_oracle_state(L, B, mode, monkeypatch, capsys)
     mode: "stream" = mfi_step (K6); "0"/"4"/"8" = mfi_run (K6r) generic / 4 / 8 rows per thread, one sweep per launch."""
     from mfmarl_b200 import IsingMFQ
     if mode != "stream":
-        monkeypatch.setenv("MFMARL_ISING_RPT", mode)
+        _select_kernel(monkeypatch, mode)
     T, sweeps = 0.8, 20
     rng = np.random.RandomState(L + 3)
     spins = rng.randint(0, 2, size=(B, L, L)).astype(np.int8)
@@ -102,15 +114,15 @@ def test_fp32_every_sweep_from_the_oracle_state(L, B, mode, monkeypatch, capsys)
     assert flips <= max(4, near // 2)       # the fp32 decision is far more accurate than the 1e-5 window
 
 
-@pytest.mark.parametrize("L,B,mode", [(256, 2, "8"), (256, 2, "4"), (256, 2, "0"), (64, 2, "8"), (20, 3, "")])
+@pytest.mark.parametrize("L,B,mode", [(256, 2, "8"), (256, 11, "8"), (256, 2, "p8"), (256, 2, "4"), (256, 2, "0"), (64, 2, "8"),
+                                        (20, 3, "")])
 def test_fp32_resident_run_of_20_sweeps_follows_the_oracle_trajectory(L, B, mode, monkeypatch, capsys):
     """K = 20 sweeps in ONE launch of the resident kernel against the fp64 oracle trajectory.  The uniforms are fixed
     up front: the oracle walks its own trajectory and every draw that comes closer than 1e-5 to its threshold is
     moved 1e-3 away (counted), so the two trajectories cannot part on a rounding tie.  Then spins and per-sweep up
     counts must be EQUAL and Q within 1e-6 relative everywhere, with no exception."""
     from mfmarl_b200 import IsingMFQ
-    if mode:
-        monkeypatch.setenv("MFMARL_ISING_RPT", mode)
+    _select_kernel(monkeypatch, mode)
     T, K = 0.8, 20
     rng = np.random.RandomState(L + 11)
     spins0 = rng.randint(0, 2, size=(B, L, L)).astype(np.int8)
@@ -200,15 +212,16 @@ def test_full_size_256x256_properties():
 
 @pytest.mark.parametrize("L,B,K,variant", [(20, 5, 30, ""), (48, 2, 9, ""), (64, 3, 12, "0"), (64, 3, 12, "4"),
                                             (64, 2, 5, "8"), (128, 2, 8, "0"), (128, 2, 8, "4"), (128, 2, 7, "8"),
-                                            (256, 3, 6, "0"), (256, 3, 6, "4"), (256, 2, 9, "8"), (256, 2, 1, "4")])
+                                            (256, 3, 6, "0"), (256, 3, 6, "4"), (256, 2, 9, "8"), (256, 2, 1, "4"),
+                                            (256, 2, 1, "8"), (256, 2, 2, "8"), (256, 12, 5, "8"), (256, 3, 7, "p8"),
+                                            (256, 3, 7, "c8")])
 def test_resident_kernel_equals_streaming_bit_for_bit(L, B, K, variant, monkeypatch):
     """K sweeps in one launch with Q resident in shared memory (cluster of 1 / 1 / 4 / 16 CTAs per lattice, halo
     rows pushed through DSMEM) give exactly the spins, Q and per-sweep statistics of K streaming launches (same
     Philox keys).  `variant` picks the kernel: "0" the generic one, "4"/"8" the shape-specialised fp32 kernel with
     4 / 8 rows per thread (MFMARL_ISING_RPT); "" leaves the default."""
     from mfmarl_b200 import IsingMFQ
-    if variant:
-        monkeypatch.setenv("MFMARL_ISING_RPT", variant)
+    _select_kernel(monkeypatch, variant)
     rng = np.random.RandomState(L)
     spins = torch.from_numpy(rng.randint(0, 2, size=(B, L, L)).astype(np.int8))
     a = IsingMFQ(B, L, seed=21, spins=spins)
@@ -225,13 +238,12 @@ def test_resident_kernel_equals_streaming_bit_for_bit(L, B, K, variant, monkeypa
     assert not torch.equal(a.spins[0], spins[0].cuda())
 
 
-@pytest.mark.parametrize("L,variant", [(20, ""), (64, "8"), (256, "8"), (256, "0")])
+@pytest.mark.parametrize("L,variant", [(20, ""), (64, "8"), (256, "8"), (256, "p8"), (256, "0")])
 def test_resident_kernel_with_act_groups_equals_streaming(L, variant, monkeypatch):
     """act_rate < 1 (main_MFQ_Ising.py:126): only a random subset of the sites updates Q each sweep -- the per-sweep
     masks go through the resident kernel exactly as through K streaming launches."""
     from mfmarl_b200 import IsingMFQ
-    if variant:
-        monkeypatch.setenv("MFMARL_ISING_RPT", variant)
+    _select_kernel(monkeypatch, variant)
     B, K = 2, 7
     gen = torch.Generator(device="cuda"); gen.manual_seed(L)
     masks = (torch.rand((K, B, L * L), generator=gen, device="cuda") < 0.6).to(torch.uint8).contiguous()
