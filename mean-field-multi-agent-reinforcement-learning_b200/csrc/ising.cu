@@ -1005,7 +1005,7 @@ __device__ __forceinline__ uint32_t field_sum(uint32_t x) {            // sum of
 }
 
 template <int L, int RPT, bool MASK>
-__global__ void __launch_bounds__(2 * L, 1) k_ising_persist_swar_f32(const IsingRunArgs<float> A, const int n_slots,
+__global__ void __launch_bounds__(2 * L, 512 / (2 * L) > 0 ? 512 / (2 * L) : 1) k_ising_persist_swar_f32(const IsingRunArgs<float> A, const int n_slots,
                                                                      unsigned long long *const halo) {
     static_assert(L % 32 == 0 && RPT % kIsingRB == 0 && RPT <= 8 && L % (2 * RPT) == 0, "shape");
     static_assert(((uint64_t)0x4B000000u * ((uint64_t)2 * RPT * L * 8)) % (1ull << 32) == 0, "plane stride must clear the float exponent bits");
@@ -1296,14 +1296,19 @@ static bool launch_ising_persistent(const IsingRunArgs<float> &A, cudaStream_t s
     }
     MF_PICK(256, 16) MF_PICK(128, 32)
 #undef MF_PICK
-    // K6s (SWAR neighbour counts) where the strip is exactly two bands of 8 rows; MFMARL_ISING_PERSIST=1 keeps K6p
+    // K6s (SWAR neighbour counts): strips of two bands of 8 rows whatever K6r's cluster would be (no cluster here, so
+    // the strip height is free); MFMARL_ISING_PERSIST=1 keeps K6p
+    int rows_per = A.rows_per;
     bool swar = false;
-    if (!(env && atoi(env) == 1) && rpt == 8 && A.L == 256 && A.rows_per == 16) {
-        kern = A.mask ? k_ising_persist_swar_f32<256, 8, true> : k_ising_persist_swar_f32<256, 8, false>;
-        threads = 512; swar = true;
+    if (!(env && atoi(env) == 1) && rpt == 8) {
+#define MF_PICK(LL) \
+        if (A.L == LL) { kern = A.mask ? k_ising_persist_swar_f32<LL, 8, true> : k_ising_persist_swar_f32<LL, 8, false>; \
+                         threads = 2 * LL; rows_per = 16; swar = true; }
+        MF_PICK(256) MF_PICK(128) MF_PICK(64)
+#undef MF_PICK
     }
     if (!kern) return false;
-    const int C = A.L / A.rows_per, wpr = A.L / 32;
+    const int C = A.L / rows_per, wpr = A.L / 32;
     constexpr int kMaxSweeps = 4096;                                 // per launch: the temperature table lives in shared memory
     if (A.K > kMaxSweeps) {
         for (int k0 = 0; k0 < A.K; k0 += kMaxSweeps) {
@@ -1319,8 +1324,8 @@ static bool launch_ising_persistent(const IsingRunArgs<float> &A, cudaStream_t s
         return true;
     }
     // K6p: bit buffers + statistics; K6s: message slots [2][2][wpr] x (1 + 2) of 8 bytes + [warps][32] statistics
-    const size_t smem = (swar ? (size_t)5 * A.rows_per * A.L * 8 + (size_t)2 * 2 * wpr * 3 * 8 + (size_t)(threads / 32) * 32 * 4
-                              : resident_smem_bytes<float>(A.L, A.rows_per)) + (size_t)A.K * sizeof(float);
+    const size_t smem = (swar ? (size_t)5 * rows_per * A.L * 8 + (size_t)2 * 2 * wpr * 3 * 8 + (size_t)(threads / 32) * 32 * 4
+                              : resident_smem_bytes<float>(A.L, rows_per)) + (size_t)A.K * sizeof(float);
     MF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, n_sm = 0, per_sm = 0;
     MF_CUDA(cudaGetDevice(&dev));
@@ -1364,7 +1369,7 @@ static void launch_ising_resident(const IsingRunArgs<T> &A0, cudaStream_t st) {
     const int C = resident_cluster_size<T>(L);
     if (C == 0) throw Fatal("ising resident kernel: lattice side " + std::to_string(L) + " not supported (use mfi_step)");
     A.rows_per = L / C;
-    if (C > 1 && launch_ising_persistent(A, st)) return;
+    if (launch_ising_persistent(A, st)) return;                     // (declines shapes it has no specialisation for)
     const int bands = (A.rows_per + kIsingRB - 1) / kIsingRB;
     const size_t smem = resident_smem_bytes<T>(L, A.rows_per);
     const bool fast = (L % 32 == 0) && (A.rows_per % kIsingRB == 0);

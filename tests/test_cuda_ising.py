@@ -214,7 +214,8 @@ def test_full_size_256x256_properties():
                                             (64, 2, 5, "8"), (128, 2, 8, "0"), (128, 2, 8, "4"), (128, 2, 7, "8"),
                                             (256, 3, 6, "0"), (256, 3, 6, "4"), (256, 2, 9, "8"), (256, 2, 1, "4"),
                                             (256, 2, 1, "8"), (256, 2, 2, "8"), (256, 12, 5, "8"), (256, 3, 7, "p8"),
-                                            (256, 3, 7, "c8")])
+                                            (256, 3, 7, "c8"), (64, 2, 5, "c8"), (64, 5, 33, "8"), (128, 2, 7, "p8"),
+                                            (128, 2, 7, "c8"), (128, 40, 3, "8")])
 def test_resident_kernel_equals_streaming_bit_for_bit(L, B, K, variant, monkeypatch):
     """K sweeps in one launch with Q resident in shared memory (cluster of 1 / 1 / 4 / 16 CTAs per lattice, halo
     rows pushed through DSMEM) give exactly the spins, Q and per-sweep statistics of K streaming launches (same
