@@ -85,6 +85,22 @@ struct Game {
     bool spec_state = false;       // committed: mir[cur ^ 1] holds the records after clear_dead once ev_spec fires
     bool spec_obs = false;         // committed: m_view / m_feat hold both groups' rows once ev_spec fires
 
+    // The steady play-loop step (set_action x2 + step, then the speculative clear_dead + observe x2 + two copies) is
+    // six enqueues, and at one 64 v 64 env the HOST side of those enqueues is what env_step costs.  Once the same
+    // sequence has run twice it is captured into a CUDA graph -- one per (mirror parity, set_action order) -- and
+    // replayed with one launch; the two events become external event-record nodes.  A cached graph is only reused
+    // while every pointer and parameter baked into it is unchanged (the key below); anything else re-captures.
+    // MAGENT_STEP_GRAPH=0 switches it off.
+    struct StepGraph {
+        cudaGraphExec_t exec = nullptr;
+        int into = -1, seq0 = -2, seq1 = -2, setact_mask = -1;
+        BattleParams P; BattleState S;
+        const void *pin = nullptr, *d_view = nullptr, *d_feat = nullptr, *d_done = nullptr, *d_perm = nullptr;
+    };
+    std::vector<StepGraph> graphs;
+    bool use_graphs = true;
+    int plain_steps = 0;           // eligible steps enqueued call by call so far (the first two warm every attribute up)
+
     // render trace (RenderGenerator.cc): config.json once, then frames appended to video_<file_ct>.txt
     std::string render_dir;
     bool first_render = true;
@@ -97,6 +113,12 @@ struct Game {
         cudaFreeHost(pin);
         if (ev_step) cudaEventDestroy(ev_step);
         if (ev_spec) cudaEventDestroy(ev_spec);
+        drop_graphs();
+    }
+
+    void drop_graphs() {
+        for (StepGraph &sg : graphs) if (sg.exec) cudaGraphExecDestroy(sg.exec);
+        graphs.clear();
     }
 
     void invalidate() { state_fresh = false; obs_fresh = false; spec_state = false; spec_obs = false; }
@@ -242,6 +264,8 @@ struct Game {
         MF_CUDA(cudaEventCreateWithFlags(&ev_spec, cudaEventDisableTiming));
         const char *sp = getenv("MAGENT_SPECULATE");
         speculate = !(sp && atoi(sp) == 0);
+        const char *gr = getenv("MAGENT_STEP_GRAPH");
+        use_graphs = !(gr && atoi(gr) == 0);
     }
 
     void ensure_staging() {
@@ -419,17 +443,12 @@ int env_step(EnvHandle game, int *done) {
         }
         io.attack_events = g->d_events;
     }
-    E.step(io, g->st);
-    MF_CUDA(cudaEventRecord(g->ev_step, g->st));
-    if (g->inject_next) { E.set_rng_mode(RNG_MINSTD); g->inject_next = false; }
-    if (want_events) {
-        const std::vector<int32_t> raw = pull(g->d_events, (size_t)1 + 6 * cap, g->st);
-        g->events.clear();
-        for (int i = 0; i < raw[0]; i++)
-            if (raw[1 + 3 * i] >= 0) g->events.insert(g->events.end(), raw.begin() + 1 + 3 * i, raw.begin() + 4 + 3 * i);
-    } else if (g->speculate) {
-        // what the play loop asks for next, enqueued now: clear_dead (its records into the OTHER mirror), both groups'
-        // observations, one copy per observation buffer
+    // what the play loop asks for next is enqueued behind the step: clear_dead (its records into the OTHER mirror),
+    // both groups' observations, one copy per observation buffer
+    auto enqueue = [&](bool with_spec, unsigned event_flags) {
+        E.step(io, g->st);
+        MF_CUDA(cudaEventRecordWithFlags(g->ev_step, g->st, event_flags));
+        if (!with_spec) return;
         StepIO c{};
         c.phases = PH_CLEAR; c.group_seq[0] = c.group_seq[1] = -1; c.mirror = g->mirror_io(g->cur);
         E.step(c, g->st);
@@ -437,7 +456,52 @@ int env_step(EnvHandle game, int *done) {
         const int FS = E.params().feature_size;
         MF_CUDA(cudaMemcpyAsync(g->m_view, g->d_view, (size_t)2 * cap * kViewRow * 4, cudaMemcpyDeviceToHost, g->st));
         MF_CUDA(cudaMemcpyAsync(g->m_feat, g->d_feat, (size_t)2 * cap * FS * 4, cudaMemcpyDeviceToHost, g->st));
-        MF_CUDA(cudaEventRecord(g->ev_spec, g->st));
+        MF_CUDA(cudaEventRecordWithFlags(g->ev_spec, g->st, event_flags));
+    };
+    const bool with_spec = !want_events && g->speculate;
+    const bool graphable = with_spec && g->use_graphs && !g->inject_next && io.phases == (PH_STEP | PH_SETACT);
+    bool launched = false;
+    if (graphable && g->plain_steps >= 2) {
+        Game::StepGraph *hit = nullptr;
+        for (Game::StepGraph &sg : g->graphs)
+            if (sg.into == into && sg.seq0 == io.group_seq[0] && sg.seq1 == io.group_seq[1] && sg.setact_mask == io.setact_mask)
+                hit = &sg;
+        const bool valid = hit && hit->pin == g->pin && hit->d_view == g->d_view && hit->d_feat == g->d_feat &&
+                           hit->d_done == g->d_done && hit->d_perm == g->d_perm &&
+                           memcmp(&hit->P, &E.params(), sizeof(BattleParams)) == 0 &&
+                           memcmp(&hit->S, &E.state(), sizeof(BattleState)) == 0;
+        if (hit && !valid) { g->drop_graphs(); hit = nullptr; }       // something was re-allocated or re-configured
+        if (!hit) {
+            if (g->graphs.size() >= 8) g->drop_graphs();
+            cudaGraph_t graph = nullptr;
+            MF_CUDA(cudaStreamBeginCapture(g->st, cudaStreamCaptureModeThreadLocal));
+            try { enqueue(true, cudaEventRecordExternal); }
+            catch (...) { cudaStreamEndCapture(g->st, &graph); if (graph) cudaGraphDestroy(graph); throw; }
+            MF_CUDA(cudaStreamEndCapture(g->st, &graph));
+            Game::StepGraph sg;
+            const cudaError_t err = cudaGraphInstantiate(&sg.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (err != cudaSuccess) throw Fatal(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(err));
+            sg.into = into; sg.seq0 = io.group_seq[0]; sg.seq1 = io.group_seq[1]; sg.setact_mask = io.setact_mask;
+            memcpy(&sg.P, &E.params(), sizeof(BattleParams)); memcpy(&sg.S, &E.state(), sizeof(BattleState));
+            sg.pin = g->pin; sg.d_view = g->d_view; sg.d_feat = g->d_feat; sg.d_done = g->d_done; sg.d_perm = g->d_perm;
+            g->graphs.push_back(sg);
+            hit = &g->graphs.back();
+        }
+        MF_CUDA(cudaGraphLaunch(hit->exec, g->st));
+        launched = true;
+    }
+    if (!launched) {
+        enqueue(with_spec, cudaEventRecordDefault);
+        if (graphable) g->plain_steps++;
+    }
+    if (g->inject_next) { E.set_rng_mode(RNG_MINSTD); g->inject_next = false; }
+    if (want_events) {
+        const std::vector<int32_t> raw = pull(g->d_events, (size_t)1 + 6 * cap, g->st);
+        g->events.clear();
+        for (int i = 0; i < raw[0]; i++)
+            if (raw[1 + 3 * i] >= 0) g->events.insert(g->events.end(), raw.begin() + 1 + 3 * i, raw.begin() + 4 + 3 * i);
+    } else if (with_spec) {
         g->spec_pending = true;
     }
     MF_CUDA(cudaEventSynchronize(g->ev_step));            // rewards, alive flags, positions, done: in the mirror now
