@@ -235,3 +235,49 @@ def test_speculation_switched_off_gives_the_same_results(monkeypatch):
     setup_pair([ora, cu], *generate_map_positions(40))
     st = run_lockstep(ora, cu, steps=120, seed=8, stream="fight", skip_clear_every=5)
     assert st["deaths"] > 10, st
+
+
+@pytest.mark.parametrize("graph", ["1", "0"])
+def test_step_graph_replay_follows_every_change_of_the_step_shape(graph, monkeypatch):
+    """After two plain steps env_step replays the steady sequence (set_action x2 + step + speculative clear_dead +
+    observe x2 + copies) as a CUDA graph keyed by mirror parity and set_action order (runtime_api.cu).  Everything
+    baked into a graph changes here while it is in use: the order of the set_action calls, a group that does not act,
+    a late add that grows the capacity (every buffer re-allocated), a new episode -- and the results stay the
+    oracle's bit for bit, with the graph on and off (MAGENT_STEP_GRAPH)."""
+    from scenarios import fight_actions
+    monkeypatch.setenv("MAGENT_STEP_GRAPH", graph)
+    ora, cu = OracleEngine(40), CudaEngine(40)
+    left, right = generate_map_positions(40)
+    rng = np.random.RandomState(17)
+
+    def check(s):
+        for g in range(2):
+            assert ora.get_num(g) == cu.get_num(g)
+            assert_same("reward", ora.get_reward(g), cu.get_reward(g), s)
+            assert_same("alive", ora.get_alive(g), cu.get_alive(g), s)
+        ora.clear_dead(); cu.clear_dead()
+        for g in range(2):
+            va, fa = ora.get_observation(g); vb, fb = cu.get_observation(g)
+            assert_same("view", va, vb, s); assert_same("feature", fa, fb, s)
+            assert_same("id", ora.get_agent_id(g), cu.get_agent_id(g), s)
+            assert_same("pos", ora.get_pos(g), cu.get_pos(g), s)
+
+    for episode in range(2):
+        setup_pair([ora, cu], left, right)
+        for s in range(60):
+            order = (0, 1) if (s // 6) % 2 == 0 else (1, 0)          # the set_action order is part of the graph key
+            if s % 17 == 16:
+                order = order[:1]                                     # one group does not act this step
+            acts = {g: fight_actions(rng, ora.get_pos(g), 40) for g in range(2)}
+            for g in order:
+                ora.set_action(g, acts[g]); cu.set_action(g, acts[g])
+            assert ora.step() == cu.step()
+            if s == 25 and episode == 0:                              # late add: 64 -> 66 agents, capacity grows
+                extra = np.array([[20, 3, 0], [21, 3, 0]], np.int32)
+                check(s)
+                for eng in (ora, cu):
+                    eng.add_agents(0, extra)
+                for g in range(2):
+                    assert_same("pos after add", ora.get_pos(g), cu.get_pos(g), s)
+            else:
+                check(s)
