@@ -144,7 +144,8 @@ const char *mfb_last_error(void);
  *   d_spins        int8 [n_lattices][side][side]      in/out, values {0, 1}
  *   d_q            T    [n_lattices][5][side*side][2]  in/out, entry (s, a) of site i at ((s*N + i)*2 + a)
  *   d_uniforms     T    [n_lattices][side*side] or NULL: injected uniforms (test hook; a = [u >= p0]);
- *                  NULL = Philox4x32-10 keyed by (seed, lattice_base + lattice) x (column, row band, step)
+ *                  NULL = Philox4x32-10, key (seed, lattice_base + lattice), counter (column, row / 4, step, 0);
+ *                  output word row % 4 is the site's draw, u = that word (rounded toward zero to 24 bits) / 2^32
  *   d_update_mask  uint8[n_lattices][side*side] or NULL: the act group (act_rate < 1); NULL = all sites
  *   d_n_up         int32[n_lattices]  out: up spins after the sweep (order parameter = |2 up - N| / N)
  *   d_reward_sum,
@@ -154,11 +155,12 @@ int mfi_step(int dtype, int n_lattices, int side, int8_t *d_spins, void *d_q, do
              const void *d_uniforms, const uint8_t *d_update_mask, unsigned seed, unsigned lattice_base,
              unsigned step, int32_t *d_n_up, void *d_reward_sum, void *d_mse, void *stream);
 
-/* K6r / K6p: `n_sweeps` sweeps in ONE launch with the Q table resident in shared memory.  A lattice is split into
- * mfi_resident_cluster_size() strips of rows, one CTA each (1 for side <= 64, 4 for 128, 16 for 256 in fp32).  For the
- * fp32 shapes 128 and 256 the strips are ordinary CTAs of a persistent, cooperatively launched grid that fills the
- * GPU (144 of 148 SMs at side 256) and exchange their halo rows through L2 (K6p); other shapes use a thread-block
- * cluster per lattice (K6r; MFMARL_ISING_PERSIST=0 forces it).  Either way: same semantics and the same Philox keys as
+/* K6r / K6p / K6s: `n_sweeps` sweeps in ONE launch with the Q table resident in shared memory.  A lattice is split into
+ * strips of rows, one CTA each.  For the fp32 sides 64, 128 and 256 the strips (16 rows) are ordinary CTAs of a
+ * persistent, cooperatively launched grid that fills the GPU (144 of 148 SMs at side 256) and exchange their halo rows
+ * through L2 (K6s; MFMARL_ISING_PERSIST=1 selects its predecessor K6p); other shapes, and MFMARL_ISING_PERSIST=0, use a
+ * thread-block cluster of mfi_resident_cluster_size() CTAs per lattice (K6r: 1 for side <= 64, 4 for 128, 16 for 256
+ * in fp32).  Either way: same semantics and the same Philox keys as
  * n_sweeps calls of mfi_step with step = step0 .. step0+n_sweeps-1 (bit-identical results); the Q table is read and
  * written once per launch.
  *   d_temperatures  T    [n_sweeps]                          in (the schedule of main_MFQ_Ising.py:108-112)

@@ -302,3 +302,31 @@ def test_cli_chunked_quiet_mode_equals_stepwise(capsys):
             cur = 0.25
         want.append(cur)
     assert sched == want and ising.temperature_schedule(60, 60, 0.97, 50, 0.25) == want[60:]
+
+
+@pytest.mark.parametrize("L,B,resident", [(256, 3, False), (256, 11, True), (128, 2, True), (64, 2, True), (20, 2, False),
+                                          (20, 2, True), (7, 2, False)])
+def test_production_draws_are_philox4x32_10_with_the_documented_keys(L, B, resident):
+    """include/mfmarl_batched.h: key (seed, lattice_base + lattice), counter (column, row / 4, step, 0), output word
+    row % 4, u = word / 2^32.  With Q = 0 both actions are equally likely and a = [u >= 1/2] is the word's top bit, so
+    the lattice after one sweep IS the Philox4x32-10 stream -- computed here in numpy from the published round function
+    (tests/philox_ref.py, pinned to the Random123 known-answer vectors)."""
+    from mfmarl_b200 import IsingMFQ
+    from philox_ref import philox4x32_10
+    seed, base, step0 = 77, 5, 3
+    m = IsingMFQ(B, L, seed=seed, lattice_base=base)
+    m.t = step0
+    if resident:
+        m.run([0.8], resident=True)
+    else:
+        m.step(0.8)
+    got = m.spins.cpu().numpy()
+    x = np.arange(L, dtype=np.uint32)[None, None, :]
+    band = (np.arange(L, dtype=np.uint32) // 4)[None, :, None]
+    lat = (base + np.arange(B, dtype=np.uint32))[:, None, None]
+    ctr = [np.broadcast_to(a, (B, L, L)).astype(np.uint32) for a in (x, band, np.uint32(step0), np.uint32(0))]
+    key = [np.broadcast_to(np.uint32(seed), (B, L, L)).astype(np.uint32), np.broadcast_to(lat, (B, L, L)).astype(np.uint32)]
+    out = philox4x32_10(ctr, key)                                # four words per (lattice, row, column)
+    comp = (np.arange(L) % 4)[None, :, None]
+    word = np.choose(np.broadcast_to(comp, (B, L, L)), out)
+    assert np.array_equal(got, (word >> 31).astype(np.int8))
