@@ -648,7 +648,7 @@ def measure_ising(ctx, args, K, W, min_seconds):
     B, L, T = total // world, wl["side"], wl["temperature"]
     model = IsingMFQ(B, L, seed=13, lr=wl["lr"], lattice_base=rank * B, device=dev)
 
-    # --sweeps-per-launch S: S > 1 runs S sweeps per launch with the Q strip resident in shared memory (K6p / K6r,
+    # --sweeps-per-launch S: S > 1 runs S sweeps per launch with the Q strip resident in shared memory (K6s / K6p / K6r,
     # mfi_run; same bits as S streaming launches); S = 1 is the streaming kernel K6 (mfi_step), one launch per sweep.
     S = args.sweeps_per_launch
     if S == 0:
@@ -717,7 +717,8 @@ def measure_ising(ctx, args, K, W, min_seconds):
     peak, peak_src = measured_peak()
     sites = B * world * L * L
     achieved = B * L * L * BYTES_PER_SITE / (ms / K * 1e-3) / 1e9
-    kernel = ("k_ising_persist_f32" if os.environ.get("MFMARL_ISING_PERSIST", "1") != "0" else "k_ising_resident_f32") if resident else "k_ising"
+    kernel = {"0": "k_ising_resident_f32", "1": "k_ising_persist_f32"}.get(
+        os.environ.get("MFMARL_ISING_PERSIST", ""), "k_ising_persist_swar_f32") if resident else "k_ising"
     return {
         "metric": "ising MFQ site-steps/sec", "value": sites * K / (ms * 1e-3), "unit": "site-steps/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,

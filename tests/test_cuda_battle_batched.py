@@ -599,3 +599,47 @@ def test_convoys_and_focused_fire_resolve_like_the_ordered_loops(map_size, cap):
         if (env.get_num() == 0).any():
             break
     assert deaths > 0, deaths
+
+
+def test_philox_attack_shuffle_uses_the_documented_keys():
+    """rng="philox": the attack shuffle of env e at its step s is the reference's inside-out Fisher-Yates
+    (GridWorld.cc:510-515) with draw i = Philox4x32-10(counter (i, s, 0, 0), key (seed, env_base + e)).x % (i + 1)
+    (battle_kernels.cuh).  The oracle gets exactly that permutation injected, computed in numpy from the published
+    round function (tests/philox_ref.py), and every output must then agree bit for bit."""
+    from philox_ref import philox4x32_10
+    E, seed, base = 3, 9, 5
+    env, oracles = make(E, rng="philox", seed=seed, env_base=base)
+    rngs = [np.random.RandomState(40 + e) for e in range(E)]
+    deaths = 0
+    for s in range(80):
+        num, pos = env.get_num(), env.get("pos")
+        actions = np.zeros((E, 2, env.capacity), np.int32)
+        for e, o in enumerate(oracles):
+            n_att = 0
+            for g in range(2):
+                n = num[e, g]
+                a = fight_actions(rngs[e], pos[e, g, :n], env.map_size)
+                actions[e, g, :n] = a
+                o.set_action(g, a)
+                n_att += int((a >= 13).sum())
+            i = np.arange(n_att, dtype=np.uint32)
+            draws = philox4x32_10([i, np.full_like(i, s), np.zeros_like(i), np.zeros_like(i)],
+                                  [np.full_like(i, seed), np.full_like(i, base + e)])[0] % (i + 1)
+            order = np.arange(n_att, dtype=np.int32)
+            for k in range(n_att):
+                j = int(draws[k]); order[k], order[j] = order[j], order[k]
+            o.inject_attack_order(order)
+        reward, alive, done, _ = env.step(torch.from_numpy(actions).cuda())
+        reward, alive = reward.cpu().numpy(), alive.cpu().numpy()
+        for e, o in enumerate(oracles):
+            assert o.step() == bool(done[e])
+            for g in range(2):
+                n = num[e, g]
+                assert_same("reward[e%d g%d]" % (e, g), o.get_reward(g), reward[e, g, :n], s)
+                al = o.get_alive(g)
+                assert_same("alive[e%d g%d]" % (e, g), al, alive[e, g, :n].astype(bool), s)
+                deaths += int((~al).sum())
+            o.clear_dead()
+        if done.any():
+            break
+    assert deaths > 10, deaths
