@@ -91,6 +91,9 @@ public:
     void download_num(cudaStream_t st);          // refresh h_num from the device (syncs)
     const BattleParams &params() const { return P_; }
     void set_rng_mode(int mode) { P_.rng_mode = mode; }
+    // a caller that replays captured step launches (CUDA graph) tells the engine that the device state has moved on:
+    // what Engine::step notes itself when it launches (late add_agents then reads the device state back first)
+    void mark_stepped() { stepped_ = true; }
     const std::vector<unsigned char> &host_walls() const { return h_walls_; }
     // E == 1 helpers for add_agents(method="random"): the engine RNG lives on the device
     uint32_t pull_rng0();

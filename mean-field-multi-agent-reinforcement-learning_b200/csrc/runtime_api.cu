@@ -100,6 +100,7 @@ struct Game {
     std::vector<StepGraph> graphs;
     bool use_graphs = true;
     int plain_steps = 0;           // eligible steps enqueued call by call so far (the first two warm every attribute up)
+    int graph_replays = 0;         // env_step calls served by a graph launch (mfmarl_step_graph_replays)
 
     // render trace (RenderGenerator.cc): config.json once, then frames appended to video_<file_ct>.txt
     std::string render_dir;
@@ -489,6 +490,8 @@ int env_step(EnvHandle game, int *done) {
             hit = &g->graphs.back();
         }
         MF_CUDA(cudaGraphLaunch(hit->exec, g->st));
+        E.mark_stepped();                     // (Engine::step did not run on the host this time)
+        g->graph_replays++;
         launched = true;
     }
     if (!launched) {
@@ -873,6 +876,8 @@ int mfmarl_inject_attack_order(EnvHandle game, const int *perm, int n) {
     g->inject_next = true;
     API_END("mfmarl_inject_attack_order")
 }
+
+int mfmarl_step_graph_replays(EnvHandle game) { return game ? reinterpret_cast<Game *>(game)->graph_replays : -1; }
 
 const char *mfmarl_last_error(void) { return last_error(); }
 

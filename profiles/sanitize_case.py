@@ -54,11 +54,15 @@ for s in range(4):
     for g in range(2): big.set_action(g, fight_actions(rng, big.get_pos(g), 104))
     big.step(); big.get_observation(0); big.clear_dead()          # (an observation before clear_dead: the rollback path)
 os.environ.pop("MFMARL_ISING_RPT", None)
-for L in (128, 256):
-    m = IsingMFQ(3, L)
-    m.run([0.8] * 4, resident=True)
-    masks = (torch.rand((4, 3, L * L), device="cuda") < 0.5).to(torch.uint8).contiguous()
-    m.run([0.8] * 4, resident=True, update_mask=masks)
+for persist in (None, "1"):                        # K6s (default; 64 / 128 / 256), then its predecessor K6p (128 / 256)
+    if persist: os.environ["MFMARL_ISING_PERSIST"] = persist
+    for L in (64, 128, 256):
+        m = IsingMFQ(11, L)                        # 11 lattices: a slot sweeps more than one (the state-number hand-over)
+        m.run([0.8] * 4, resident=True)
+        masks = (torch.rand((4, 11, L * L), device="cuda") < 0.5).to(torch.uint8).contiguous()
+        m.run([0.8] * 4, resident=True, update_mask=masks)
+        m.run([0.8] * 35, resident=True)           # more than 32 sweeps: the per-warp statistics flush inside the loop
+os.environ.pop("MFMARL_ISING_PERSIST", None)
 import ctypes
 from mfmarl_b200.lib import load_library
 lib = load_library(); lib.mfi_env_step.argtypes = [ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 6

@@ -262,9 +262,13 @@ def test_step_graph_replay_follows_every_change_of_the_step_shape(graph, monkeyp
             assert_same("id", ora.get_agent_id(g), cu.get_agent_id(g), s)
             assert_same("pos", ora.get_pos(g), cu.get_pos(g), s)
 
+    import ctypes
+    cu.lib.mfmarl_step_graph_replays.argtypes = [ctypes.c_void_p]
+    replays = lambda: cu.lib.mfmarl_step_graph_replays(cu.env.game)
     for episode in range(2):
         setup_pair([ora, cu], left, right)
         for s in range(60):
+            before = replays()
             order = (0, 1) if (s // 6) % 2 == 0 else (1, 0)          # the set_action order is part of the graph key
             if s % 17 == 16:
                 order = order[:1]                                     # one group does not act this step
@@ -272,7 +276,11 @@ def test_step_graph_replay_follows_every_change_of_the_step_shape(graph, monkeyp
             for g in order:
                 ora.set_action(g, acts[g]); cu.set_action(g, acts[g])
             assert ora.step() == cu.step()
-            if s == 25 and episode == 0:                              # late add: 64 -> 66 agents, capacity grows
+            # late adds: 64 -> 66 agents in episode 0 (the capacity grows, every buffer moves); in episode 1 right after
+            # its FIRST step, which was a graph replay (nothing but the replay tells the engine that it has stepped)
+            if (s == 25 and episode == 0) or (s == 0 and episode == 1):
+                if graph == "1":
+                    assert replays() == before + 1, "this step was meant to be a graph replay"
                 extra = np.array([[20, 3, 0], [21, 3, 0]], np.int32)
                 check(s)
                 for eng in (ora, cu):
@@ -281,3 +289,4 @@ def test_step_graph_replay_follows_every_change_of_the_step_shape(graph, monkeyp
                     assert_same("pos after add", ora.get_pos(g), cu.get_pos(g), s)
             else:
                 check(s)
+    assert (replays() > 80) if graph == "1" else (replays() == 0), replays()
