@@ -983,7 +983,10 @@ __global__ void __launch_bounds__(L * (ROWS / RPT), 1) k_ising_persist_f32(const
 // always the strip's boundary row (the one that needs the halo word and feeds the neighbouring strip), slot RPT-1
 // always the row facing the other band, and the neighbour sum is symmetric in up / down -- one code path, no
 // per-row "is this the boundary row" branches.  The sweep loop is peeled (first sweep: nothing to finish; after the
-// last: nothing to draw).  Same Philox keys, same float operations in the same order as K6 / K6r / K6p: same bits.
+// last: nothing to draw) and has NO CTA barrier: the three words a warp reads from other warps are 8-byte
+// {word, sequence number} messages in shared memory (see `sweep` below), the per-warp statistics stay in registers and
+// meet every 32 sweeps.  Same Philox keys, same float operations in the same order as K6 / K6r / K6p: same bits.
+// Measured (C5, B200): K6p 3.27e11 -> 4.59e11 site-steps/s; 69 -> 50 thread instructions per site-step (profiles/r02).
 template <int I0, int I1, class F> __device__ __forceinline__ void static_for(F &&f) {
     if constexpr (I0 < I1) { f(std::integral_constant<int, I0>{}); static_for<I0 + 1, I1>(f); }
 }
