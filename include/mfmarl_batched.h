@@ -156,11 +156,11 @@ int mfi_step(int dtype, int n_lattices, int side, int8_t *d_spins, void *d_q, do
              unsigned step, int32_t *d_n_up, void *d_reward_sum, void *d_mse, void *stream);
 
 /* K6r / K6p / K6s: `n_sweeps` sweeps in ONE launch with the Q table resident in shared memory.  A lattice is split into
- * strips of rows, one CTA each.  For the fp32 sides 64, 128 and 256 the strips (16 rows) are ordinary CTAs of a
- * persistent, cooperatively launched grid that fills the GPU (144 of 148 SMs at side 256) and exchange their halo rows
- * through L2 (K6s; MFMARL_ISING_PERSIST=1 selects its predecessor K6p); other shapes, and MFMARL_ISING_PERSIST=0, use a
- * thread-block cluster of mfi_resident_cluster_size() CTAs per lattice (K6r: 1 for side <= 64, 4 for 128, 16 for 256
- * in fp32).  Either way: same semantics and the same Philox keys as
+ * strips of rows, one CTA each.  For the fp32 sides 64, 128, 256 (strips of 16 rows) and 512 (strips of 8 rows) the
+ * strips are ordinary CTAs of a persistent, cooperatively launched grid that fills the GPU (144 of 148 SMs at side 256)
+ * and exchange their halo rows through L2 (K6s; MFMARL_ISING_PERSIST=1 selects its predecessor K6p at 128 / 256); other
+ * shapes, and MFMARL_ISING_PERSIST=0, use a thread-block cluster of mfi_resident_cluster_size() CTAs per lattice (K6r:
+ * 1 for side <= 64, 4 for 128, 16 for 256 in fp32; mfi_resident_cluster_size(fp32, 512) = 64 is K6s's strip count).  Either way: same semantics and the same Philox keys as
  * n_sweeps calls of mfi_step with step = step0 .. step0+n_sweeps-1 (bit-identical results); the Q table is read and
  * written once per launch.
  *   d_temperatures  T    [n_sweeps]                          in (the schedule of main_MFQ_Ising.py:108-112)

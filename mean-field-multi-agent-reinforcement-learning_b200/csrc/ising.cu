@@ -978,7 +978,7 @@ __global__ void __launch_bounds__(L * (ROWS / RPT), 1) k_ising_persist_f32(const
 //   * the per-sweep statistics are a popcount and two horizontal field sums,
 //   * the reward as a float is (2^23 + count) reinterpreted, minus (2^23 + 2): no integer-to-float conversion,
 //   * only the two rows other threads' columns look at from above / below are still published as ballot words.
-// Shape: exactly two bands per strip (ROWS == 2 RPT).  The lower band holds its rows in REVERSE order (slot i = local
+// Shape: exactly two bands per strip (ROWS == 2 RPT; RPT = 8 at sides 64 / 128 / 256, 4 at 512 where 16 rows do not fit).  The lower band holds its rows in REVERSE order (slot i = local
 // row ROWS-1-i, in registers and in the shared-memory Q strip), which makes the two bands mirror images: slot 0 is
 // always the strip's boundary row (the one that needs the halo word and feeds the neighbouring strip), slot RPT-1
 // always the row facing the other band, and the neighbour sum is symmetric in up / down -- one code path, no
@@ -1286,9 +1286,11 @@ static void specialised_resident_kernel(const IsingRunArgs<float> &A, void (*&ke
 static bool launch_ising_persistent(const IsingRunArgs<double> &, cudaStream_t) { return false; }
 static bool launch_ising_persistent(const IsingRunArgs<float> &A, cudaStream_t st) {
     const char *env = getenv("MFMARL_ISING_PERSIST");
-    if (env && atoi(env) == 0) return false;                        // 0 = the cluster kernel K6r (tests, comparisons)
     const char *renv = getenv("MFMARL_ISING_RPT");
-    if (renv && atoi(renv) == 0) return false;                      // the generic kernel was asked for
+    if (A.L != 512) {                                               // (512: K6s is the only resident kernel, see below)
+        if (env && atoi(env) == 0) return false;                    // 0 = the cluster kernel K6r (tests, comparisons)
+        if (renv && atoi(renv) == 0) return false;                  // the generic kernel was asked for
+    }
     const int rpt = renv ? atoi(renv) : 8;
     void (*kern)(const IsingRunArgs<float>, int, unsigned long long *) = nullptr;
     unsigned threads = 0;
@@ -1309,6 +1311,12 @@ static bool launch_ising_persistent(const IsingRunArgs<float> &A, cudaStream_t s
                          threads = 2 * LL; rows_per = 16; swar = true; }
         MF_PICK(256) MF_PICK(128) MF_PICK(64)
 #undef MF_PICK
+    }
+    // 512 x 512: a 16-row strip's Q (327 KB) does not fit, so strips of 8 rows with 4 rows per thread (1024 threads, 64
+    // registers); no cluster kernel exists for this side, so neither MFMARL_ISING_PERSIST nor _RPT (other than 0) applies
+    if (A.L == 512) {
+        kern = A.mask ? k_ising_persist_swar_f32<512, 4, true> : k_ising_persist_swar_f32<512, 4, false>;
+        threads = 1024; rows_per = 8; swar = true;
     }
     if (!kern) return false;
     const int C = A.L / rows_per, wpr = A.L / 32;
@@ -1370,9 +1378,9 @@ static void launch_ising_resident(const IsingRunArgs<T> &A0, cudaStream_t st) {
     IsingRunArgs<T> A = A0;
     const int L = A.L, wpr = (L + 31) >> 5, LP = wpr * 32;
     const int C = resident_cluster_size<T>(L);
-    if (C == 0) throw Fatal("ising resident kernel: lattice side " + std::to_string(L) + " not supported (use mfi_step)");
-    A.rows_per = L / C;
+    A.rows_per = C > 0 ? L / C : 0;
     if (launch_ising_persistent(A, st)) return;                     // (declines shapes it has no specialisation for)
+    if (C == 0) throw Fatal("ising resident kernel: lattice side " + std::to_string(L) + " not supported (use mfi_step)");
     const int bands = (A.rows_per + kIsingRB - 1) / kIsingRB;
     const size_t smem = resident_smem_bytes<T>(L, A.rows_per);
     const bool fast = (L % 32 == 0) && (A.rows_per % kIsingRB == 0);
@@ -1487,6 +1495,7 @@ extern "C" int mfi_step(int dtype, int n_lattices, int side, int8_t *d_spins, vo
 }
 
 extern "C" int mfi_resident_cluster_size(int dtype, int side) {
+    if (dtype != 1 && side == 512) return 64;          // K6s only: 64 strips of 8 rows (no cluster kernel at this side)
     return dtype == 1 ? resident_cluster_size<double>(side) : resident_cluster_size<float>(side);
 }
 

@@ -11,7 +11,7 @@ d=json.loads(open("gpurun_out/bench_c5.json").read().strip().splitlines()[-1])
 print("c5", "%.4g"%d["value"], "ms/step %.4f"%d["ms_per_step"], "frac", d["roofline"]["frac"], "e2e %.4g"%d["e2e"]["value"])
 PY
 {
-for L in 128 64; do
+for L in 512 128 64; do
   B=$((16384 * 65536 / L / L / 8))
   echo "== L=$L K6s"; timeout 120 python profiles/ising_probe.py $B 100 $L resident
   echo "== L=$L previous resident kernel"; MFMARL_ISING_PERSIST=1 timeout 120 python profiles/ising_probe.py $B 100 $L resident

@@ -215,7 +215,7 @@ def test_full_size_256x256_properties():
                                             (256, 3, 6, "0"), (256, 3, 6, "4"), (256, 2, 9, "8"), (256, 2, 1, "4"),
                                             (256, 2, 1, "8"), (256, 2, 2, "8"), (256, 12, 5, "8"), (256, 3, 7, "p8"),
                                             (256, 3, 7, "c8"), (64, 2, 5, "c8"), (64, 5, 33, "8"), (128, 2, 7, "p8"),
-                                            (128, 2, 7, "c8"), (128, 40, 3, "8")])
+                                            (128, 2, 7, "c8"), (128, 40, 3, "8"), (512, 3, 5, ""), (512, 1, 34, "")])
 def test_resident_kernel_equals_streaming_bit_for_bit(L, B, K, variant, monkeypatch):
     """K sweeps in one launch with Q resident in shared memory (cluster of 1 / 1 / 4 / 16 CTAs per lattice, halo
     rows pushed through DSMEM) give exactly the spins, Q and per-sweep statistics of K streaming launches (same
@@ -227,7 +227,7 @@ def test_resident_kernel_equals_streaming_bit_for_bit(L, B, K, variant, monkeypa
     spins = torch.from_numpy(rng.randint(0, 2, size=(B, L, L)).astype(np.int8))
     a = IsingMFQ(B, L, seed=21, spins=spins)
     b = IsingMFQ(B, L, seed=21, spins=spins)
-    assert a.resident_cluster == {20: 1, 48: 1, 64: 1, 128: 4, 256: 16}[L]
+    assert a.resident_cluster == {20: 1, 48: 1, 64: 1, 128: 4, 256: 16, 512: 64}[L]
     temps = [max(0.8, 0.3 * 0.99)] * K
     for rounds in range(2):            # two launches: state carries over (step counter, spins, Q)
         n_res, r_res = a.run(temps, resident=True)
@@ -239,7 +239,7 @@ def test_resident_kernel_equals_streaming_bit_for_bit(L, B, K, variant, monkeypa
     assert not torch.equal(a.spins[0], spins[0].cuda())
 
 
-@pytest.mark.parametrize("L,variant", [(20, ""), (64, "8"), (256, "8"), (256, "p8"), (256, "0")])
+@pytest.mark.parametrize("L,variant", [(20, ""), (64, "8"), (256, "8"), (256, "p8"), (256, "0"), (512, "")])
 def test_resident_kernel_with_act_groups_equals_streaming(L, variant, monkeypatch):
     """act_rate < 1 (main_MFQ_Ising.py:126): only a random subset of the sites updates Q each sweep -- the per-sweep
     masks go through the resident kernel exactly as through K streaming launches."""
@@ -304,7 +304,7 @@ def test_cli_chunked_quiet_mode_equals_stepwise(capsys):
     assert sched == want and ising.temperature_schedule(60, 60, 0.97, 50, 0.25) == want[60:]
 
 
-@pytest.mark.parametrize("L,B,resident", [(256, 3, False), (256, 11, True), (128, 2, True), (64, 2, True), (20, 2, False),
+@pytest.mark.parametrize("L,B,resident", [(256, 3, False), (256, 11, True), (512, 3, True), (128, 2, True), (64, 2, True), (20, 2, False),
                                           (20, 2, True), (7, 2, False)])
 def test_production_draws_are_philox4x32_10_with_the_documented_keys(L, B, resident):
     """include/mfmarl_batched.h: key (seed, lattice_base + lattice), counter (column, row / 4, step, 0), output word
