@@ -70,7 +70,7 @@ def _neighbourhood(mask):
 
 
 @pytest.mark.parametrize("L,B,mode", [(20, 2, "stream"), (256, 2, "stream"), (256, 2, "0"), (256, 2, "4"), (256, 2, "8"),
-                                        (256, 2, "p8"), (256, 2, "c8"), (64, 3, "8"), (128, 2, "8")])
+                                        (256, 2, "p8"), (256, 2, "c8"), (64, 3, "8"), (128, 2, "8"), (512, 1, "")])
 def test_fp32_every_sweep_from_the_oracle_state(L, B, mode, monkeypatch, capsys):
     """Production precision, production kernels (BASELINE config 5 shape, main_MFQ_Ising.py:55-67,105-134): 20 sweeps,
     each started from the oracle's state and driven by the same injected uniforms.  The fp32 decision
