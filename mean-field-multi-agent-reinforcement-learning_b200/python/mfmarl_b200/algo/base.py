@@ -63,7 +63,23 @@ def _dense(n_in, n_out):
     return layer
 
 
+def _conv_bias_relu(conv, x, fused):
+    """relu(conv(x) + bias).  `fused` (the bf16 rollout twin on CUDA, no autograd): cuDNN's convolution with the bias and
+    the ReLU in its epilogue -- one pass over the output instead of three (PyTorch's conv adds the bias with a
+    broadcasting elementwise kernel and the ReLU is one more; at 65 536 rows those two passes were 1.3 ms of the 2.9 ms
+    MF-Q forward, profiles/r02/play_busy_probe.txt)."""
+    if fused and x.is_cuda and not torch.is_grad_enabled():
+        try:
+            return torch.cudnn_convolution_relu(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation,
+                                                conv.groups)
+        except RuntimeError:
+            pass
+    return F.relu(conv(x))
+
+
 class QNet(nn.Module):
+    fused_conv = False        # set on the bf16 rollout twin (bf16_rollout_copy)
+
     def __init__(self, view_space, feature_space, num_actions, use_mf):
         super().__init__()
         h, w, c = view_space
@@ -86,7 +102,7 @@ class QNet(nn.Module):
 
     def forward(self, view, feature, prob=None):
         x = view.permute(0, 3, 1, 2)                      # engine layout is NHWC: a channels_last view, no copy
-        x = F.relu(self.conv2(F.relu(self.conv1(x))))
+        x = _conv_bias_relu(self.conv2, _conv_bias_relu(self.conv1, x, self.fused_conv), self.fused_conv)
         x = x.permute(0, 2, 3, 1).flatten(1)              # flatten in (H, W, C) order like the TF graph (base.py:134-136)
         parts = [F.relu(self.dense_obs(x)), F.relu(self.dense_emb(feature))]
         if self.use_mf:
@@ -146,6 +162,7 @@ def bf16_rollout_copy(net):
             conv1.weight[:, :c_in] = net.conv1.weight
             conv1.bias.copy_(net.conv1.bias)
         twin.conv1 = conv1.to(net.conv1.weight.device)
+    twin.fused_conv = True
     return twin.to(torch.bfloat16).to(memory_format=torch.channels_last).eval()
 
 

@@ -190,3 +190,34 @@ def test_data_parallel_training_keeps_the_ranks_in_step(algo, tmp_path):
     assert len(a) == len(b) > 0
     for x, y in zip(a, b):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("use_mf", [True, False])
+def test_bf16_rollout_twin_with_the_fused_convolutions_agrees_with_the_plain_path(use_mf):
+    """The bf16 rollout twin runs conv + bias + ReLU as ONE cuDNN call (algo.base._conv_bias_relu).  Same weights, same
+    bf16 observation rows: its Q values must agree with the unfused bf16 path to bf16 resolution, and its greedy actions
+    with the fp32 network on (almost) every row."""
+    from mfmarl_b200.algo.base import QNet, bf16_rollout_copy
+    torch.manual_seed(5)
+    net = QNet((13, 13, 7), (34,), 21, use_mf).cuda()
+    with torch.no_grad():
+        for conv in (net.conv1, net.conv2):
+            conv.bias.uniform_(-0.2, 0.2)                 # (zero at initialisation: make the bias matter)
+    N = 4096
+    view = torch.zeros((N, 13, 13, 8), device="cuda")
+    view[..., :7] = (torch.rand((N, 13, 13, 7), device="cuda") < 0.08).float() * torch.rand((N, 13, 13, 7), device="cuda")
+    feat = torch.rand((N, 34), device="cuda")
+    prob = torch.softmax(torch.randn((N, 21), device="cuda"), dim=1) if use_mf else None
+    twin = bf16_rollout_copy(net)
+    assert twin.fused_conv
+    v16, f16, p16 = view.to(torch.bfloat16), feat.to(torch.bfloat16), None if prob is None else prob.to(torch.bfloat16)
+    with torch.no_grad():
+        q_fused = twin(v16, f16, p16).float()
+        twin.fused_conv = False
+        q_plain = twin(v16, f16, p16).float()
+        q32 = net(view[..., :7].contiguous(), feat, prob)
+    scale = float(q32.abs().max())
+    assert float((q_fused - q_plain).abs().max()) < 0.03 * scale, (float((q_fused - q_plain).abs().max()), scale)
+    assert float((q_fused - q32).abs().max()) < 0.05 * scale
+    agree = float((q_fused.argmax(1) == q32.argmax(1)).float().mean())
+    assert agree > 0.9, agree
