@@ -16,6 +16,8 @@ class Spaces:
     def get_action_space(self, h): return (21,)
 
 
+if os.environ.get("CUDNN_BENCHMARK") == "1":
+    torch.backends.cudnn.benchmark = True          # let cuDNN time its algorithms instead of using the heuristic
 for algo in sys.argv[1:] or ["mfac", "mfq"]:
     dev = torch.device("cuda", 0)
     env = BatchedGridWorld(1024, map_size=40, capacity=64, device=dev, rng="philox", seed=0)
