@@ -101,7 +101,7 @@ def battle(env, n_round, map_size, max_steps, handles, models, print_every, eps=
 # batched, device-resident form
 # ----------------------------------------------------------------------------------------------------------
 def play_batched(env, n_round, max_steps, models, eps=1.0, train=False, print_every=0, left_group=None,
-                 positions=None, obs_dtype=None):
+                 positions=None, obs_dtype=None, host_lag=None):
     """E episodes in lockstep on a `BatchedGridWorld` (one per environment), everything on the device.
 
     Per environment this is the loop of `play`: observe both groups -> models[g].act on the group's rows (with the
@@ -113,6 +113,9 @@ def play_batched(env, n_round, max_steps, models, eps=1.0, train=False, print_ev
     obs_dtype=torch.bfloat16: the policies act on the engine's bf16 NHWC-8 observation rows (no cast, no padding pass,
     bf16 tensor cores; see algo.base.bf16_rollout_copy); the fp32 rows are still produced for the replay buffer when
     train=True.
+
+    host_lag: how many steps the host may run ahead of the device before it looks at the "any environment still
+    playing" flag (see below); None = 2 on a CUDA device, 0 = ask after every step.
 
     Returns (max_nums [E, 2], nums [E, 2], mean_rewards [E, 2], total_rewards [E, 2]) as numpy arrays.
     """
@@ -138,7 +141,25 @@ def play_batched(env, n_round, max_steps, models, eps=1.0, train=False, print_ev
     steps_run = torch.zeros((E,), dtype=torch.int64, device=dev)
     actions = torch.zeros((E, 2, cap), dtype=torch.int32, device=dev)
     step_ct = 0
-    while step_ct < max_steps and bool(active.any()):
+    # "is any environment still playing" is the one thing the host has to learn from the device.  Asking after every
+    # step would make the host wait for the step it has just enqueued before it can enqueue the next one (for the
+    # dense MF-AC network the GPU then idles a quarter of the time, profiles/r02/play_busy_probe.txt), so the flag
+    # travels to pinned memory behind each step and the host looks at the one from TWO steps back: it runs one step
+    # ahead of the device.  After the last environment finishes, at most two more steps run with every environment
+    # masked out (`active` gates the statistics and the replay rows), which changes nothing that is returned.
+    lag = (2 if dev.type == "cuda" else 0) if host_lag is None else int(host_lag)
+    flags = [torch.ones((1,), dtype=torch.bool).pin_memory() if lag else None for _ in range(max(lag, 1))]
+    events = [torch.cuda.Event() if lag else None for _ in range(max(lag, 1))]
+
+    def still_playing():
+        if not lag:
+            return bool(active.any())
+        if step_ct < lag:
+            return True
+        events[step_ct % lag].synchronize()           # recorded behind step step_ct - lag
+        return bool(flags[step_ct % lag][0])
+
+    while step_ct < max_steps and still_playing():
         if obs_dtype is not None and obs_dtype != torch.float32:
             act_obs = env.observe_groups(dtype=obs_dtype)  # bf16 [E, cap, 13, 13, 8] rows for the policies
             obs = env.observe_groups(groups=(0,)) if train else act_obs
@@ -169,6 +190,9 @@ def play_batched(env, n_round, max_steps, models, eps=1.0, train=False, print_ev
         final_nums = torch.where(active[:, None], num, final_nums)
         former = torch.where(active[:, None, None], mean, former)
         active = active & (done == 0)
+        if lag:
+            flags[step_ct % lag].copy_(active.any().reshape(1), non_blocking=True)
+            events[step_ct % lag].record()
         step_ct += 1
         if print_every and step_ct % print_every == 0:
             print("> step #{}, active envs: {}, agents: {}".format(step_ct, int(active.sum()),

@@ -221,3 +221,32 @@ def test_bf16_rollout_twin_with_the_fused_convolutions_agrees_with_the_plain_pat
     assert float((q_fused - q32).abs().max()) < 0.05 * scale
     agree = float((q_fused.argmax(1) == q32.argmax(1)).float().mean())
     assert agree > 0.9, agree
+
+
+def test_play_batched_host_running_ahead_returns_what_the_step_by_step_loop_returns():
+    """play_batched looks at the "any environment still playing" flag two steps late so that the host can enqueue ahead
+    of the device (senario_battle.py).  With armies that are annihilated after a few steps the round ends early: the
+    lagging loop runs at most two more steps, with every environment masked out, and returns exactly what the loop that
+    asks after every step returns; the rows handed to the learner are the same, plus all-inactive ones at the end."""
+    from mfmarl_b200 import BatchedGridWorld
+    from mfmarl_b200.senario_battle import play_batched
+    E = 4
+    # six attackers around one defender per side pair: group 1 dies within a few steps in every environment
+    pos0 = np.array([[10, 10, 0], [11, 10, 0], [12, 10, 0], [10, 12, 0], [11, 12, 0], [12, 12, 0]], np.int32)
+    pos1 = np.array([[11, 11, 0]], np.int32)
+    out = {}
+    for lag in (0, 2):
+        env = BatchedGridWorld(E, map_size=40, capacity=64, rng="minstd", seed=0)
+        models = [ExactPolicy(+1), ExactPolicy(-1)]
+        res = play_batched(env, 0, 50, models, eps=1.0, train=True, left_group=0, positions=(pos0, pos1), host_lag=lag)
+        out[lag] = (res, models[0].rows)
+    (r0, rows0), (r2, rows2) = out[0], out[2]
+    assert len(rows0) < 20, "the round was meant to end early"
+    assert len(rows0) <= len(rows2) <= len(rows0) + 2
+    for a, b in zip(r0, r2):
+        assert np.array_equal(a, b)
+    for d0, d2 in zip(rows0, rows2):
+        for k in ("ids", "acts", "rewards", "alives", "prob", "num", "active"):
+            assert np.array_equal(d0[k], d2[k]), k
+    for extra in rows2[len(rows0):]:
+        assert not extra["active"].any()
