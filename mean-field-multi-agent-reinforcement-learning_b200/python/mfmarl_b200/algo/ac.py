@@ -8,6 +8,8 @@ value_coef * mean((R - V)^2) + ent_coef * mean(sum pi log pi), Adam 1e-4 (the un
 the reference keeps, :97-104).  `train` turns every agent's episode into discounted returns bootstrapped from the
 value of its LAST state (ac.py:139-148), then does one update on the whole batch.
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -148,8 +150,8 @@ class _ActorCriticBase:
         if isinstance(view, torch.Tensor) and view.dtype == torch.bfloat16:       # the engine's bf16 rows [N, 13, 13, 8]
             if getattr(self, "_rollout16", None) is None or self._rollout16_stale:
                 self._rollout16, self._rollout16_stale = self.net.bf16_rollout_copy(self.view_space), False
-            policy = self._rollout16.policy(view, feature.to(torch.bfloat16)).float()
-            return torch.multinomial(policy, 1, generator=self.generator).reshape(-1).to(torch.int32)
+                self._act_graphs = {}
+            return self._act_rows16(view, feature)
         v, f = as_tensor(view, self.device), as_tensor(feature, self.device)
         if self.act_autocast is not None and v.is_cuda:
             with torch.autocast("cuda", dtype=self.act_autocast):
@@ -158,6 +160,39 @@ class _ActorCriticBase:
             policy = self.net.policy(v, f)
         action = torch.multinomial(policy, 1, generator=self.generator).reshape(-1).to(torch.int32)
         return action if isinstance(view, torch.Tensor) else action.cpu().numpy()
+
+    def _act_rows16(self, view, feature):
+        """Forward of the bf16 twin + the multinomial draw on the engine's observation buffers.  The dense network is
+        ~20 small launches per group and the rollout loop is bound by the host issuing them (profiles/r02/
+        play_busy_probe.txt), and the engine hands out the SAME buffers every step, so the sequence is captured into a
+        CUDA graph per (view buffer, feature buffer) and replayed; the result lands in a fixed tensor that the caller
+        copies from right away.  MFMARL_ACT_GRAPH=0, a CPU tensor or a failed capture fall back to the eager calls."""
+        def eager():
+            policy = self._rollout16.policy(view, feature.to(torch.bfloat16)).float()
+            return torch.multinomial(policy, 1, generator=self.generator).reshape(-1).to(torch.int32)
+
+        if not view.is_cuda or not getattr(self, "_act_graph_ok", os.environ.get("MFMARL_ACT_GRAPH", "1") != "0"):
+            return eager()
+        key = (view.data_ptr(), feature.data_ptr(), tuple(view.shape), tuple(feature.shape))
+        hit = self._act_graphs.get(key)
+        if hit is None:
+            try:
+                side = torch.cuda.Stream(device=view.device)
+                side.wait_stream(torch.cuda.current_stream(view.device))
+                with torch.cuda.stream(side):
+                    eager(); eager()                                   # warm-up outside the capture
+                torch.cuda.current_stream(view.device).wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                graph.register_generator_state(self.generator)
+                with torch.cuda.graph(graph):
+                    out = eager()
+                hit = self._act_graphs[key] = (graph, out)
+            except Exception as ex:                                    # capture not possible here: stay eager for good
+                self._act_graph_ok = False
+                print("[mfmarl] rollout graph capture failed (%s): eager rollout forward" % type(ex).__name__)
+                return eager()
+        hit[0].replay()
+        return hit[1]
 
     @torch.no_grad()
     def _value(self, view, feature, prob):
