@@ -1369,7 +1369,14 @@ static bool launch_ising_persistent(const IsingRunArgs<float> &A, cudaStream_t s
     attr[0].id = cudaLaunchAttributeCooperative;                    // the strips of a lattice wait for each other: the
     attr[0].val.cooperative = 1;                                    // whole grid must be resident at once
     cfg.attrs = attr; cfg.numAttrs = 1;
-    MF_CUDA(cudaLaunchKernelEx(&cfg, kern, A, n_slots, halo));
+    const cudaError_t err = cudaLaunchKernelEx(&cfg, kern, A, n_slots, halo);
+    if (err == cudaErrorCooperativeLaunchTooLarge && A.L != 512) {
+        // fewer SMs are available to this process than the device reports (MPS with a limited SM share, ...): the
+        // co-scheduled grid cannot be resident at once -- leave the launch to the cluster kernel K6r, same bits
+        (void)cudaGetLastError();
+        return false;
+    }
+    MF_CUDA(err);
     return true;
 }
 
