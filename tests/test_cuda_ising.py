@@ -215,12 +215,14 @@ def test_full_size_256x256_properties():
                                             (256, 3, 6, "0"), (256, 3, 6, "4"), (256, 2, 9, "8"), (256, 2, 1, "4"),
                                             (256, 2, 1, "8"), (256, 2, 2, "8"), (256, 12, 5, "8"), (256, 3, 7, "p8"),
                                             (256, 3, 7, "c8"), (64, 2, 5, "c8"), (64, 5, 33, "8"), (128, 2, 7, "p8"),
-                                            (128, 2, 7, "c8"), (128, 40, 3, "8"), (512, 3, 5, ""), (512, 1, 34, "")])
+                                            (128, 2, 7, "c8"), (128, 40, 3, "8"), (512, 3, 5, ""), (512, 1, 34, ""),
+                                            (64, 2, 4100, "8")])
 def test_resident_kernel_equals_streaming_bit_for_bit(L, B, K, variant, monkeypatch):
     """K sweeps in one launch with Q resident in shared memory (cluster of 1 / 1 / 4 / 16 CTAs per lattice, halo
     rows pushed through DSMEM) give exactly the spins, Q and per-sweep statistics of K streaming launches (same
     Philox keys).  `variant` picks the kernel: "0" the generic one, "4"/"8" the shape-specialised fp32 kernel with
-    4 / 8 rows per thread (MFMARL_ISING_RPT); "" leaves the default."""
+    4 / 8 rows per thread (MFMARL_ISING_RPT); "" leaves the default.  K = 4100 exceeds the persistent kernels' sweeps per
+    launch (the temperature table in shared memory): mfi_run splits it into two launches."""
     from mfmarl_b200 import IsingMFQ
     _select_kernel(monkeypatch, variant)
     rng = np.random.RandomState(L)
@@ -330,3 +332,19 @@ def test_production_draws_are_philox4x32_10_with_the_documented_keys(L, B, resid
     comp = (np.arange(L) % 4)[None, :, None]
     word = np.choose(np.broadcast_to(comp, (B, L, L)), out)
     assert np.array_equal(got, (word >> 31).astype(np.int8))
+
+
+@pytest.mark.parametrize("L,T", [(256, 0.05), (64, 0.02), (512, 0.05)])
+def test_persistent_kernel_at_very_low_temperature_equals_streaming(L, T):
+    """Deep in the ordered phase exp((q1 - q0) / T) overflows to +inf (or underflows to 0) in fp32 for most sites: the
+    decision u (1 + e) >= 1 must still come out the same in every kernel (they share the function), the lattice orders
+    locally (aligned neighbours: the reward sum, 0 for a random lattice and 2 N for a uniform one, is well above 0; the
+    global order parameter stays small while the domains coarsen), and nothing turns into NaN."""
+    from mfmarl_b200 import IsingMFQ
+    B, K = 3, 40
+    a, b = IsingMFQ(B, L, seed=31), IsingMFQ(B, L, seed=31)
+    n_res, r_res = a.run([T] * K, resident=True)
+    n_str, r_str = b.run([T] * K, resident=False)
+    assert torch.equal(a.spins, b.spins) and torch.equal(a.Q, b.Q) and torch.equal(n_res, n_str)
+    assert torch.isfinite(a.Q).all()
+    assert float(r_res[-1].min()) > 0.5 * L * L, r_res[-1]
