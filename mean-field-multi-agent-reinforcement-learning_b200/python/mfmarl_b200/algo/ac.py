@@ -175,6 +175,10 @@ class _ActorCriticBase:
             return eager()
         key = (view.data_ptr(), feature.data_ptr(), tuple(view.shape), tuple(feature.shape))
         hit = self._act_graphs.get(key)
+        if hit is None and len(self._act_graphs) >= 4:
+            # the caller does not hand in the same buffers again (a graph per call would cost more than it saves)
+            self._act_graph_ok, self._act_graphs = False, {}
+            return eager()
         if hit is None:
             try:
                 side = torch.cuda.Stream(device=view.device)
