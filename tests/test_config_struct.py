@@ -41,3 +41,39 @@ def test_integration_stub_matches_the_header():
     stub = text[text.index("class _Cfg(ctypes.Structure)"):text.index("def make(")]
     names = re.findall(r'"(\w+)"', stub)
     assert names == [n for n, _, _ in header_fields()]
+
+
+def header_prototypes():
+    """{name: [parameter type strings]} of every `int mfb_*(...)` prototype in include/mfmarl_batched.h"""
+    text = open(os.path.join(ROOT, "include", "mfmarl_batched.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\bint\s+(mf[bi]_\w+)\s*\(([^)]*)\)\s*;", text):
+        params = [p.strip() for p in m.group(2).split(",")] if m.group(2).strip() not in ("", "void") else []
+        protos[m.group(1)] = params
+    return protos
+
+
+def test_package_argtypes_match_the_header_prototypes():
+    """every function the package binds: same number of arguments as the header, pointers where the header has
+    pointers, and the scalar kinds of the header"""
+    import ctypes
+    from mfmarl_b200.lib import load_library
+    lib = load_library()
+    protos = header_prototypes()
+    assert len(protos) >= 20 and "mfb_step" in protos and "mfi_run" in protos
+    scalar = {"int": ctypes.c_int, "unsigned": ctypes.c_uint, "unsigned long": ctypes.c_ulong, "double": ctypes.c_double}
+    checked = 0
+    for name, params in protos.items():
+        fn = getattr(lib, name)                       # (also: every prototype is exported)
+        if fn.argtypes is None:
+            continue                                  # bound elsewhere (mfi_* in ising.py, on a GPU box)
+        assert len(fn.argtypes) == len(params), (name, len(fn.argtypes), params)
+        for at, p in zip(fn.argtypes, params):
+            if "*" in p:
+                assert at in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(at, "contents") or issubclass(at, ctypes._Pointer), (name, p)
+            else:
+                kind = " ".join(p.split()[:-1])
+                assert at is scalar[kind], (name, p, at)
+        checked += 1
+    assert checked >= 18
